@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""Benchmark of the torchext op path on B200 (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this framework (libctd_b200.so)
+    python bench.py --impl reference [...]                          # the reference's CPU path, host cores
+    torchrun --nproc-per-node N ... bench.py --gpus N ...           # one rank per GPU, weak scaling
+
+A "step" is one pass of the hot path over one batch of synthetic 480x640 dot-pattern pairs
+(SURVEY.md section 8d data), batch 8 per GPU:
+    LCN(5, 0.05) forward  ->  PhotometricLoss 'sad' ("l1") forward + backward
+                          ->  PhotometricLoss 'census_sad' (the reference's structural mode, standing in
+                              for "ssim") forward + backward
+                          ->  the caller's masked loss reduction (networks.py:377), twice
+and, for N > 1, one packed NCCL all-reduce of the four loss scalars.  value = pixels per second through
+that whole chain (N * B * H * W / step time); per-op figures are in "ops".
+
+Timing: CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks;
+inputs AND outputs rotate over NSETS buffer sets whose footprint exceeds L2, so every step streams
+from HBM.  roofline: per-kernel CUDA-event durations measured inside the same timed steps;
+algorithmic bytes per pixel from SURVEY.md section 8d; peak from MEASURED_PEAKS.json.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "oracle")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+H, W, B_PER_GPU, BS, EPS, LCN_R, LCN_EPS = 480, 640, 8, 9, 0.5, 5, 0.05
+NSETS = 4
+METRIC = "Mpix/s through LCN fwd + PhotometricLoss sad fwd+bwd + census_sad fwd+bwd (batch 8, 480x640); per-op Mpix/s in ops"
+WORKLOAD = ("configs[1]: LCN(5,0.05) fwd + PhotometricLoss l1(sad) fwd+bwd + census_sad (stands in for ssim) fwd+bwd "
+            "+ masked loss sums, batch 8 per GPU, 480x640, block 9, eps 0.5, C=1")
+# algorithmic bytes per pixel, fp32, C=1
+BYTES_PER_PX = {"lcn_fwd": 12, "sad_fwd": 12, "sad_bwd": 16, "census_sad_fwd": 12, "census_sad_bwd": 16,
+                "masked_sums": 8}
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU implementations (test infrastructure, used ONLY as the reported baseline / reference arm)
+# ------------------------------------------------------------------------------------------------
+def _cpu_chain_factory():
+    """Returns (run(images: dict of [n,1,H,W] arrays) -> None, kind).  kind 'reference' = the unmodified
+    reference extension compiled into oracle/_ref (photometric ops) + the reference's torch LCN recipe on
+    CPU; 'port' = the plain-C oracle."""
+    import oracle
+    ref = None
+    try:
+        import build_ref
+        ref = build_ref.load_ref()
+    except Exception:
+        ref = None
+    if ref is not None:
+        import torch
+        torch.set_num_threads(1)
+
+        def lcn_torch(x):  # model/networks.py:523-533 restated with the same torch ops
+            k = 2 * LCN_R + 1
+            w = torch.ones(1, 1, k, k)
+            pad = torch.nn.functional.pad(x, (LCN_R,) * 4, mode="reflect")
+            box = torch.nn.functional.conv2d(pad, w)
+            box2 = torch.nn.functional.conv2d(pad * pad, w)
+            avg = box / k ** 2
+            std = torch.sqrt(box2 / k ** 2 - avg ** 2 + 1e-6) + LCN_EPS
+            return (x - avg) / std, std
+
+        def run(d):
+            t = {k: torch.from_numpy(v) for k, v in d.items()}
+            lcn_torch(t["im"])
+            for ty in (1, 3):
+                ref.photometric_loss_forward(t["es"], t["ta"], BS, ty, EPS)
+                ref.photometric_loss_backward(t["es"], t["ta"], t["go"], BS, ty, EPS)
+        return run, "reference"
+
+    def run(d):
+        oracle.lcn(d["im"], LCN_R, LCN_EPS)
+        for ty in (1, 3):
+            oracle.photometric_loss_forward(d["es"], d["ta"], BS, ty, EPS)
+            oracle.photometric_loss_backward(d["es"], d["ta"], d["go"], BS, ty, EPS)
+    return run, "port"
+
+
+_POOL_RUN = None
+
+
+def _pool_init():
+    global _POOL_RUN
+    _POOL_RUN = _cpu_chain_factory()[0]
+
+
+def _pool_task(d):
+    t0 = time.perf_counter()
+    _POOL_RUN(d)
+    return time.perf_counter() - t0
+
+
+def run_reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the path on this box's host cores (all of them: one
+    image per worker process, because the reference's loop is serial, ext_cpu.cpp:7-12)."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from connecting_the_dots_b200 import synth
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    kind = _cpu_chain_factory()[1]
+    batch = synth.make_batch(min(cores, 8), H, W)
+    images = [{k: np.ascontiguousarray(batch[k][i % batch["im"].shape[0]:i % batch["im"].shape[0] + 1]) for k in ("im", "es", "ta", "go")}
+              for i in range(cores)]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores, initializer=_pool_init) as pool:
+        for _ in range(args.warmup):
+            pool.map(_pool_task, images[:cores])
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            pool.map(_pool_task, images)
+        dt = time.perf_counter() - t0
+    ms = dt / args.steps * 1e3
+    value = cores * H * W / (ms * 1e-3) / 1e6
+    sample = "%d images of 480x640 per step (one per worker process), full chain LCN + sad f+b + census_sad f+b" % cores
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpix/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "CPU arm: each step is a bounded sample of the workload"},
+            "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_leg(n_images=4):
+    """Single-threaded reference CPU path on a bounded sample (the reference's own figure is 1 core)."""
+    from connecting_the_dots_b200 import synth
+    run, kind = _cpu_chain_factory()
+    batch = synth.make_batch(n_images, H, W)
+    d = {k: batch[k] for k in ("im", "es", "ta", "go")}
+    one = {k: v[:1] for k, v in d.items()}
+    run(one)  # warm-up (page in the library)
+    t0 = time.perf_counter()
+    run(d)
+    dt = time.perf_counter() - t0
+    return {"value": n_images * H * W / dt / 1e6, "unit": "Mpix/s", "cores": 1, "kind": kind,
+            "sample": "%d images of 480x640, full chain LCN + sad f+b + census_sad f+b, one pass, %.1f s" % (n_images, dt)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------
+def run_b200_arm(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import connecting_the_dots_b200 as ctd
+    from connecting_the_dots_b200 import _lib, synth
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    B = B_PER_GPU
+    npx = B * H * W
+
+    # ---- inputs: NSETS distinct device-resident sets (and pinned host copies for the e2e leg)
+    base = synth.make_batch(B, H, W)
+    sets, host_sets = [], []
+    for s in range(NSETS):
+        arrs = {k: np.ascontiguousarray(np.roll(base[k], 3 * s + rank, axis=2)) for k in ("im", "es", "ta", "go")}
+        host = {k: torch.from_numpy(v).pin_memory() for k, v in arrs.items()}
+        for k in ("lcn", "std", "out_sad", "gi_sad", "out_cs", "gi_cs"):
+            host[k] = torch.empty(B, 1, H, W).pin_memory()
+        host_sets.append(host)
+        d = {k: host[k].to(dev) for k in ("im", "es", "ta", "go")}
+        for k in ("lcn", "std", "out_sad", "gi_sad", "out_cs", "gi_cs"):
+            d[k] = torch.empty(B, 1, H, W, device=dev)
+        d["sums"] = torch.zeros(2, 2, device=dev)
+        sets.append(d)
+    ws = torch.zeros(int(L.ctd_masked_sums_workspace_bytes()), dtype=torch.uint8, device=dev)
+    footprint_mb = NSETS * 10 * npx * 4 / 1e6
+    stream = torch.cuda.current_stream(dev)
+    st = stream.cuda_stream
+    OPS = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums")
+
+    def step(k, ev=None):
+        d = sets[k % NSETS]
+        p = {n: t.data_ptr() for n, t in d.items()}
+        mark = (lambda i: ev[i].record(stream)) if ev is not None else (lambda i: None)
+        mark(0)
+        _lib.call("ctd_lcn_f32", p["im"], p["lcn"], p["std"], B, H, W, LCN_R, LCN_EPS, st)
+        mark(1)
+        _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_sad"], B, 1, H, W, BS, 1, EPS, st)
+        mark(2)
+        _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_sad"], B, 1, H, W, BS, 1, EPS, st)
+        mark(3)
+        _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_cs"], B, 1, H, W, BS, 3, EPS, st)
+        mark(4)
+        _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_cs"], B, 1, H, W, BS, 3, EPS, st)
+        mark(5)
+        _lib.call("ctd_masked_sums_f32", p["out_sad"], p["std"], npx, p["sums"], ws.data_ptr(), st)
+        _lib.call("ctd_masked_sums_f32", p["out_cs"], p["std"], npx, p["sums"] + 8, ws.data_ptr(), st)
+        mark(6)
+        if world > 1:
+            dist.all_reduce(d["sums"])  # 4 floats: the only inter-GPU traffic of the path
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    sync_all()
+    launches0 = _lib.launch_count()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sync_all()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(k, evs[k])
+    e1.record(stream)
+    sync_all()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = _lib.launch_count() - launches0
+    total_ms = e0.elapsed_time(e1)
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    op_ms = {n: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)])) for i, n in enumerate(OPS)}
+    op_ms["masked_sums"] /= 2  # two launches in that interval
+
+    # ---- e2e leg: the C ABI's host-buffer entry points, pinned host inputs/outputs, copies timed
+    P = lambda t_: ctypes.c_void_p(t_.data_ptr())
+
+    def e2e_step(k):
+        h = host_sets[k % NSETS]
+        _lib.call("ctd_host_lcn_f32", P(h["im"]), P(h["lcn"]), P(h["std"]), B, H, W, LCN_R, LCN_EPS)
+        _lib.call("ctd_host_photometric_fwd_bwd_f32", P(h["es"]), P(h["ta"]), P(h["go"]), P(h["out_sad"]), P(h["gi_sad"]),
+                  B, 1, H, W, BS, 1, EPS)
+        _lib.call("ctd_host_photometric_fwd_bwd_f32", P(h["es"]), P(h["ta"]), P(h["go"]), P(h["out_cs"]), P(h["gi_cs"]),
+                  B, 1, H, W, BS, 3, EPS)
+
+    e2e_steps = max(3, min(args.steps, 20))
+    for k in range(3):
+        e2e_step(k)
+    sync_all()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)  # each call returns when its results are in host memory
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / e2e_steps * 1e3
+    h2d = (1 + 3 + 3) * npx * 4
+    d2h = (2 + 2 + 2) * npx * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = measured_peak()
+    ops = {}
+    for n in OPS:
+        gbs = BYTES_PER_PX[n] * npx / (op_ms[n] * 1e-3) / 1e9
+        ops[n] = {"ms": op_ms[n], "mpix_s": npx / (op_ms[n] * 1e-3) / 1e6, "algo_bytes_per_px": BYTES_PER_PX[n],
+                  "achieved_gbs": gbs, "frac_hbm": gbs / peak}
+    fb = {"sad_fwd_bwd": op_ms["sad_fwd"] + op_ms["sad_bwd"], "census_sad_fwd_bwd": op_ms["census_sad_fwd"] + op_ms["census_sad_bwd"]}
+    for n, ms in fb.items():
+        gbs = 28 * npx / (ms * 1e-3) / 1e9
+        ops[n] = {"ms": ms, "mpix_s": npx / (ms * 1e-3) / 1e6, "algo_bytes_per_px": 28, "achieved_gbs": gbs, "frac_hbm": gbs / peak}
+    dom = max(OPS[:5], key=lambda n: op_ms[n])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": ops[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                "frac": ops[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                "algo_bytes_per_launch": BYTES_PER_PX[dom] * npx, "ms_per_launch": op_ms[dom],
+                "share_of_step": op_ms[dom] / sum(op_ms[n] * (2 if n == "masked_sums" else 1) for n in OPS)}
+    line = {"metric": METRIC, "value": world * npx / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "height": H, "width": W,
+                       "l2_policy": "inputs and outputs rotate over %d buffer sets, %.0f MB touched > 126 MB L2" % (NSETS, footprint_mb),
+                       "parallelism": "batch-sharded x%d, one packed 4-float NCCL all-reduce per step" % world},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": world * npx / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+                    "api": "ctd_host_lcn_f32 + 2x ctd_host_photometric_fwd_bwd_f32, pinned host buffers"},
+            "roofline": roofline, "ops": ops}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_leg()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200_arm(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,234 @@
+// Host-buffer entry points of libctd_b200 (ctd_host_*): what a CPU-side caller -- the reference's
+// ext_cpu.cpp entry points (torchext/ext/ext_cpu.cpp:14-184) -- binds to.  Inputs and outputs are
+// host memory (pinned memory makes the copies asynchronous DMA); each call stages through a
+// per-thread, grow-only device workspace on the current device, runs the same kernels as the
+// device-pointer API on a private stream, copies the results back and returns once they are in host
+// memory.  There is no CPU compute path: without a CUDA device these calls fail with CTD_ERR_CUDA.
+#include <vector>
+
+#include "ctd_common.cuh"
+
+namespace ctd {
+
+struct Workspace {
+  int device = -1;
+  char* base = nullptr;
+  size_t cap = 0;
+  cudaStream_t stream = nullptr;
+
+  int ensure(size_t bytes) {
+    int dev = 0;
+    CTD_CUDA(cudaGetDevice(&dev));
+    if (dev != device) {
+      release();
+      device = dev;
+    }
+    if (!stream) CTD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (bytes > cap) {
+      if (base) {
+        CTD_CUDA(cudaStreamSynchronize(stream));
+        cudaFree(base);
+        base = nullptr;
+        cap = 0;
+      }
+      const size_t want = bytes + bytes / 8 + (1 << 20);
+      if (cudaMalloc(&base, want) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(CTD_ERR_NOMEM, "host api: cannot allocate %zu bytes of device workspace", want);
+      }
+      cap = want;
+    }
+    return CTD_OK;
+  }
+  void release() {
+    if (stream) {
+      cudaStreamSynchronize(stream);
+      cudaStreamDestroy(stream);
+    }
+    if (base) cudaFree(base);
+    base = nullptr;
+    cap = 0;
+    stream = nullptr;
+    device = -1;
+  }
+  ~Workspace() {}  // process teardown: the driver reclaims everything; do not touch CUDA here
+};
+
+static thread_local Workspace g_ws;
+
+// carve 256-byte aligned sub-buffers out of the workspace
+struct Carver {
+  std::vector<size_t> sizes;
+  size_t total = 0;
+  size_t add(size_t bytes) {
+    const size_t off = total;
+    total += (bytes + 255) & ~size_t(255);
+    return off;
+  }
+};
+
+}  // namespace ctd
+
+using namespace ctd;
+
+#define H2D(dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, g_ws.stream))
+#define D2H(dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, g_ws.stream))
+#define RUN(call)                    \
+  do {                               \
+    if (int rc__ = (call)) return rc__; \
+  } while (0)
+
+static int photometric_host(const float* es, const float* ta, const float* go, float* out, float* gi, int64_t B,
+                            int64_t C, int64_t H, int64_t W, int bs, int type, float eps) {
+  CTD_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, "photometric: negative size");
+  const size_t nin = (size_t)(B * C * H * W) * sizeof(float), nout = (size_t)(B * H * W) * sizeof(float);
+  Carver cv;
+  const size_t o_es = cv.add(nin), o_ta = cv.add(nin), o_go = cv.add(go ? nout : 0), o_out = cv.add(out ? nout : 0),
+               o_gi = cv.add(gi ? nin : 0);
+  RUN(g_ws.ensure(cv.total));
+  char* b = g_ws.base;
+  if (nin) {
+    CTD_REQUIRE(es && ta, "photometric: null pointer");
+    H2D(b + o_es, es, nin);
+    H2D(b + o_ta, ta, nin);
+  }
+  if (out) {
+    RUN(ctd_photometric_fwd_f32((float*)(b + o_es), (float*)(b + o_ta), (float*)(b + o_out), B, C, H, W, bs, type, eps,
+                                g_ws.stream));
+    if (nout) D2H(out, b + o_out, nout);
+  }
+  if (gi) {
+    CTD_REQUIRE(go || !nout, "photometric_bwd: null grad_out");
+    if (nout) H2D(b + o_go, go, nout);
+    RUN(ctd_photometric_bwd_f32((float*)(b + o_es), (float*)(b + o_ta), (float*)(b + o_go), (float*)(b + o_gi), B, C, H,
+                                W, bs, type, eps, g_ws.stream));
+    if (nin) D2H(gi, b + o_gi, nin);
+  }
+  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
+  return CTD_OK;
+}
+
+CTD_API int ctd_host_photometric_fwd_f32(const float* es, const float* ta, float* out, int64_t B, int64_t C,
+                                            int64_t H, int64_t W, int bs, int type, float eps) {
+  CTD_REQUIRE(out || B * H * W == 0, "photometric_fwd: null output");
+  return photometric_host(es, ta, nullptr, out, nullptr, B, C, H, W, bs, type, eps);
+}
+CTD_API int ctd_host_photometric_bwd_f32(const float* es, const float* ta, const float* go, float* gi, int64_t B,
+                                            int64_t C, int64_t H, int64_t W, int bs, int type, float eps) {
+  CTD_REQUIRE(gi || B * C * H * W == 0, "photometric_bwd: null output");
+  return photometric_host(es, ta, go, nullptr, gi, B, C, H, W, bs, type, eps);
+}
+CTD_API int ctd_host_photometric_fwd_bwd_f32(const float* es, const float* ta, const float* go, float* out,
+                                                float* gi, int64_t B, int64_t C, int64_t H, int64_t W, int bs,
+                                                int type, float eps) {
+  CTD_REQUIRE((out && gi) || B * C * H * W == 0, "photometric_fwd_bwd: null output");
+  return photometric_host(es, ta, go, out, gi, B, C, H, W, bs, type, eps);
+}
+
+CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,
+                                     int64_t W, int64_t D, int bs) {
+  CTD_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0 && D >= 0, "xcorrvol: negative size");
+  const size_t nin = (size_t)(B * C * H * W) * sizeof(float), nout = (size_t)(B * D * H * W) * sizeof(float);
+  Carver cv;
+  const size_t o0 = cv.add(nin), o1 = cv.add(nin), oo = cv.add(nout);
+  RUN(g_ws.ensure(cv.total));
+  char* b = g_ws.base;
+  if (nin) {
+    CTD_REQUIRE(in0 && in1, "xcorrvol: null pointer");
+    H2D(b + o0, in0, nin);
+    H2D(b + o1, in1, nin);
+  }
+  RUN(ctd_xcorrvol_f32((float*)(b + o0), (float*)(b + o1), (float*)(b + oo), B, C, H, W, D, bs, g_ws.stream));
+  if (nout) {
+    CTD_REQUIRE(out, "xcorrvol: null output");
+    D2H(out, b + oo, nout);
+  }
+  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
+  return CTD_OK;
+}
+
+CTD_API int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const float* K, int64_t* out, int64_t B,
+                                    int64_t H, int64_t W, int ps) {
+  CTD_REQUIRE(B >= 0 && H >= 0 && W >= 0, "proj_nn: negative size");
+  const size_t npt = (size_t)(B * H * W) * 3 * sizeof(float), nout = (size_t)(B * H * W) * sizeof(int64_t);
+  Carver cv;
+  const size_t o0 = cv.add(npt), o1 = cv.add(npt), ok = cv.add(9 * sizeof(float)), oo = cv.add(nout);
+  RUN(g_ws.ensure(cv.total));
+  char* b = g_ws.base;
+  if (nout) {
+    CTD_REQUIRE(xyz0 && xyz1 && K && out, "proj_nn: null pointer");
+    H2D(b + o0, xyz0, npt);
+    H2D(b + o1, xyz1, npt);
+    H2D(b + ok, K, 9 * sizeof(float));
+  }
+  RUN(ctd_proj_nn_f32((float*)(b + o0), (float*)(b + o1), (float*)(b + ok), (int64_t*)(b + oo), B, H, W, ps,
+                      g_ws.stream));
+  if (nout) D2H(out, b + oo, nout);
+  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
+  return CTD_OK;
+}
+
+CTD_API int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, int64_t N0, int64_t N1) {
+  CTD_REQUIRE(N0 >= 0 && N1 >= 0, "nn: negative size");
+  const size_t n0 = (size_t)N0 * 3 * sizeof(float), n1 = (size_t)N1 * 3 * sizeof(float), no = (size_t)N0 * sizeof(int64_t);
+  Carver cv;
+  const size_t o0 = cv.add(n0), o1 = cv.add(n1), oo = cv.add(no);
+  RUN(g_ws.ensure(cv.total));
+  char* b = g_ws.base;
+  if (n0) {
+    CTD_REQUIRE(in0 && out, "nn: null pointer");
+    H2D(b + o0, in0, n0);
+  }
+  if (n1) {
+    CTD_REQUIRE(in1, "nn: null pointer");
+    H2D(b + o1, in1, n1);
+  }
+  RUN(ctd_nn_f32((float*)(b + o0), (float*)(b + o1), (int64_t*)(b + oo), N0, N1, g_ws.stream));
+  if (no) D2H(out, b + oo, no);
+  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
+  return CTD_OK;
+}
+
+CTD_API int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t N0, int64_t N1) {
+  CTD_REQUIRE(N0 >= 0 && N1 >= 0, "crosscheck: negative size");
+  const size_t n0 = (size_t)N0 * sizeof(int64_t), n1 = (size_t)N1 * sizeof(int64_t), no = (size_t)N0;
+  Carver cv;
+  const size_t o0 = cv.add(n0), o1 = cv.add(n1), oo = cv.add(no);
+  RUN(g_ws.ensure(cv.total));
+  char* b = g_ws.base;
+  if (n0) {
+    CTD_REQUIRE(in0 && out, "crosscheck: null pointer");
+    H2D(b + o0, in0, n0);
+  }
+  if (n1) {
+    CTD_REQUIRE(in1, "crosscheck: null pointer");
+    H2D(b + o1, in1, n1);
+  }
+  RUN(ctd_crosscheck((int64_t*)(b + o0), (int64_t*)(b + o1), (uint8_t*)(b + oo), N0, N1, g_ws.stream));
+  if (no) D2H(out, b + oo, no);
+  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
+  return CTD_OK;
+}
+
+CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, int64_t H, int64_t W, int r,
+                                float eps) {
+  CTD_REQUIRE(N >= 0 && H >= 0 && W >= 0, "lcn: negative size");
+  const size_t n = (size_t)(N * H * W) * sizeof(float);
+  Carver cv;
+  const size_t ox = cv.add(n), ol = cv.add(n), os = cv.add(n);
+  RUN(g_ws.ensure(cv.total));
+  char* b = g_ws.base;
+  if (n) {
+    CTD_REQUIRE(x && lcn && sd, "lcn: null pointer");
+    H2D(b + ox, x, n);
+  }
+  RUN(ctd_lcn_f32((float*)(b + ox), (float*)(b + ol), (float*)(b + os), N, H, W, r, eps, g_ws.stream));
+  if (n) {
+    D2H(lcn, b + ol, n);
+    D2H(sd, b + os, n);
+  }
+  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
+  return CTD_OK;
+}
+
+CTD_API void ctd_host_release(void) { g_ws.release(); }

@@ -1,0 +1,691 @@
+// PhotometricLoss forward / backward for sm_100a.
+//
+// Reference semantics: torchext/ext/ext.h:201-266 (forward) and :268-344 (backward), bound at
+// torchext/ext/ext_cuda.cpp:92-123.  Nothing here is a translation of those functors: the
+// reference runs one thread per output pixel that walks bs*bs taps in global memory and, in the
+// backward, scatters with atomicAdd.  Here
+//   * mse/sad forward is a separable replicate-clamped box filter of phi(es-ta) on a shared-memory
+//     tile, 128-bit loads/stores;
+//   * mse/sad backward is the adjoint box filter of grad_out (zero padded, border rows/columns
+//     re-weighted by the clamp multiplicity) times phi'(es-ta): a gather, no atomics, no memset;
+//   * census forward/backward are gathers over a shared-memory halo tile with four pixels per
+//     thread so every tap row is fetched with three 128-bit shared loads; the backward uses the
+//     antisymmetry of the soft census step to fold the "tap" and "centre" roles of a pixel pair
+//     into one term, and keeps sign() decisions bit-identical to the reference by recomputing
+//     near-ties with IEEE operations;
+//   * every other case (block size != 9, fp64, tiny images) runs generic gather kernels that
+//     follow the reference's operation order (this file is compiled with -fmad=false for them).
+#include <algorithm>
+
+#include "ctd_common.cuh"
+
+namespace ctd {
+
+extern int g_force_generic;
+
+// ------------------------------------------------------------------------------------------
+// generic kernels (any block size, channel count, size; float or double)
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T soft_step(T x, T eps) {  // ext.h:245-246
+  T q = x / sqrt(x * x + eps);
+  return T(0.5) * (T(1) + q);
+}
+
+template <typename T>
+__device__ __forceinline__ T sgn(T d) {
+  return d < T(0) ? T(-1) : (d > T(0) ? T(1) : T(0));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+photo_fwd_generic(const T* __restrict__ es, const T* __restrict__ ta, T* __restrict__ out, int64_t B,
+                  int C, int H, int W, int bs, int type, T eps) {
+  const int64_t total = B * H * W;
+  const int bs2 = bs * bs, half = bs / 2;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int w = idx % W, h = (idx / W) % H;
+    const int64_t n = idx / ((int64_t)W * H);
+    T acc = 0;
+    for (int t = 0; t < bs2; ++t) {
+      const int hh = clampi(h + t / bs - half, 0, H - 1);
+      const int ww = clampi(w + t % bs - half, 0, W - 1);
+      for (int c = 0; c < C; ++c) {
+        const int64_t base = (n * C + c) * H;
+        const int64_t tap = (base + hh) * W + ww;
+        T d;
+        if (type <= 1) {
+          d = es[tap] - ta[tap];
+        } else {
+          const int64_t ctr = (base + h) * W + w;
+          d = soft_step(es[tap] - es[ctr], eps) - soft_step(ta[tap] - ta[ctr], eps);
+        }
+        acc += ((type & 1) ? fabs(d) : d * d) / T(bs2);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// number of window offsets delta in [-lo, hi] with clamp(p + delta, 0, n-1) == i
+__device__ __forceinline__ int clamp_mult(int p, int i, int n, int lo, int hi) {
+  int m = 0;
+  for (int d = -lo; d <= hi; ++d) m += (clampi(p + d, 0, n - 1) == i);
+  return m;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+photo_bwd_generic(const T* __restrict__ es, const T* __restrict__ ta, const T* __restrict__ go,
+                  T* __restrict__ gi, int64_t B, int C, int H, int W, int bs, int type, T eps) {
+  const int64_t total = B * C * H * W;
+  const int lo = bs / 2, hi = bs - 1 - lo;
+  const T inv_n = T(bs * bs);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int x = idx % W, y = (idx / W) % H;
+    const int64_t nc = idx / ((int64_t)W * H);
+    const int64_t n = nc / C;
+    const T* esp = es + nc * H * W;
+    const T* tap = ta + nc * H * W;
+    const T* gop = go + n * H * W;
+    const T ei = esp[(int64_t)y * W + x], ti = tap[(int64_t)y * W + x];
+    T acc = 0;
+    // role 1: pixel i is the (clamped) tap of centre p
+    for (int py = max(0, y - hi); py <= min(H - 1, y + lo); ++py) {
+      const int my = clamp_mult(py, y, H, lo, hi);
+      if (!my) continue;
+      for (int px = max(0, x - hi); px <= min(W - 1, x + lo); ++px) {
+        const int mx = clamp_mult(px, x, W, lo, hi);
+        if (!mx) continue;
+        const T g0 = gop[(int64_t)py * W + px];
+        T g;
+        if (type <= 1) {
+          const T d = ei - ti;
+          g = ((type & 1) ? sgn(d) : T(2) * d) / inv_n * g0;
+        } else {
+          const T des = ei - esp[(int64_t)py * W + px];
+          const T dta = ti - tap[(int64_t)py * W + px];
+          const T d = soft_step(des, eps) - soft_step(dta, eps);
+          const T gl = ((type & 1) ? sgn(d) : T(2) * d) / inv_n;
+          const T s = des * des + eps;
+          const T gh = T(0.5) * eps / sqrt(s * s * s);
+          g = g0 * gl * gh;
+        }
+        acc += T(my * mx) * g;
+      }
+    }
+    // role 2 (census only): pixel i is the centre; every tap sends -g back to it
+    if (type >= 2) {
+      const T g0 = gop[(int64_t)y * W + x];
+      for (int t = 0; t < bs * bs; ++t) {
+        const int hh = clampi(y + t / bs - lo, 0, H - 1);
+        const int ww = clampi(x + t % bs - lo, 0, W - 1);
+        const T des = esp[(int64_t)hh * W + ww] - ei;
+        const T dta = tap[(int64_t)hh * W + ww] - ti;
+        const T d = soft_step(des, eps) - soft_step(dta, eps);
+        const T gl = ((type & 1) ? sgn(d) : T(2) * d) / inv_n;
+        const T s = des * des + eps;
+        const T gh = T(0.5) * eps / sqrt(s * s * s);
+        acc -= g0 * gl * gh;
+      }
+    }
+    gi[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fast path, block size 9, fp32: mse / sad
+// ------------------------------------------------------------------------------------------
+constexpr int R9 = 4;                 // window radius of block size 9
+constexpr int BT_W = 128, BT_H = 32;  // output tile of the box-filter kernels
+constexpr int BE_W = BT_W + 2 * R9;   // 136
+constexpr int BE_H = BT_H + 2 * R9;   // 40
+constexpr float INV81 = 1.0f / 81.0f;
+
+// four horizontally adjacent 9-sums from 12 consecutive values a|b|c
+__device__ __forceinline__ float4 hsum9x4(const float4 a, const float4 b, const float4 c) {
+  const float mid = ((a.w + b.x) + (b.y + b.z)) + (b.w + c.x);  // columns 3..8, shared by all four
+  const float l12 = a.y + a.z, r910 = c.y + c.z;
+  float4 o;
+  o.x = mid + (a.x + l12);
+  o.y = mid + (l12 + c.y);
+  o.z = mid + (a.z + r910);
+  o.w = mid + (r910 + c.w);
+  return o;
+}
+__device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
+  return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+}
+__device__ __forceinline__ float4 fma4s(const float s, const float4 a, const float4 b) {
+  return make_float4(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y), fmaf(s, a.z, b.z), fmaf(s, a.w, b.w));
+}
+
+template <int TYPE>
+__device__ __forceinline__ float phi(float d) {
+  return TYPE == 0 ? d * d : fabsf(d);
+}
+
+// out = box9(phi(es - ta)) / 81 with replicate-clamped borders, summed over channels.
+template <int TYPE>
+__global__ void __launch_bounds__(256)
+photo_fwd_box9(const float* __restrict__ es, const float* __restrict__ ta, float* __restrict__ out,
+               int C, int H, int W, int vec) {
+  __shared__ __align__(16) float E[BE_H][BE_W];
+  __shared__ __align__(16) float Hs[BE_H][BT_W];
+  const int x0 = blockIdx.x * BT_W, y0 = blockIdx.y * BT_H;
+  const int64_t n = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int64_t plane = (int64_t)H * W;
+  const float* esn = es + n * C * plane;
+  const float* tan = ta + n * C * plane;
+
+  for (int ch = tid; ch < BE_H * (BE_W / 4); ch += 256) {
+    const int r = ch / (BE_W / 4), k = ch % (BE_W / 4);
+    const int gy = clampi(y0 - R9 + r, 0, H - 1);
+    const int gx = x0 - R9 + 4 * k;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (vec && gx >= 0 && gx + 3 < W) {
+      const int64_t off = (int64_t)gy * W + gx;
+      for (int c = 0; c < C; ++c) {
+        const float4 a = ldg4(esn + c * plane + off), b = ldg4(tan + c * plane + off);
+        acc.x += phi<TYPE>(a.x - b.x);
+        acc.y += phi<TYPE>(a.y - b.y);
+        acc.z += phi<TYPE>(a.z - b.z);
+        acc.w += phi<TYPE>(a.w - b.w);
+      }
+    } else {
+      float v[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t off = (int64_t)gy * W + clampi(gx + j, 0, W - 1);
+        float s = 0.f;
+        for (int c = 0; c < C; ++c) s += phi<TYPE>(__ldg(esn + c * plane + off) - __ldg(tan + c * plane + off));
+        v[j] = s;
+      }
+      acc = make_float4(v[0], v[1], v[2], v[3]);
+    }
+    *reinterpret_cast<float4*>(&E[r][4 * k]) = acc;
+  }
+  __syncthreads();
+  for (int it = tid; it < BE_H * (BT_W / 4); it += 256) {
+    const int r = it / (BT_W / 4), q = it % (BT_W / 4);
+    const float4* p = reinterpret_cast<const float4*>(&E[r][4 * q]);
+    *reinterpret_cast<float4*>(&Hs[r][4 * q]) = hsum9x4(p[0], p[1], p[2]);
+  }
+  __syncthreads();
+  {
+    const int q = tid % 32, rs = tid / 32;  // 4 columns x 4 rows per thread
+    float4 v[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v[j] = *reinterpret_cast<const float4*>(&Hs[rs * 4 + j][4 * q]);
+    const float4 mid = add4(add4(add4(v[3], v[4]), add4(v[5], v[6])), add4(v[7], v[8]));
+    const float4 l12 = add4(v[1], v[2]), r910 = add4(v[9], v[10]);
+    float4 o[4];
+    o[0] = add4(mid, add4(v[0], l12));
+    o[1] = add4(mid, add4(l12, v[9]));
+    o[2] = add4(mid, add4(v[2], r910));
+    o[3] = add4(mid, add4(r910, v[11]));
+    const int gx = x0 + 4 * q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gy = y0 + rs * 4 + j;
+      if (gy >= H) continue;
+      float* dst = out + n * plane + (int64_t)gy * W + gx;
+      const float4 r = make_float4(o[j].x * INV81, o[j].y * INV81, o[j].z * INV81, o[j].w * INV81);
+      if (vec) {
+        if (gx < W) *reinterpret_cast<float4*>(dst) = r;
+      } else {
+        if (gx + 0 < W) dst[0] = r.x;
+        if (gx + 1 < W) dst[1] = r.y;
+        if (gx + 2 < W) dst[2] = r.z;
+        if (gx + 3 < W) dst[3] = r.w;
+      }
+    }
+  }
+}
+
+// grad_in[c] = phi'(es[c]-ta[c]) / 81 * S(grad_out), S = adjoint of the replicate-clamped 9x9 box:
+// a zero-padded box sum whose first/last row and column collect the extra clamp multiplicity
+// (weights 5,4,3,2,1 over the five pixels nearest the border instead of 1,1,1,1,1).
+template <int TYPE>
+__global__ void __launch_bounds__(256)
+photo_bwd_box9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
+               float* __restrict__ gi, int C, int H, int W, int vec) {
+  __shared__ __align__(16) float G[BE_H][BE_W];
+  __shared__ __align__(16) float Hs[BE_H][BT_W];
+  const int x0 = blockIdx.x * BT_W, y0 = blockIdx.y * BT_H;
+  const int64_t n = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int64_t plane = (int64_t)H * W;
+  const float* gon = go + n * plane;
+
+  for (int ch = tid; ch < BE_H * (BE_W / 4); ch += 256) {
+    const int r = ch / (BE_W / 4), k = ch % (BE_W / 4);
+    const int gy = y0 - R9 + r, gx = x0 - R9 + 4 * k;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gy >= 0 && gy < H) {
+      if (vec && gx >= 0 && gx + 3 < W) {
+        v = ldg4(gon + (int64_t)gy * W + gx);
+      } else {
+        if (gx + 0 >= 0 && gx + 0 < W) v.x = __ldg(gon + (int64_t)gy * W + gx + 0);
+        if (gx + 1 >= 0 && gx + 1 < W) v.y = __ldg(gon + (int64_t)gy * W + gx + 1);
+        if (gx + 2 >= 0 && gx + 2 < W) v.z = __ldg(gon + (int64_t)gy * W + gx + 2);
+        if (gx + 3 >= 0 && gx + 3 < W) v.w = __ldg(gon + (int64_t)gy * W + gx + 3);
+      }
+    }
+    *reinterpret_cast<float4*>(&G[r][4 * k]) = v;
+  }
+  __syncthreads();
+  const int xr = W - 1 - x0;  // tile-local column of the last image column
+  for (int it = tid; it < BE_H * (BT_W / 4); it += 256) {
+    const int r = it / (BT_W / 4), q = it % (BT_W / 4);
+    const float4* p = reinterpret_cast<const float4*>(&G[r][4 * q]);
+    const float4 a = p[0], b = p[1], c = p[2];
+    float4 o = hsum9x4(a, b, c);
+    if (x0 == 0 && q == 0) o.x += 4.f * b.x + 3.f * b.y + 2.f * b.z + b.w;
+    if (xr >= 0 && xr < BT_W && q == xr / 4) {
+      const float* g = &G[r][xr + R9];
+      const float extra = 4.f * g[0] + 3.f * g[-1] + 2.f * g[-2] + g[-3];
+      const int j = xr % 4;
+      if (j == 0) o.x += extra;
+      if (j == 1) o.y += extra;
+      if (j == 2) o.z += extra;
+      if (j == 3) o.w += extra;
+    }
+    *reinterpret_cast<float4*>(&Hs[r][4 * q]) = o;
+  }
+  __syncthreads();
+  {
+    const int q = tid % 32, rs = tid / 32;
+    float4 v[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) v[j] = *reinterpret_cast<const float4*>(&Hs[rs * 4 + j][4 * q]);
+    const float4 mid = add4(add4(add4(v[3], v[4]), add4(v[5], v[6])), add4(v[7], v[8]));
+    const float4 l12 = add4(v[1], v[2]), r910 = add4(v[9], v[10]);
+    float4 o[4];
+    o[0] = add4(mid, add4(v[0], l12));
+    o[1] = add4(mid, add4(l12, v[9]));
+    o[2] = add4(mid, add4(v[2], r910));
+    o[3] = add4(mid, add4(r910, v[11]));
+    const int gx = x0 + 4 * q;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gy = y0 + rs * 4 + j;
+      if (gy >= H) continue;
+      float4 s = o[j];
+      // output row gy sits at padded row (rs*4 + j + 4) = v[j + 4]
+      if (gy == 0) s = fma4s(4.f, v[j + 4], fma4s(3.f, v[j + 5], fma4s(2.f, v[j + 6], add4(s, v[j + 7]))));
+      if (gy == H - 1) s = fma4s(4.f, v[j + 4], fma4s(3.f, v[j + 3], fma4s(2.f, v[j + 2], add4(s, v[j + 1]))));
+      const int64_t off = (int64_t)gy * W + gx;
+      for (int c = 0; c < C; ++c) {
+        const float* ep = es + (n * C + c) * plane + off;
+        const float* tp = ta + (n * C + c) * plane + off;
+        float* gp = gi + (n * C + c) * plane + off;
+        if (vec) {
+          if (gx < W) {
+            const float4 e = ldg4(ep), t = ldg4(tp);
+            float4 r;
+            if (TYPE == 0) {
+              r = make_float4(2.f * (e.x - t.x) * INV81 * s.x, 2.f * (e.y - t.y) * INV81 * s.y,
+                              2.f * (e.z - t.z) * INV81 * s.z, 2.f * (e.w - t.w) * INV81 * s.w);
+            } else {
+              r = make_float4(sgn(e.x - t.x) * INV81 * s.x, sgn(e.y - t.y) * INV81 * s.y,
+                              sgn(e.z - t.z) * INV81 * s.z, sgn(e.w - t.w) * INV81 * s.w);
+            }
+            *reinterpret_cast<float4*>(gp) = r;
+          }
+        } else {
+          const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            if (gx + k < W) {
+              const float d = __ldg(ep + k) - __ldg(tp + k);
+              gp[k] = (TYPE == 0 ? 2.f * d : sgn(d)) * INV81 * sv[k];
+            }
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// fast path, block size 9, fp32: census_mse / census_sad
+// ------------------------------------------------------------------------------------------
+constexpr int CT_W = 64, CT_H = 32;  // output tile
+constexpr int CE_W = CT_W + 2 * R9;  // 72
+constexpr int CE_H = CT_H + 2 * R9;  // 40
+
+// load a (CE_H x CE_W) halo tile; REPL: replicate-clamped (es, ta), else zero padded (grad_out)
+template <bool REPL>
+__device__ __forceinline__ void load_halo_tile(float (*S)[CE_W], const float* __restrict__ src, int x0,
+                                               int y0, int H, int W, int vec, int tid) {
+  for (int ch = tid; ch < CE_H * (CE_W / 4); ch += 256) {
+    const int r = ch / (CE_W / 4), k = ch % (CE_W / 4);
+    int gy = y0 - R9 + r;
+    const int gx = x0 - R9 + 4 * k;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const bool row_ok = gy >= 0 && gy < H;
+    if (REPL) gy = clampi(gy, 0, H - 1);
+    if (REPL || row_ok) {
+      const float* row = src + (int64_t)gy * W;
+      if (vec && gx >= 0 && gx + 3 < W) {
+        v = ldg4(row + gx);
+      } else if (REPL) {
+        v.x = __ldg(row + clampi(gx + 0, 0, W - 1));
+        v.y = __ldg(row + clampi(gx + 1, 0, W - 1));
+        v.z = __ldg(row + clampi(gx + 2, 0, W - 1));
+        v.w = __ldg(row + clampi(gx + 3, 0, W - 1));
+      } else {
+        if (gx + 0 >= 0 && gx + 0 < W) v.x = __ldg(row + gx + 0);
+        if (gx + 1 >= 0 && gx + 1 < W) v.y = __ldg(row + gx + 1);
+        if (gx + 2 >= 0 && gx + 2 < W) v.z = __ldg(row + gx + 2);
+        if (gx + 3 >= 0 && gx + 3 < W) v.w = __ldg(row + gx + 3);
+      }
+    }
+    *reinterpret_cast<float4*>(&S[r][4 * k]) = v;
+  }
+}
+
+__device__ __forceinline__ void unpack12(float* d, const float* srow) {
+  const float4* p = reinterpret_cast<const float4*>(srow);
+  const float4 a = p[0], b = p[1], c = p[2];
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w;
+  d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+  d[8] = c.x; d[9] = c.y; d[10] = c.z; d[11] = c.w;
+}
+
+// out = sum over the window of psi(h(es_tap - es_ctr) - h(ta_tap - ta_ctr)) / 81,
+// h(x) = (1 + x / sqrt(x^2 + eps)) / 2; psi = square (census_mse) or abs (census_sad).
+template <int TYPE>
+__global__ void __launch_bounds__(256)
+photo_fwd_census9(const float* __restrict__ es, const float* __restrict__ ta, float* __restrict__ out,
+                  int C, int H, int W, float eps, int vec) {
+  __shared__ __align__(16) float Es[CE_H][CE_W];
+  __shared__ __align__(16) float Ts[CE_H][CE_W];
+  const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+  const int64_t n = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int64_t plane = (int64_t)H * W;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int c = 0; c < C; ++c) {
+    if (c) __syncthreads();
+    load_halo_tile<true>(Es, es + (n * C + c) * plane, x0, y0, H, W, vec, tid);
+    load_halo_tile<true>(Ts, ta + (n * C + c) * plane, x0, y0, H, W, vec, tid);
+    __syncthreads();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int yl = ty + 16 * half;
+      if (y0 + yl >= H) continue;
+      const float4 ec4 = *reinterpret_cast<const float4*>(&Es[yl + R9][4 * tx + R9]);
+      const float4 tc4 = *reinterpret_cast<const float4*>(&Ts[yl + R9][4 * tx + R9]);
+      const float ec[4] = {ec4.x, ec4.y, ec4.z, ec4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
+#pragma unroll 1
+      for (int dy = 0; dy < 9; ++dy) {
+        float e[12], t[12];
+        unpack12(e, &Es[yl + dy][4 * tx]);
+        unpack12(t, &Ts[yl + dy][4 * tx]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+          for (int dx = 0; dx < 9; ++dx) {
+            const float des = e[k + dx] - ec[k];
+            const float dta = t[k + dx] - tc[k];
+            const float r1 = rsqrt_approx(fmaf(des, des, eps));
+            const float r2 = rsqrt_approx(fmaf(dta, dta, eps));
+            const float dd = fmaf(des, r1, -(dta * r2));  // = 2 * (h(des) - h(dta))
+            if (TYPE == 2) acc[half][k] = fmaf(dd, dd, acc[half][k]);
+            else acc[half][k] += fabsf(dd);
+          }
+        }
+      }
+    }
+  }
+  const float scale = (TYPE == 2 ? 0.25f : 0.5f) * INV81;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int gy = y0 + ty + 16 * half, gx = x0 + 4 * tx;
+    if (gy >= H) continue;
+    float* dst = out + n * plane + (int64_t)gy * W + gx;
+    if (vec) {
+      if (gx < W)
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[half][0] * scale, acc[half][1] * scale,
+                                                      acc[half][2] * scale, acc[half][3] * scale);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (gx + k < W) dst[k] = acc[half][k] * scale;
+    }
+  }
+}
+
+// IEEE restatement of the reference's soft step difference, used only to decide sign() on near-ties
+__device__ __noinline__ void census_exact_signs(float des, float dta, float eps, float* s_tap, float* s_ctr) {
+  // pixel as the tap of the neighbour (des = es_i - es_q) ...
+  const float q1 = __fdiv_rn(des, __fsqrt_rn(__fadd_rn(__fmul_rn(des, des), eps)));
+  const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
+  const float d1 = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
+  // ... and as the centre (des = es_q - es_i = -des exactly; the quotients flip sign exactly)
+  const float d2 = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
+  *s_tap = sgn(d1);
+  *s_ctr = sgn(d2);
+}
+
+// grad_in[i] = eps/(2*81) * sum_q gl(dd) * r1^3 * (M(i,q) * go[q] + go[i]) over the 9x9 window of i:
+// the first summand is i as a tap of centre q (M = clamp multiplicity, 1 away from the image
+// border), the second is i as the centre scattering -g back to itself; both share dd and r1
+// because h(-x) = 1 - h(x).  go is zero outside the image, es/ta are replicate-clamped.
+template <int TYPE, bool BORDER>
+__device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[CE_W], float (*Gs)[CE_W],
+                                                float* __restrict__ gi, int x0, int y0, int H, int W,
+                                                float eps, int vec, int tx, int ty) {
+#pragma unroll 1
+  for (int half = 0; half < 2; ++half) {
+    const int yl = ty + 16 * half;
+    const int gy = y0 + yl, gx = x0 + 4 * tx;
+    if (gy >= H) continue;
+    const float4 ec4 = *reinterpret_cast<const float4*>(&Es[yl + R9][4 * tx + R9]);
+    const float4 tc4 = *reinterpret_cast<const float4*>(&Ts[yl + R9][4 * tx + R9]);
+    const float4 gc4 = *reinterpret_cast<const float4*>(&Gs[yl + R9][4 * tx + R9]);
+    const float ec[4] = {ec4.x, ec4.y, ec4.z, ec4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
+    const float gc[4] = {gc4.x, gc4.y, gc4.z, gc4.w};
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // clamp multiplicity of the column / row offset d (-4..4): base + slope * d
+    float bx[4], sx[4], by = 1.f, sy = 0.f;
+    if (BORDER) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        bx[k] = 1.f; sx[k] = 0.f;
+        if (gx + k == 0) { bx[k] = 5.f; sx[k] = -1.f; }
+        if (gx + k == W - 1) { bx[k] = 5.f; sx[k] = 1.f; }
+      }
+      if (gy == 0) { by = 5.f; sy = -1.f; }
+      if (gy == H - 1) { by = 5.f; sy = 1.f; }
+    }
+#pragma unroll 1
+    for (int dy = 0; dy < 9; ++dy) {
+      float e[12], t[12], g[12];
+      unpack12(e, &Es[yl + dy][4 * tx]);
+      unpack12(t, &Ts[yl + dy][4 * tx]);
+      unpack12(g, &Gs[yl + dy][4 * tx]);
+      const float my = BORDER ? fmaf(sy, float(dy - R9), by) : 1.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+#pragma unroll
+        for (int dx = 0; dx < 9; ++dx) {
+          const float des = ec[k] - e[k + dx];
+          const float dta = tc[k] - t[k + dx];
+          const float r1 = rsqrt_approx(fmaf(des, des, eps));
+          const float r2 = rsqrt_approx(fmaf(dta, dta, eps));
+          const float dd = fmaf(des, r1, -(dta * r2));
+          const float r3 = r1 * r1 * r1;
+          float gq = g[k + dx];
+          if (BORDER) gq *= my * fmaf(sx[k], float(dx - R9), bx[k]);
+          if (TYPE == 2) {
+            acc[k] = fmaf(dd * r3, gq + gc[k], acc[k]);
+          } else {
+            if (fabsf(dd) < 1e-5f) {
+              float s1, s2;
+              census_exact_signs(des, dta, eps, &s1, &s2);
+              acc[k] = fmaf(r3, s1 * gq - s2 * gc[k], acc[k]);
+            } else {
+              acc[k] += copysignf(r3 * (gq + gc[k]), dd);
+            }
+          }
+        }
+      }
+    }
+    const float scale = 0.5f * eps * INV81;
+    float* dst = gi + (int64_t)gy * W + gx;
+    if (vec) {
+      if (gx < W)
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[0] * scale, acc[1] * scale, acc[2] * scale, acc[3] * scale);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (gx + k < W) dst[k] = acc[k] * scale;
+    }
+  }
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(256)
+photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
+                  float* __restrict__ gi, int C, int H, int W, float eps, int vec) {
+  __shared__ __align__(16) float Es[CE_H][CE_W];
+  __shared__ __align__(16) float Ts[CE_H][CE_W];
+  __shared__ __align__(16) float Gs[CE_H][CE_W];
+  const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+  const int64_t n = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int64_t plane = (int64_t)H * W;
+  const bool border = x0 == 0 || y0 == 0 || x0 + CT_W >= W || y0 + CT_H >= H;
+  load_halo_tile<false>(Gs, go + n * plane, x0, y0, H, W, vec, tid);
+  for (int c = 0; c < C; ++c) {
+    if (c) __syncthreads();
+    load_halo_tile<true>(Es, es + (n * C + c) * plane, x0, y0, H, W, vec, tid);
+    load_halo_tile<true>(Ts, ta + (n * C + c) * plane, x0, y0, H, W, vec, tid);
+    __syncthreads();
+    float* gic = gi + (n * C + c) * plane;
+    if (border) census_bwd_tile<TYPE, true>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty);
+    else census_bwd_tile<TYPE, false>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// dispatch
+// ------------------------------------------------------------------------------------------
+static inline bool fast9_ok(int bs, int64_t H, int64_t W) {
+  return !g_force_generic && bs == 9 && H >= 9 && W >= 9 && H * W < (int64_t)1 << 31;
+}
+
+static int check_common(const void* a, const void* b, const void* c, int64_t B, int64_t C, int64_t H,
+                        int64_t W, int bs, int type) {
+  CTD_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, "photometric: negative size");
+  CTD_REQUIRE(bs >= 1 && bs <= 255, "photometric: block_size %d out of range [1,255]", bs);
+  CTD_REQUIRE(type >= 0 && type <= 3, "photometric: invalid loss type %d", type);
+  CTD_REQUIRE(H <= INT32_MAX && W <= INT32_MAX && C <= INT32_MAX, "photometric: dimension too large");
+  if (B * C * H * W > 0) CTD_REQUIRE(a && b && c, "photometric: null pointer");
+  return CTD_OK;
+}
+
+template <typename T>
+static int fwd_impl(const T* es, const T* ta, T* out, int64_t B, int64_t C, int64_t H, int64_t W, int bs,
+                    int type, float eps, cudaStream_t st) {
+  if (int rc = check_common(es, ta, out, B, C, H, W, bs, type)) return rc;
+  if (B * H * W == 0) return CTD_OK;
+  const int64_t total = B * H * W;
+  const int grid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 64);
+  photo_fwd_generic<T><<<grid, 256, 0, st>>>(es, ta, out, B, (int)C, (int)H, (int)W, bs, type, (T)eps);
+  count_launch();
+  return check_launch("photometric_fwd(generic)");
+}
+
+template <typename T>
+static int bwd_impl(const T* es, const T* ta, const T* go, T* gi, int64_t B, int64_t C, int64_t H, int64_t W,
+                    int bs, int type, float eps, cudaStream_t st) {
+  if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
+  if (B * C * H * W == 0) return CTD_OK;
+  CTD_REQUIRE(go, "photometric_bwd: null grad_out");
+  const int64_t total = B * C * H * W;
+  const int grid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 64);
+  photo_bwd_generic<T><<<grid, 256, 0, st>>>(es, ta, go, gi, B, (int)C, (int)H, (int)W, bs, type, (T)eps);
+  count_launch();
+  return check_launch("photometric_bwd(generic)");
+}
+
+static inline int vec_ok(int64_t W, const void* a, const void* b, const void* c, const void* d) {
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  return W % 4 == 0 && al(a) && al(b) && al(c) && al(d);
+}
+
+}  // namespace ctd
+
+using namespace ctd;
+
+CTD_API int ctd_photometric_fwd_f32(const float* es, const float* ta, float* out, int64_t B, int64_t C,
+                                       int64_t H, int64_t W, int bs, int type, float eps, ctd_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  if (!fast9_ok(bs, H, W) || C < 1 || B < 1) return fwd_impl<float>(es, ta, out, B, C, H, W, bs, type, eps, st);
+  if (int rc = check_common(es, ta, out, B, C, H, W, bs, type)) return rc;
+  const int vec = vec_ok(W, es, ta, out, out);
+  for (int64_t b0 = 0; b0 < B; b0 += 32768) {
+    const int nb = (int)std::min<int64_t>(32768, B - b0);
+    const float* e = es + b0 * C * H * W;
+    const float* t = ta + b0 * C * H * W;
+    float* o = out + b0 * H * W;
+    if (type <= 1) {
+      dim3 grid((unsigned)cdiv(W, BT_W), (unsigned)cdiv(H, BT_H), nb);
+      if (type == 0) photo_fwd_box9<0><<<grid, 256, 0, st>>>(e, t, o, (int)C, (int)H, (int)W, vec);
+      else photo_fwd_box9<1><<<grid, 256, 0, st>>>(e, t, o, (int)C, (int)H, (int)W, vec);
+    } else {
+      dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
+      if (type == 2) photo_fwd_census9<2><<<grid, 256, 0, st>>>(e, t, o, (int)C, (int)H, (int)W, eps, vec);
+      else photo_fwd_census9<3><<<grid, 256, 0, st>>>(e, t, o, (int)C, (int)H, (int)W, eps, vec);
+    }
+    count_launch();
+  }
+  return check_launch("photometric_fwd");
+}
+
+CTD_API int ctd_photometric_fwd_f64(const double* es, const double* ta, double* out, int64_t B, int64_t C,
+                                       int64_t H, int64_t W, int bs, int type, float eps, ctd_stream_t stream) {
+  return fwd_impl<double>(es, ta, out, B, C, H, W, bs, type, eps, as_stream(stream));
+}
+
+CTD_API int ctd_photometric_bwd_f32(const float* es, const float* ta, const float* go, float* gi, int64_t B,
+                                       int64_t C, int64_t H, int64_t W, int bs, int type, float eps,
+                                       ctd_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  if (!fast9_ok(bs, H, W) || C < 1 || B < 1) return bwd_impl<float>(es, ta, go, gi, B, C, H, W, bs, type, eps, st);
+  if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
+  CTD_REQUIRE(go, "photometric_bwd: null grad_out");
+  const int vec = vec_ok(W, es, ta, go, gi);
+  for (int64_t b0 = 0; b0 < B; b0 += 32768) {
+    const int nb = (int)std::min<int64_t>(32768, B - b0);
+    const float* e = es + b0 * C * H * W;
+    const float* t = ta + b0 * C * H * W;
+    const float* g = go + b0 * H * W;
+    float* o = gi + b0 * C * H * W;
+    if (type <= 1) {
+      dim3 grid((unsigned)cdiv(W, BT_W), (unsigned)cdiv(H, BT_H), nb);
+      if (type == 0) photo_bwd_box9<0><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, vec);
+      else photo_bwd_box9<1><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, vec);
+    } else {
+      dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
+      if (type == 2) photo_bwd_census9<2><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec);
+      else photo_bwd_census9<3><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec);
+    }
+    count_launch();
+  }
+  return check_launch("photometric_bwd");
+}
+
+CTD_API int ctd_photometric_bwd_f64(const double* es, const double* ta, const double* go, double* gi,
+                                       int64_t B, int64_t C, int64_t H, int64_t W, int bs, int type, float eps,
+                                       ctd_stream_t stream) {
+  return bwd_impl<double>(es, ta, go, gi, B, C, H, W, bs, type, eps, as_stream(stream));
+}

@@ -1,0 +1,181 @@
+"""The reference's native CUDA entry points, re-bound onto libctd_b200.so.
+
+Mirrors the pybind11 module `ext_cuda` of the reference (torchext/ext/ext_cuda.cpp:126-135): same
+function names, argument order and meaning, same Python-visible exception types (RuntimeError for
+contiguity / device / shape violations like AT_ASSERTM, NotImplementedError for dtypes other than
+float32/float64).  Differences, all deliberate ("reference hazards"): outputs are
+allocated on the INPUT's device, kernels run on torch's CURRENT stream under a device guard, CUDA
+errors raise instead of exit(-1), es/ta shape and K shape are checked, an invalid loss type raises
+instead of returning uninitialised memory, xcorrvol also accepts a batched [B,C,H,W] pair, and
+photometric_loss_backward overwrites its result (no zero fill, no atomics).
+"""
+import torch
+
+from .. import _lib
+
+_SUFFIX = {torch.float32: "_f32", torch.float64: "_f64"}
+
+
+def _check(cond, msg):
+    if not cond:
+        raise RuntimeError(msg)
+
+
+def _check_input_cuda(t, name):
+    _check(isinstance(t, torch.Tensor), "%s must be a tensor" % name)
+    _check(t.is_cuda, "%s must be a CUDA tensor" % name)
+    _check(t.is_contiguous(), "%s must be contiguous" % name)
+
+
+def _real_suffix(t, op):
+    try:
+        return _SUFFIX[t.dtype]
+    except KeyError:
+        raise NotImplementedError('"%s" not implemented for \'%s\'' % (op, str(t.dtype).replace("torch.", "").capitalize()))
+
+
+def _same(a, b, na, nb):
+    _check(a.dtype == b.dtype, "%s and %s must have the same dtype" % (na, nb))
+    _check(a.device == b.device, "%s and %s must be on the same device" % (na, nb))
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def nn_cuda(in0, in1):
+    """ext_cuda.cpp:9-26.  in0 [N0,3], in1 [N1,3] -> int64 [N0] nearest-neighbour indices (or -1)."""
+    _check_input_cuda(in0, "in0")
+    _check_input_cuda(in1, "in1")
+    _check(in0.dim() == 2, "in0 has to be N0 x 3")
+    _check(in1.dim() == 2, "in1 has to be N1 x 3")
+    _check(in0.size(1) == in1.size(1), "in0 and in1 have to be the same shape")
+    _check(in0.size(1) == 3, "dim hast to be 3")
+    _same(in0, in1, "in0", "in1")
+    sfx = _real_suffix(in0, "nn")
+    out = torch.empty((in0.size(0),), dtype=torch.int64, device=in0.device)
+    with torch.cuda.device(in0.device):
+        _lib.call("ctd_nn" + sfx, in0.data_ptr(), in1.data_ptr(), out.data_ptr(), in0.size(0), in1.size(0), _stream(in0))
+    return out
+
+
+def crosscheck_cuda(in0, in1):
+    """ext_cuda.cpp:31-43.  in0 int64 [N0], in1 int64 [N1] -> uint8 [N0] mutual-consistency mask."""
+    _check_input_cuda(in0, "in0")
+    _check_input_cuda(in1, "in1")
+    _check(in0.dim() == 1, "in0 has to be 1-D")
+    _check(in1.dim() == 1, "in1 has to be 1-D")
+    _check(in0.dtype == torch.int64 and in1.dtype == torch.int64, "crosscheck expects int64 index tensors")
+    _check(in0.device == in1.device, "in0 and in1 must be on the same device")
+    out = torch.empty((in0.size(0),), dtype=torch.uint8, device=in0.device)
+    with torch.cuda.device(in0.device):
+        _lib.call("ctd_crosscheck", in0.data_ptr(), in1.data_ptr(), out.data_ptr(), in0.size(0), in1.size(0), _stream(in0))
+    return out
+
+
+def proj_nn_cuda(xyz0, xyz1, K, patch_size):
+    """ext_cuda.cpp:47-69.  xyz0, xyz1 [B,H,W,3], K [3,3] -> int64 [B,H,W] flat indices into xyz1 (or -1)."""
+    _check_input_cuda(xyz0, "xyz0")
+    _check_input_cuda(xyz1, "xyz1")
+    _check_input_cuda(K, "K")
+    _check(xyz0.dim() == 4 and xyz1.dim() == 4, "xyz0 and xyz1 have to be B x H x W x 3")
+    _check(tuple(xyz0.shape) == tuple(xyz1.shape), "xyz0 and xyz1 have to be the same shape")
+    _check(xyz0.size(3) == 3, "last dimension has to be 3")
+    _check(K.numel() == 9, "K has to be 3 x 3")
+    _same(xyz0, xyz1, "xyz0", "xyz1")
+    _same(xyz0, K, "xyz0", "K")
+    sfx = _real_suffix(xyz0, "proj_nn")
+    B, H, W = xyz0.shape[:3]
+    out = torch.empty((B, H, W), dtype=torch.int64, device=xyz0.device)
+    with torch.cuda.device(xyz0.device):
+        _lib.call("ctd_proj_nn" + sfx, xyz0.data_ptr(), xyz1.data_ptr(), K.data_ptr(), out.data_ptr(), B, H, W,
+                  int(patch_size), _stream(xyz0))
+    return out
+
+
+def xcorrvol_cuda(in0, in1, n_disps, block_size):
+    """ext_cuda.cpp:73-86.  in0, in1 [C,H,W] -> [n_disps,H,W]; batched: [B,C,H,W] -> [B,n_disps,H,W]."""
+    _check_input_cuda(in0, "in0")
+    _check_input_cuda(in1, "in1")
+    _check(in0.dim() in (3, 4), "in0 has to be C x H x W (or B x C x H x W)")
+    _check(tuple(in0.shape) == tuple(in1.shape), "in0 and in1 have to be the same shape")
+    _same(in0, in1, "in0", "in1")
+    sfx = _real_suffix(in0, "xcorrvol")
+    batched = in0.dim() == 4
+    B = in0.size(0) if batched else 1
+    C, H, W = in0.shape[-3:]
+    out = torch.empty((B, int(n_disps), H, W) if batched else (int(n_disps), H, W), dtype=in0.dtype, device=in0.device)
+    with torch.cuda.device(in0.device):
+        _lib.call("ctd_xcorrvol" + sfx, in0.data_ptr(), in1.data_ptr(), out.data_ptr(), B, C, H, W, int(n_disps),
+                  int(block_size), _stream(in0))
+    return out
+
+
+def _photometric_args(es, ta, type):
+    _check_input_cuda(es, "es")
+    _check_input_cuda(ta, "ta")
+    _check(es.dim() == 4, "es has to be B x C x H x W")
+    _check(tuple(es.shape) == tuple(ta.shape), "es and ta have to be the same shape")
+    _same(es, ta, "es", "ta")
+    _check(int(type) in (0, 1, 2, 3), "invalid loss type")
+    return _real_suffix(es, "photometric_loss")
+
+
+def photometric_loss_forward(es, ta, block_size, type, eps):
+    """ext_cuda.cpp:92-104.  es, ta [B,C,H,W] -> [B,1,H,W]; type 0 mse, 1 sad, 2 census_mse, 3 census_sad."""
+    sfx = _photometric_args(es, ta, type)
+    B, C, H, W = es.shape
+    out = torch.empty((B, 1, H, W), dtype=es.dtype, device=es.device)
+    with torch.cuda.device(es.device):
+        _lib.call("ctd_photometric_fwd" + sfx, es.data_ptr(), ta.data_ptr(), out.data_ptr(), B, C, H, W,
+                  int(block_size), int(type), float(eps), _stream(es))
+    return out
+
+
+def photometric_loss_backward(es, ta, grad_out, block_size, type, eps):
+    """ext_cuda.cpp:109-123.  grad_out [B,1,H,W] -> gradient w.r.t. es, [B,C,H,W]."""
+    sfx = _photometric_args(es, ta, type)
+    _check_input_cuda(grad_out, "grad_out")
+    B, C, H, W = es.shape
+    _check(grad_out.numel() == B * H * W, "grad_out has to be B x 1 x H x W")
+    _same(es, grad_out, "es", "grad_out")
+    grad_in = torch.empty((B, C, H, W), dtype=es.dtype, device=es.device)
+    with torch.cuda.device(es.device):
+        _lib.call("ctd_photometric_bwd" + sfx, es.data_ptr(), ta.data_ptr(), grad_out.data_ptr(), grad_in.data_ptr(),
+                  B, C, H, W, int(block_size), int(type), float(eps), _stream(es))
+    return grad_in
+
+
+def lcn_forward(x, radius, epsilon):
+    """model/networks.py:523-533 as one kernel.  x [N,1,H,W] -> (lcn, std), both [N,1,H,W]."""
+    _check_input_cuda(x, "x")
+    _check(x.dim() == 4 and x.size(1) == 1, "x has to be N x 1 x H x W")
+    sfx = _real_suffix(x, "lcn")
+    N, _, H, W = x.shape
+    out = torch.empty_like(x)
+    std = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.call("ctd_lcn" + sfx, x.data_ptr(), out.data_ptr(), std.data_ptr(), N, H, W, int(radius), float(epsilon),
+                  _stream(x))
+    return out, std
+
+
+_reduce_ws = {}
+
+
+def masked_sums(diff, mask):
+    """model/networks.py:377 numerator and denominator in one deterministic kernel:
+    returns float32 [2] = (sum(mask * diff), sum(mask)).  val = r[0] / r[1]."""
+    _check_input_cuda(diff, "diff")
+    _check_input_cuda(mask, "mask")
+    _check(diff.dtype == torch.float32 and mask.dtype == torch.float32, "masked_sums expects float32")
+    _check(diff.numel() == mask.numel(), "diff and mask have to be the same size")
+    _same(diff, mask, "diff", "mask")
+    key = (diff.device, torch.cuda.current_stream(diff.device).cuda_stream)
+    ws = _reduce_ws.get(key)
+    if ws is None:
+        ws = _reduce_ws[key] = torch.zeros(int(_lib.lib().ctd_masked_sums_workspace_bytes()), dtype=torch.uint8, device=diff.device)
+    out = torch.empty(2, dtype=torch.float32, device=diff.device)
+    with torch.cuda.device(diff.device):
+        _lib.call("ctd_masked_sums_f32", diff.data_ptr(), mask.data_ptr(), diff.numel(), out.data_ptr(), ws.data_ptr(), _stream(diff))
+    return out

@@ -1,0 +1,160 @@
+"""The reference's op API (torchext/functions.py:5-147), same names, signatures, defaults and return
+types, dispatching to the B200 kernels.  CUDA tensors go to ext_cuda (libctd_b200.so); CPU tensors
+reach ext_cpu, which raises -- there is no CPU implementation.
+
+Only photometric_loss is differentiable (w.r.t. `es`); the index / cost-volume ops return None
+gradients like the reference (functions.py:15-17,33-35,50-52,69-71).
+"""
+import torch
+
+from . import ext_cpu
+from . import ext_cuda
+
+LOSS_TYPES = {"mse": 0, "sad": 1, "census_mse": 2, "census_sad": 3}  # ext.h:196-199
+
+
+def _native(t, cuda_name, cpu_name):
+    return getattr(ext_cuda, cuda_name) if t.is_cuda else getattr(ext_cpu, cpu_name)
+
+
+class NNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in0, in1):
+        return _native(in0, "nn_cuda", "nn_cpu")(in0, in1)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, None
+
+
+def nn(in0, in1):
+    """For every row of in0 [N0,3] the index of its nearest row of in1 [N1,3] (int64, -1 if none)."""
+    return NNFunction.apply(in0, in1)
+
+
+class CrossCheckFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in0, in1):
+        return _native(in0, "crosscheck_cuda", "crosscheck_cpu")(in0, in1)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, None
+
+
+def crosscheck(in0, in1):
+    """uint8 mask: in0[i] = j >= 0 and in1[j] == i (mutual consistency of two index maps)."""
+    return CrossCheckFunction.apply(in0, in1)
+
+
+class ProjNNFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xyz0, xyz1, K, patch_size):
+        return _native(xyz0, "proj_nn_cuda", "proj_nn_cpu")(xyz0, xyz1, K, patch_size)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, None, None, None
+
+
+def proj_nn(xyz0, xyz1, K, patch_size):
+    """Project xyz0 with K, search a patch_size^2 pixel patch of xyz1 for the nearest 3-D point."""
+    return ProjNNFunction.apply(xyz0, xyz1, K, patch_size)
+
+
+class XCorrVolFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, in0, in1, n_disps, block_size):
+        return _native(in0, "xcorrvol_cuda", "xcorrvol_cpu")(in0, in1, n_disps, block_size)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        return None, None, None, None
+
+
+def xcorrvol(in0, in1, n_disps, block_size):
+    """Normalised cross-correlation cost volume [n_disps,H,W] of in0 against in1 shifted by d."""
+    return XCorrVolFunction.apply(in0, in1, n_disps, block_size)
+
+
+class PhotometricLossFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, es, ta, block_size, type, eps):
+        ctx.save_for_backward(es, ta)
+        ctx.block_size, ctx.type, ctx.eps = block_size, type, eps
+        return _native(es, "photometric_loss_forward", "photometric_loss_forward")(es, ta, block_size, type, eps)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        es, ta = ctx.saved_tensors
+        fn = _native(grad_out, "photometric_loss_backward", "photometric_loss_backward")
+        grad_es = fn(es, ta, grad_out.contiguous(), ctx.block_size, ctx.type, ctx.eps)
+        return grad_es, None, None, None, None
+
+
+def _loss_type_id(type):
+    try:
+        return LOSS_TYPES[type.lower()]
+    except KeyError:
+        raise Exception("invalid loss type")
+
+
+def photometric_loss(es, ta, block_size, type="mse", eps=0.1):
+    """Block-window photometric loss map [B,1,H,W]; type in mse | sad | census_mse | census_sad."""
+    return PhotometricLossFunction.apply(es, ta, block_size, _loss_type_id(type), eps)
+
+
+def photometric_loss_pytorch(es, ta, block_size, type="mse", eps=0.1):
+    """Plain-torch evaluation of the same loss (differentiable by autograd, any device); the
+    counterpart of the reference's functions.py:120-147, written as a loop over window offsets on a
+    replicate-padded copy instead of an unfold, so it needs O(1) extra image copies."""
+    kind = type.lower()
+    if kind not in LOSS_TYPES:
+        raise Exception("invalid loss type")
+    lo = block_size // 2
+    hi = block_size - 1 - lo
+    H, W = es.shape[2], es.shape[3]
+    es_p = torch.nn.functional.pad(es, (lo, hi, lo, hi), mode="replicate")
+    ta_p = torch.nn.functional.pad(ta, (lo, hi, lo, hi), mode="replicate")
+
+    def soft_step(x):
+        return 0.5 * (1 + x / torch.sqrt(x * x + eps))
+
+    total = None
+    for dy in range(block_size):
+        for dx in range(block_size):
+            e = es_p[:, :, dy:dy + H, dx:dx + W]
+            t = ta_p[:, :, dy:dy + H, dx:dx + W]
+            d = (soft_step(e - es) - soft_step(t - ta)) if kind.startswith("census") else (e - t)
+            term = (d * d if kind.endswith("mse") else d.abs()).sum(dim=1, keepdim=True)
+            total = term if total is None else total + term
+    return total / block_size ** 2
+
+
+class LCNFunction(torch.autograd.Function):
+    """Fused local contrast normalisation (model/networks.py:507-533); forward only -- in the
+    reference the gradient flows to an input image nobody reads (exp_synph.py:80-91)."""
+
+    @staticmethod
+    def forward(ctx, x, radius, epsilon):
+        if not x.is_cuda:
+            raise RuntimeError("torchext.lcn: connecting_the_dots_b200 has no CPU implementation")
+        out, std = ext_cuda.lcn_forward(x, radius, epsilon)
+        ctx.mark_non_differentiable(out, std)
+        return out, std
+
+    @staticmethod
+    def backward(ctx, g0, g1):
+        return None, None, None
+
+
+def lcn(x, radius=5, epsilon=0.05):
+    """(x - box_mean) / (box_std + epsilon) over a (2*radius+1)^2 reflection-padded window -> (lcn, std)."""
+    return LCNFunction.apply(x, radius, epsilon)
+
+
+def masked_mean_terms(diff, mask):
+    """(sum(mask*diff), sum(mask)) as a float32 [2] tensor: the two scalars of the caller's
+    `(mask*diff).sum() / mask.sum()` (model/networks.py:377); under batch sharding they are what gets
+    all-reduced.  Not differentiable (use photometric_loss's own backward with grad_out = mask / sum)."""
+    return ext_cuda.masked_sums(diff.detach(), mask.detach())

@@ -1,0 +1,135 @@
+/*
+ * ctd_b200.h -- C ABI of libctd_b200.so, the B200 (sm_100a) implementation of the
+ * per-pixel custom ops of "Connecting the Dots" (reference: torchext/ext/).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no torch types.  Each entry
+ * point names the reference interface it replaces (paths relative to the reference
+ * repository).  Two families:
+ *
+ *   ctd_<op>_<dtype>(..., stream)      DEVICE pointers; asynchronous launch on `stream`
+ *                                      (cudaStream_t; NULL = legacy default stream);
+ *                                      what ext_cuda.cpp's *_cuda / photometric_loss_*
+ *                                      functions would call instead of ext_kernel.cu.
+ *   ctd_host_<op>_<dtype>(...)         HOST pointers (pageable or pinned); copies in,
+ *                                      runs the same kernels, copies out, returns when the
+ *                                      result is in host memory; what ext_cpu.cpp's *_cpu
+ *                                      functions would call instead of iterate_cpu.
+ *
+ * Every function returns CTD_OK (0) or a CTD_ERR_* code and never terminates the process
+ * (the reference's CUDA_CHECK calls exit(-1), common_cuda.h:11-20).  ctd_last_error()
+ * returns a thread-local message for the last failure.  There is no CPU fallback: without
+ * a CUDA device every compute entry point returns CTD_ERR_CUDA.
+ *
+ * Layouts are the reference's: contiguous row-major, es/ta/grad [B,C,H,W], out [B,1,H,W],
+ * xyz [B,H,W,3], K [3,3], cost volume [D,H,W] per image.  Index outputs are int64,
+ * CrossCheck masks are uint8 (ext_cpu.cpp:31,50,76).
+ */
+#ifndef CTD_B200_H
+#define CTD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* ctd_stream_t; /* a cudaStream_t */
+
+enum {
+  CTD_OK = 0,
+  CTD_ERR_INVALID = 1, /* bad argument (shape, type id, null pointer) */
+  CTD_ERR_CUDA = 2,    /* CUDA runtime error, message in ctd_last_error() */
+  CTD_ERR_NOMEM = 3    /* workspace allocation failed */
+};
+
+/* loss type ids, torchext/ext/ext.h:196-199 */
+enum { CTD_LOSS_MSE = 0, CTD_LOSS_SAD = 1, CTD_LOSS_CENSUS_MSE = 2, CTD_LOSS_CENSUS_SAD = 3 };
+
+const char* ctd_last_error(void);
+/* library version and the SM architecture the kernels were compiled for ("sm_100a") */
+const char* ctd_version(void);
+/* number of kernel launches issued by this library in the calling process so far */
+uint64_t ctd_launch_count(void);
+/* test/tuning switches: "force_generic" = 1 routes every op through its generic kernel */
+int ctd_set_option(const char* name, int value);
+
+/* ---- PhotometricLossForward: ext.h:201-266, ext_cuda.cpp:92-104 (photometric_loss_forward) */
+int ctd_photometric_fwd_f32(const float* es, const float* ta, float* out, int64_t B, int64_t C,
+                            int64_t H, int64_t W, int block_size, int type, float eps,
+                            ctd_stream_t stream);
+int ctd_photometric_fwd_f64(const double* es, const double* ta, double* out, int64_t B, int64_t C,
+                            int64_t H, int64_t W, int block_size, int type, float eps,
+                            ctd_stream_t stream);
+/* ---- PhotometricLossBackward: ext.h:268-344, ext_cuda.cpp:109-123 (photometric_loss_backward).
+ * grad_in [B,C,H,W] is fully overwritten (no zero-initialisation needed, no atomics). */
+int ctd_photometric_bwd_f32(const float* es, const float* ta, const float* grad_out, float* grad_in,
+                            int64_t B, int64_t C, int64_t H, int64_t W, int block_size, int type,
+                            float eps, ctd_stream_t stream);
+int ctd_photometric_bwd_f64(const double* es, const double* ta, const double* grad_out,
+                            double* grad_in, int64_t B, int64_t C, int64_t H, int64_t W,
+                            int block_size, int type, float eps, ctd_stream_t stream);
+
+/* ---- XCorrVolFunctor: ext.h:120-191, ext_cuda.cpp:73-86 (xcorrvol_cuda).  The reference has no
+ * batch dimension; here in0,in1 are [B,C,H,W] and out is [B,D,H,W] (B=1 is the reference call). */
+int ctd_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,
+                     int64_t W, int64_t n_disps, int block_size, ctd_stream_t stream);
+int ctd_xcorrvol_f64(const double* in0, const double* in1, double* out, int64_t B, int64_t C,
+                     int64_t H, int64_t W, int64_t n_disps, int block_size, ctd_stream_t stream);
+
+/* ---- ProjNNFunctor: ext.h:65-117, ext_cuda.cpp:47-69 (proj_nn_cuda).  K is a DEVICE pointer to
+ * 9 values (row-major 3x3), like the reference's K tensor. */
+int ctd_proj_nn_f32(const float* xyz0, const float* xyz1, const float* K, int64_t* out, int64_t B,
+                    int64_t H, int64_t W, int patch_size, ctd_stream_t stream);
+int ctd_proj_nn_f64(const double* xyz0, const double* xyz1, const double* K, int64_t* out, int64_t B,
+                    int64_t H, int64_t W, int patch_size, ctd_stream_t stream);
+
+/* ---- NNFunctor<T,3>: ext.h:13-46, ext_cuda.cpp:9-26 (nn_cuda).  in0 [N0,3], in1 [N1,3]. */
+int ctd_nn_f32(const float* in0, const float* in1, int64_t* out, int64_t N0, int64_t N1,
+               ctd_stream_t stream);
+int ctd_nn_f64(const double* in0, const double* in1, int64_t* out, int64_t N0, int64_t N1,
+               ctd_stream_t stream);
+
+/* ---- CrossCheckFunctor: ext.h:48-63, ext_cuda.cpp:31-43 (crosscheck_cuda).  N1 is used only to
+ * reject out-of-range gathers (they yield 0; the reference reads out of bounds there). */
+int ctd_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t N0, int64_t N1,
+                   ctd_stream_t stream);
+
+/* ---- LCN: model/networks.py:507-533 (LCN.tforward).  x [N,1,H,W] -> lcn, std [N,1,H,W]. */
+int ctd_lcn_f32(const float* x, float* lcn, float* std, int64_t N, int64_t H, int64_t W, int radius,
+                float epsilon, ctd_stream_t stream);
+int ctd_lcn_f64(const double* x, double* lcn, double* std, int64_t N, int64_t H, int64_t W,
+                int radius, double epsilon, ctd_stream_t stream);
+
+/* ---- masked loss reduction of the caller, model/networks.py:377: val = (mask*diff).sum() / mask.sum().
+ * out2[0] = sum(mask*diff), out2[1] = sum(mask), deterministic.  `workspace`: device memory of
+ * ctd_masked_sums_workspace_bytes() bytes, zero-filled once before first use, one per concurrent stream. */
+int64_t ctd_masked_sums_workspace_bytes(void);
+int ctd_masked_sums_f32(const float* diff, const float* mask, int64_t n, float* out2, void* workspace,
+                        ctd_stream_t stream);
+
+/* ---- host-buffer entry points (fp32): same arguments, HOST pointers, synchronous.  They stage
+ * through a per-thread grow-only device workspace on the current device. */
+int ctd_host_photometric_fwd_f32(const float* es, const float* ta, float* out, int64_t B, int64_t C,
+                                 int64_t H, int64_t W, int block_size, int type, float eps);
+int ctd_host_photometric_bwd_f32(const float* es, const float* ta, const float* grad_out,
+                                 float* grad_in, int64_t B, int64_t C, int64_t H, int64_t W,
+                                 int block_size, int type, float eps);
+/* forward and backward in one staged call: es/ta cross the bus once */
+int ctd_host_photometric_fwd_bwd_f32(const float* es, const float* ta, const float* grad_out,
+                                     float* out, float* grad_in, int64_t B, int64_t C, int64_t H,
+                                     int64_t W, int block_size, int type, float eps);
+int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C,
+                          int64_t H, int64_t W, int64_t n_disps, int block_size);
+int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const float* K, int64_t* out,
+                         int64_t B, int64_t H, int64_t W, int patch_size);
+int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, int64_t N0, int64_t N1);
+int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t N0, int64_t N1);
+int ctd_host_lcn_f32(const float* x, float* lcn, float* std, int64_t N, int64_t H, int64_t W,
+                     int radius, float epsilon);
+/* release the calling thread's staging workspace */
+void ctd_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTD_B200_H */

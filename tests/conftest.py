@@ -32,3 +32,25 @@ def ref_ext():
     if mod is None:
         pytest.skip("oracle/_ref not built (reference sources absent)")
     return mod
+
+
+@pytest.fixture(scope="session")
+def tx():
+    """The drop-in torchext package, with the kernel library built and loaded (fails loudly if not)."""
+    import connecting_the_dots_b200 as ctd
+    ctd._lib.lib()
+    return ctd.torchext
+
+
+def assert_close(got, ref, tol=1e-5, what=""):
+    """The floating-point comparator of this repo: max |got - ref| <= tol * max |ref|.
+    Gradients have mixed signs and near-zero entries, so the scale is the tensor's, not the element's."""
+    import numpy as np
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert got.shape == ref.shape, (what, got.shape, ref.shape)
+    scale = max(float(np.abs(ref).max()) if ref.size else 0.0, 1e-30)
+    err = float(np.abs(got - ref).max()) if ref.size else 0.0
+    assert np.isfinite(got).all(), what + ": non-finite values"
+    assert err <= tol * scale, "%s: max abs err %.3e > %.0e * max|ref| (%.3e)" % (what, err, tol, scale)
+    return err / scale

@@ -1,0 +1,393 @@
+"""GPU parity suite (-m gpu): every op of the drop-in torchext package, called through the C ABI of
+libctd_b200.so, against the CPU oracle (oracle/ctd_oracle.c, pinned to the reference by
+tests/test_oracle.py) and the committed golden vectors of the unmodified reference.
+
+Tolerances: bit-exact for CrossCheck masks and NN / ProjNN indices; 1e-5 relative for loss maps,
+gradients, cost volumes and LCN, with the comparator tests/conftest.py:assert_close
+(max |got - ref| <= 1e-5 * max |ref|).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from conftest import assert_close
+
+pytestmark = pytest.mark.gpu
+TYPES = ("mse", "sad", "census_mse", "census_sad")
+DEV = "cuda:0"
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def photometric_both(tx, es, ta, go, bs, ty, eps):
+    e = cu(es).requires_grad_(True)
+    out = tx.photometric_loss(e, cu(ta), bs, TYPES[ty], eps)
+    out.backward(cu(go))
+    return out.detach().cpu().numpy(), e.grad.cpu().numpy()
+
+
+# ---------------------------------------------------------------- photometric loss
+@pytest.mark.parametrize("C", (1, 2))
+@pytest.mark.parametrize("bs", (2, 3, 9))
+@pytest.mark.parametrize("ty", range(4))
+def test_photometric_golden(tx, golden, C, bs, ty):
+    g = golden("photometric")
+    es, ta, go = g[f"f32_C{C}_es"], g[f"f32_C{C}_ta"], g[f"f32_C{C}_go"]
+    eps = 0.5 if ty == 3 else 0.1
+    fwd, bwd = photometric_both(tx, es, ta, go, bs, ty, eps)
+    assert_close(fwd, g[f"f32_C{C}_bs{bs}_t{ty}_fwd"], what="fwd")
+    assert_close(bwd, g[f"f32_C{C}_bs{bs}_t{ty}_bwd"], what="bwd")
+
+
+@pytest.mark.parametrize("ty", range(4))
+def test_photometric_golden_f64(tx, golden, ty):
+    g = golden("photometric")
+    for C in (1, 2):
+        es, ta, go = g[f"f64_C{C}_es"], g[f"f64_C{C}_ta"], g[f"f64_C{C}_go"]
+        eps = 0.5 if ty == 3 else 0.1
+        fwd, bwd = photometric_both(tx, es, ta, go, 9, ty, eps)
+        assert fwd.dtype == np.float64
+        assert_close(fwd, g[f"f64_C{C}_bs9_t{ty}_fwd"], tol=1e-12, what="fwd64")
+        assert_close(bwd, g[f"f64_C{C}_bs9_t{ty}_bwd"], tol=1e-12, what="bwd64")
+
+
+SHAPES = [  # B, C, H, W, bs -- ragged widths (scalar path), multi-tile, tiny (generic path), block sizes
+    (2, 1, 33, 132, 9), (1, 1, 40, 67, 9), (1, 2, 64, 256, 9), (1, 1, 9, 9, 9), (3, 1, 70, 200, 9),
+    (1, 3, 17, 23, 9), (1, 1, 5, 6, 9), (1, 1, 3, 3, 9), (2, 1, 20, 31, 5), (1, 2, 16, 16, 4), (1, 1, 12, 40, 1),
+    (1, 1, 8, 300, 9), (1, 1, 300, 12, 9),
+]
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("ty", range(4))
+def test_photometric_vs_oracle(tx, shape, ty):
+    B, C, H, W, bs = shape
+    rng = np.random.RandomState(hash(shape) % 2**31)
+    es = rng.randn(B, C, H, W).astype(np.float32)
+    ta = (es + 0.7 * rng.randn(B, C, H, W)).astype(np.float32)
+    es[0, 0, H // 2, W // 2] = ta[0, 0, H // 2, W // 2]
+    go = rng.rand(B, 1, H, W).astype(np.float32)
+    eps = 0.5
+    fwd, bwd = photometric_both(tx, es, ta, go, bs, ty, eps)
+    assert_close(fwd, oracle.photometric_loss_forward(es, ta, bs, ty, eps), what="fwd")
+    assert_close(bwd, oracle.photometric_loss_backward(es, ta, go, bs, ty, eps), what="bwd")
+
+
+@pytest.mark.parametrize("ty", range(4))
+def test_photometric_generic_kernels_agree(tx, ty):
+    """force_generic routes block-size-9 fp32 through the generic kernels as well."""
+    from connecting_the_dots_b200 import _lib
+    rng = np.random.RandomState(5)
+    es = rng.randn(2, 2, 30, 44).astype(np.float32)
+    ta = rng.randn(2, 2, 30, 44).astype(np.float32)
+    go = rng.randn(2, 1, 30, 44).astype(np.float32)  # signed upstream gradient
+    _lib.set_option("force_generic", 1)
+    try:
+        fwd, bwd = photometric_both(tx, es, ta, go, 9, ty, 0.3)
+    finally:
+        _lib.set_option("force_generic", 0)
+    assert_close(fwd, oracle.photometric_loss_forward(es, ta, 9, ty, 0.3), what="fwd")
+    assert_close(bwd, oracle.photometric_loss_backward(es, ta, go, 9, ty, 0.3), what="bwd")
+    fwd2, bwd2 = photometric_both(tx, es, ta, go, 9, ty, 0.3)
+    assert_close(fwd2, fwd, what="fast vs generic fwd")
+    assert_close(bwd2, bwd, what="fast vs generic bwd")
+
+
+@pytest.mark.parametrize("ty", (1, 3))
+def test_photometric_full_size_synthetic(tx, ty):
+    """BASELINE config 1/2 data: 480x640 LCN'd dot-pattern pairs, grad_out = std / sum(std)."""
+    from connecting_the_dots_b200 import synth
+    d = synth.make_batch(2)
+    eps = 0.5
+    fwd, bwd = photometric_both(tx, d["es"], d["ta"], d["go"], 9, ty, eps)
+    assert_close(fwd, oracle.photometric_loss_forward(d["es"], d["ta"], 9, ty, eps), what="fwd")
+    assert_close(bwd, oracle.photometric_loss_backward(d["es"], d["ta"], d["go"], 9, ty, eps), what="bwd")
+
+
+def test_photometric_backward_is_deterministic_and_linear(tx):
+    """No atomics: two runs are bit-identical; the backward is linear in grad_out (size-independent
+    property checked at the bench size, batch 8)."""
+    torch.manual_seed(0)
+    es = torch.randn(8, 1, 480, 640, device=DEV)
+    ta = torch.randn(8, 1, 480, 640, device=DEV)
+    g1 = torch.rand(8, 1, 480, 640, device=DEV)
+    g2 = torch.rand(8, 1, 480, 640, device=DEV)
+    for ty in (1, 3):
+        a = tx.ext_cuda.photometric_loss_backward(es, ta, g1, 9, ty, 0.5)
+        b = tx.ext_cuda.photometric_loss_backward(es, ta, g1, 9, ty, 0.5)
+        assert torch.equal(a, b)
+        c = tx.ext_cuda.photometric_loss_backward(es, ta, g2, 9, ty, 0.5)
+        s = tx.ext_cuda.photometric_loss_backward(es, ta, g1 + g2, 9, ty, 0.5)
+        assert_close((a + c).cpu().numpy(), s.cpu().numpy(), tol=2e-5, what="linearity")
+
+
+@pytest.mark.parametrize("ty", range(4))
+def test_photometric_matches_torch_restatement_and_autograd(tx, ty):
+    """photometric_loss_pytorch (functions.py:120-147 counterpart) in fp64 with autograd is an
+    independent second implementation of forward AND backward."""
+    rng = np.random.RandomState(8)
+    es = torch.from_numpy(rng.randn(1, 2, 21, 37)).to(DEV).requires_grad_(True)
+    ta = torch.from_numpy(rng.randn(1, 2, 21, 37)).to(DEV)
+    go = torch.from_numpy(rng.randn(1, 1, 21, 37)).to(DEV)
+    ref = tx.photometric_loss_pytorch(es, ta, 9, TYPES[ty], 0.5)
+    (gref,) = torch.autograd.grad(ref, es, go)
+    out = tx.photometric_loss(es, ta, 9, TYPES[ty], 0.5)
+    (g,) = torch.autograd.grad(out, es, go)
+    assert_close(out.detach().cpu().numpy(), ref.detach().cpu().numpy(), tol=1e-10, what="fwd")
+    assert_close(g.cpu().numpy(), gref.cpu().numpy(), tol=1e-9, what="bwd")
+
+
+def test_photometric_empty_and_errors(tx):
+    e = torch.zeros(0, 1, 16, 16, device=DEV)
+    assert tx.photometric_loss(e, e, 9, "sad").shape == (0, 1, 16, 16)
+    x = torch.randn(1, 1, 16, 16, device=DEV)
+    with pytest.raises(Exception, match="invalid loss type"):
+        tx.photometric_loss(x, x, 9, "ssim")
+    with pytest.raises(RuntimeError):
+        tx.photometric_loss(x.transpose(2, 3), x, 9, "sad")          # non-contiguous
+    with pytest.raises(NotImplementedError):
+        tx.photometric_loss(x.half(), x.half(), 9, "sad")
+    with pytest.raises(RuntimeError):
+        tx.photometric_loss(x.cpu(), x.cpu(), 9, "sad")              # no CPU path
+    with pytest.raises(RuntimeError):
+        tx.photometric_loss(x, x[:, :, :8].contiguous(), 9, "sad")   # shape mismatch
+    assert tx.photometric_loss(x, x, 9, "MSE").abs().max().item() == 0  # case-insensitive type
+
+
+# ---------------------------------------------------------------- LCN
+@pytest.mark.parametrize("r,e", ((5, 0.05), (2, 0.1)))
+def test_lcn_golden(tx, golden, r, e):
+    """vs the reference torch module: same bound as the oracle's own test (the reference's fp32 conv
+    summation order is unspecified and var cancels on flat regions)."""
+    g = golden("lcn")
+    l, s = tx.lcn(cu(g["x"]), r, e)
+    l, s = l.cpu().numpy(), s.cpu().numpy()
+    assert np.abs(s - g[f"r{r}_std"]).max() <= 2e-4 * np.abs(g[f"r{r}_std"]).max()
+    assert np.abs(l - g[f"r{r}_lcn"]).max() <= 2e-4 * np.abs(g[f"r{r}_lcn"]).max()
+    lo, so = oracle.lcn(g["x"], r, e)
+    assert_close(l, lo, what="lcn vs oracle")
+    assert_close(s, so, what="std vs oracle")
+
+
+@pytest.mark.parametrize("shape", [(1, 480, 640, 5), (3, 37, 130, 5), (2, 16, 12, 3), (1, 61, 259, 7), (1, 40, 40, 17),
+                                   (1, 6, 6, 5), (2, 100, 128, 0), (1, 9, 1000, 2)])
+def test_lcn_vs_oracle(tx, shape):
+    N, H, W, r = shape
+    rng = np.random.RandomState(N * 7 + H)
+    x = rng.rand(N, 1, H, W).astype(np.float32)
+    x[0, 0, : H // 2, : W // 2] = 0.5   # flat region: var collapses to the 1e-6 floor
+    l, s = tx.lcn(cu(x), r, 0.05)
+    lo, so = oracle.lcn(x, r, 0.05)
+    assert_close(l.cpu().numpy(), lo, what="lcn")
+    assert_close(s.cpu().numpy(), so, what="std")
+    mod = tx.LCN(r, 0.05)
+    l2, s2 = mod(cu(x))
+    assert torch.equal(l2, l) and torch.equal(s2, s)
+
+
+def test_lcn_f64_and_errors(tx):
+    rng = np.random.RandomState(2)
+    x = rng.rand(2, 1, 30, 50)
+    l, s = tx.lcn(cu(x), 5, 0.05)
+    lo, so = oracle.lcn(x, 5, 0.05)
+    assert_close(l.cpu().numpy(), lo, tol=1e-12)
+    assert_close(s.cpu().numpy(), so, tol=1e-12)
+    with pytest.raises(RuntimeError):
+        tx.lcn(torch.rand(1, 1, 4, 40, device=DEV), 5, 0.05)   # radius >= height: ReflectionPad2d refuses too
+    with pytest.raises(RuntimeError):
+        tx.lcn(torch.rand(1, 2, 40, 40, device=DEV), 5, 0.05)  # single channel only (networks.py:514)
+
+
+# ---------------------------------------------------------------- xcorrvol
+def test_xcorrvol_golden(tx, golden):
+    g = golden("xcorrvol")
+    for k in [k[:-4] for k in g.files if k.endswith("_in0")]:
+        D = int(k.split("_D")[1].split("_")[0])
+        bs = int(k.split("_bs")[1])
+        got = tx.xcorrvol(cu(g[k + "_in0"]), cu(g[k + "_in1"]), D, bs)
+        assert_close(got.cpu().numpy(), g[k + "_out"], what=k)
+    flat = np.full((1, 6, 8), 0.25, np.float32)
+    assert_close(tx.xcorrvol(cu(flat), cu(flat), 3, 3).cpu().numpy() + 1, g["flat_out"] + 1, what="flat")
+    assert_close(tx.xcorrvol(cu(g["self_in"]), cu(g["self_in"]), 1, 3).cpu().numpy(), g["self_out"], what="self")
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 40, 150, 32, 9), (2, 1, 24, 70, 17, 9), (1, 2, 20, 40, 8, 5), (1, 1, 9, 33, 40, 9),
+                                   (1, 1, 30, 64, 5, 3), (1, 3, 12, 20, 4, 2)])
+def test_xcorrvol_vs_oracle(tx, shape):
+    B, C, H, W, D, bs = shape
+    rng = np.random.RandomState(D)
+    a = rng.randn(B, C, H, W).astype(np.float32)
+    b = (np.roll(a, 3, axis=3) + 0.3 * rng.randn(B, C, H, W)).astype(np.float32)
+    got = tx.xcorrvol(cu(a), cu(b), D, bs).cpu().numpy()
+    assert got.shape == (B, D, H, W)
+    for i in range(B):
+        assert_close(got[i], oracle.xcorrvol(a[i], b[i], D, bs), what="batched image %d" % i)
+    one = tx.xcorrvol(cu(a[0]), cu(b[0]), D, bs).cpu().numpy()  # the reference's 3-D signature
+    assert one.shape == (D, H, W)
+    assert np.array_equal(one, got[0])
+
+
+def test_xcorrvol_synthetic_lcn_data(tx):
+    """LCN'd dot-pattern rows (the BASELINE config 3 data) on a crop the oracle finishes quickly."""
+    from connecting_the_dots_b200 import synth
+    d = synth.make_pair(0, 96, 256)
+    a, b = d["ta"][None], d["pat_lcn"][None]
+    got = tx.xcorrvol(cu(a), cu(b), 48, 9).cpu().numpy()
+    assert_close(got, oracle.xcorrvol(a, b, 48, 9), what="lcn crop")
+
+
+# ---------------------------------------------------------------- proj_nn / nn / crosscheck: bit-exact
+@pytest.mark.parametrize("ps", (1, 2, 3, 5, 9))
+def test_proj_nn_golden(tx, golden, ps):
+    g = golden("proj_nn")
+    got = tx.proj_nn(cu(g["xyz0"]), cu(g["xyz1"]), cu(g["K"]), ps)
+    assert got.dtype == torch.int64
+    assert np.array_equal(got.cpu().numpy(), g[f"ps{ps}"])
+
+
+@pytest.mark.parametrize("dt", (np.float32, np.float64))
+def test_proj_nn_vs_oracle(tx, dt):
+    from connecting_the_dots_b200 import synth
+    xyz, K, poses = synth.make_clouds(3, 120, 160, seed=3)
+    K = K.astype(dt)
+    for ps in (3, 5):
+        for i, j in ((0, 1), (1, 2), (2, 0)):
+            x0 = synth.transform(xyz[i], poses[j]).astype(dt)[None]
+            x1 = xyz[j].astype(dt)[None]
+            x0[0, 0, :4] = [[1, 1, 0], [0, 0, 0], [np.nan, 1, 1], [1e30, 1, 1e-8]]
+            got = tx.proj_nn(cu(x0), cu(x1), cu(K), ps).cpu().numpy()
+            want = oracle.proj_nn(x0, x1, K, ps)
+            assert np.array_equal(got, want)
+            assert (want >= 0).mean() > 0.5
+    xb = np.stack([xyz[0], xyz[1]]).astype(dt)
+    got = tx.proj_nn(cu(xb), cu(xb[::-1].copy()), cu(K), 3).cpu().numpy()   # batch offset in the flat index
+    assert np.array_equal(got, oracle.proj_nn(xb, xb[::-1].copy(), K, 3))
+
+
+def test_nn_golden_and_split(tx, golden):
+    g = golden("nn")
+    assert np.array_equal(tx.nn(cu(g["p0"]), cu(g["p1"])).cpu().numpy(), g["idx"])
+    assert np.array_equal(tx.nn(cu(g["p0"][:5]), cu(g["p1"][:0].reshape(0, 3))).cpu().numpy(), g["idx_empty"])
+    rng = np.random.RandomState(21)
+    for n0, n1, dt in ((1000, 5000, np.float32), (777, 4099, np.float32), (300, 2500, np.float64), (5000, 300, np.float32)):
+        p0 = rng.randn(n0, 3).astype(dt)
+        p1 = rng.randn(n1, 3).astype(dt)
+        p1[n1 // 2:] = p1[: n1 - n1 // 2]          # every point twice: ties across in1 chunks -> lowest index
+        p0[3] = [np.nan, 0, 0]
+        p0[4] = [4e4, 0, 0]
+        assert np.array_equal(tx.nn(cu(p0), cu(p1)).cpu().numpy(), oracle.nn(p0, p1)), (n0, n1, dt)
+
+
+def test_crosscheck(tx, golden):
+    g = golden("crosscheck")
+    got = tx.crosscheck(cu(g["in0"]), cu(g["in1"]))
+    assert got.dtype == torch.uint8
+    assert np.array_equal(got.cpu().numpy(), g["out"])
+    assert tx.crosscheck(cu(g["kat_in0"]), cu(g["kat_in1"])).cpu().tolist() == [1, 1, 0, 0, 0]
+    rng = np.random.RandomState(4)
+    for n in (1, 3, 1001, 307200):
+        perm = rng.permutation(n).astype(np.int64)
+        inv = np.empty(n, np.int64)
+        inv[perm] = np.arange(n)
+        perm[rng.rand(n) < 0.1] = -1
+        inv[rng.rand(n) < 0.1] = rng.randint(-1, n)
+        assert np.array_equal(tx.crosscheck(cu(perm), cu(inv)).cpu().numpy(), oracle.crosscheck(perm, inv))
+        assert np.array_equal(tx.crosscheck(cu(perm[1:]), cu(inv)).cpu().numpy(), oracle.crosscheck(perm[1:], inv))
+    wide = np.array([2**32 + 1, 1], np.int64)   # int64 -> int32 truncation of the index (ext.h:59)
+    back = np.array([5, 0], np.int64)
+    assert np.array_equal(tx.crosscheck(cu(wide), cu(back)).cpu().numpy(), oracle.crosscheck(wide, back))
+    with pytest.raises(RuntimeError):
+        tx.crosscheck(cu(perm).view(1, -1), cu(inv))
+
+
+def test_geometric_step_composition(tx):
+    """BASELINE config 4 as composed in SURVEY.md section 8d: for a 4-frame track, proj_nn both ways
+    for each frame pair + crosscheck both ways; checked bit-exact against the oracle."""
+    from connecting_the_dots_b200 import synth
+    xyz, K, poses = synth.make_clouds(4, 60, 80, seed=1)
+    Kd = cu(K)
+    for i in range(4):
+        for j in range(i + 1, 4):
+            xij, xji = synth.transform(xyz[i], poses[j])[None], synth.transform(xyz[j], poses[i])[None]
+            i01 = tx.proj_nn(cu(xij), cu(xyz[j][None]), Kd, 3)
+            i10 = tx.proj_nn(cu(xji), cu(xyz[i][None]), Kd, 3)
+            m01 = tx.crosscheck(i01.view(-1), i10.view(-1))
+            m10 = tx.crosscheck(i10.view(-1), i01.view(-1))
+            o01, o10 = oracle.proj_nn(xij, xyz[j][None], K, 3), oracle.proj_nn(xji, xyz[i][None], K, 3)
+            assert np.array_equal(i01.cpu().numpy(), o01) and np.array_equal(i10.cpu().numpy(), o10)
+            assert np.array_equal(m01.cpu().numpy(), oracle.crosscheck(o01.ravel(), o10.ravel()))
+            assert np.array_equal(m10.cpu().numpy(), oracle.crosscheck(o10.ravel(), o01.ravel()))
+
+
+# ---------------------------------------------------------------- host-buffer C ABI
+def test_host_api(golden):
+    from connecting_the_dots_b200 import _lib
+    L = _lib.lib()
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rng = np.random.RandomState(12)
+    es = rng.randn(2, 1, 40, 72).astype(np.float32)
+    ta = rng.randn(2, 1, 40, 72).astype(np.float32)
+    go = rng.rand(2, 1, 40, 72).astype(np.float32)
+    out, gi = np.empty_like(go), np.empty_like(es)
+    _lib.call("ctd_host_photometric_fwd_bwd_f32", P(es), P(ta), P(go), P(out), P(gi), 2, 1, 40, 72, 9, 3, 0.5)
+    assert_close(out, oracle.photometric_loss_forward(es, ta, 9, 3, 0.5))
+    assert_close(gi, oracle.photometric_loss_backward(es, ta, go, 9, 3, 0.5))
+    out2 = np.empty_like(go)
+    _lib.call("ctd_host_photometric_fwd_f32", P(es), P(ta), P(out2), 2, 1, 40, 72, 9, 3, 0.5)
+    assert np.array_equal(out, out2)
+    l, s = np.empty_like(es), np.empty_like(es)
+    _lib.call("ctd_host_lcn_f32", P(es), P(l), P(s), 2, 40, 72, 5, 0.05)
+    lo, so = oracle.lcn(es, 5, 0.05)
+    assert_close(l, lo)
+    assert_close(s, so)
+    g = golden("proj_nn")
+    idx = np.empty(g["ps3"].shape, np.int64)
+    B, H, W, _ = g["xyz0"].shape
+    _lib.call("ctd_host_proj_nn_f32", P(g["xyz0"]), P(g["xyz1"]), P(g["K"]), P(idx), B, H, W, 3)
+    assert np.array_equal(idx, g["ps3"])
+    g = golden("nn")
+    idx = np.empty(len(g["p0"]), np.int64)
+    _lib.call("ctd_host_nn_f32", P(g["p0"]), P(g["p1"]), P(idx), len(g["p0"]), len(g["p1"]))
+    assert np.array_equal(idx, g["idx"])
+    g = golden("crosscheck")
+    m = np.empty(len(g["in0"]), np.uint8)
+    _lib.call("ctd_host_crosscheck", P(g["in0"]), P(g["in1"]), P(m), len(g["in0"]), len(g["in1"]))
+    assert np.array_equal(m, g["out"])
+    g = golden("xcorrvol")
+    k = "C1_H10_W24_D6_bs9"
+    vol = np.empty_like(g[k + "_out"])
+    _lib.call("ctd_host_xcorrvol_f32", P(g[k + "_in0"]), P(g[k + "_in1"]), P(vol), 1, 1, 10, 24, 6, 9)
+    assert_close(vol, g[k + "_out"])
+    with pytest.raises(_lib.CtdError, match="invalid loss type"):
+        _lib.call("ctd_host_photometric_fwd_f32", P(es), P(ta), P(out2), 2, 1, 40, 72, 9, 7, 0.5)
+    assert _lib.launch_count() > 0
+    L.ctd_host_release()
+
+
+def test_runs_on_current_stream_and_device(tx):
+    """Launches go to torch's current stream (the reference uses the legacy default stream)."""
+    x = torch.randn(2, 1, 64, 64, device=DEV)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        y = x * 2                      # produced on s; the op below must be ordered after it on s
+        out = tx.photometric_loss(y, x, 9, "sad")
+    s.synchronize()
+    assert_close(out.cpu().numpy(), oracle.photometric_loss_forward((x * 2).cpu().numpy(), x.cpu().numpy(), 9, 1, 0.1))
+
+
+def test_masked_sums(tx):
+    """(mask*diff).sum() and mask.sum() of model/networks.py:377 in one deterministic kernel."""
+    rng = np.random.RandomState(6)
+    for n in (1, 5, 4096, 8 * 480 * 640, 1000003):
+        d = rng.rand(n).astype(np.float32)
+        m = rng.rand(n).astype(np.float32)
+        a = tx.masked_mean_terms(cu(d), cu(m))
+        b = tx.masked_mean_terms(cu(d), cu(m))
+        assert torch.equal(a, b)
+        want = np.array([(m.astype(np.float64) * d).sum(), m.astype(np.float64).sum()])
+        assert np.abs(a.cpu().numpy() - want).max() <= 2e-6 * want.max()
