@@ -461,16 +461,41 @@ photo_fwd_census9(const float* __restrict__ es, const float* __restrict__ ta, fl
   }
 }
 
-// IEEE restatement of the reference's soft step difference, used only to decide sign() on near-ties
-__device__ __noinline__ void census_exact_signs(float des, float dta, float eps, float* s_tap, float* s_ctr) {
-  // pixel as the tap of the neighbour (des = es_i - es_q) ...
-  const float q1 = __fdiv_rn(des, __fsqrt_rn(__fadd_rn(__fmul_rn(des, des), eps)));
-  const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
-  const float d1 = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
-  // ... and as the centre (des = es_q - es_i = -des exactly; the quotients flip sign exactly)
-  const float d2 = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
-  *s_tap = sgn(d1);
-  *s_ctr = sgn(d2);
+// census_sad backward takes sign(h(des) - h(dta)); the fast path evaluates the difference with
+// rsqrt.approx (|error| < ~1.2e-6 on dd = 2 * difference), so any pixel with a term closer to zero than
+// SIGN_GUARD is recomputed here with the reference's own IEEE operation sequence (ext.h:321-330): the
+// sign decisions -- and therefore the gradient -- then match the CPU extension exactly.
+constexpr float SIGN_GUARD = 4e-6f;
+
+// One pixel (tile-local row yl, column xl), all 81 taps, exact signs.  mx/my: clamp multiplicity of the
+// column/row offset as base + slope * offset.  Returns the unscaled sum (caller applies eps/(2*81)).
+__device__ __noinline__ float census_sad_bwd_exact_pixel(const float* __restrict__ Es, const float* __restrict__ Ts,
+                                                         const float* __restrict__ Gs, int yl, int xl, float eps,
+                                                         float bx, float sx, float by, float sy) {
+  const float ec = Es[(yl + R9) * CE_W + xl + R9], tc = Ts[(yl + R9) * CE_W + xl + R9], gc = Gs[(yl + R9) * CE_W + xl + R9];
+  float acc = 0.f;
+  for (int dy = 0; dy < 9; ++dy) {
+    const float my = fmaf(sy, float(dy - R9), by);
+    for (int dx = 0; dx < 9; ++dx) {
+      const int o = (yl + dy) * CE_W + xl + dx;
+      const float des = ec - Es[o], dta = tc - Ts[o];
+      const float gq = Gs[o] * (my * fmaf(sx, float(dx - R9), bx));
+      const float s = __fadd_rn(__fmul_rn(des, des), eps);
+      const float q1 = __fdiv_rn(des, __fsqrt_rn(s));
+      const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
+      // this pixel as the tap of centre q (des = es_i - es_q) ...
+      const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
+      // ... and as the centre with q as the tap: des flips sign exactly, so do the quotients
+      const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
+      const float r1 = rsqrt_approx(s);
+      acc = fmaf(r1 * r1 * r1, sgn(d_tap) * gq - sgn(d_ctr) * gc, acc);
+    }
+  }
+  return acc;
+}
+
+__device__ __forceinline__ float xor_sign(float v, float s) {  // v * sign(s) for s != 0
+  return __int_as_float(__float_as_int(v) ^ (__float_as_int(s) & 0x80000000));
 }
 
 // grad_in[i] = eps/(2*81) * sum_q gl(dd) * r1^3 * (M(i,q) * go[q] + go[i]) over the 9x9 window of i:
@@ -492,12 +517,12 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
     const float ec[4] = {ec4.x, ec4.y, ec4.z, ec4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
     const float gc[4] = {gc4.x, gc4.y, gc4.z, gc4.w};
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float near0[4] = {1.f, 1.f, 1.f, 1.f};  // census_sad: smallest |dd| over the non-centre taps
     // clamp multiplicity of the column / row offset d (-4..4): base + slope * d
-    float bx[4], sx[4], by = 1.f, sy = 0.f;
+    float bx[4] = {1.f, 1.f, 1.f, 1.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, by = 1.f, sy = 0.f;
     if (BORDER) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        bx[k] = 1.f; sx[k] = 0.f;
         if (gx + k == 0) { bx[k] = 5.f; sx[k] = -1.f; }
         if (gx + k == W - 1) { bx[k] = 5.f; sx[k] = 1.f; }
       }
@@ -511,6 +536,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
       unpack12(t, &Ts[yl + dy][4 * tx]);
       unpack12(g, &Gs[yl + dy][4 * tx]);
       const float my = BORDER ? fmaf(sy, float(dy - R9), by) : 1.f;
+      const bool ctr_row = dy == R9;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -526,16 +552,23 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
           if (TYPE == 2) {
             acc[k] = fmaf(dd * r3, gq + gc[k], acc[k]);
           } else {
-            if (fabsf(dd) < 1e-5f) {
-              float s1, s2;
-              census_exact_signs(des, dta, eps, &s1, &s2);
-              acc[k] = fmaf(r3, s1 * gq - s2 * gc[k], acc[k]);
-            } else {
-              acc[k] += copysignf(r3 * (gq + gc[k]), dd);
+            float term = xor_sign(r3 * (gq + gc[k]), dd);
+            float mag = fabsf(dd);
+            if (dx == R9) {  // the centre tap itself: dd == 0, sign(0) = 0, and it is not a near-tie
+              term = ctr_row ? 0.f : term;
+              mag = ctr_row ? 1.f : mag;
             }
+            acc[k] += term;
+            near0[k] = fminf(near0[k], mag);
           }
         }
       }
+    }
+    if (TYPE == 3) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (near0[k] < SIGN_GUARD)
+          acc[k] = census_sad_bwd_exact_pixel(&Es[0][0], &Ts[0][0], &Gs[0][0], yl, 4 * tx + k, eps, bx[k], sx[k], by, sy);
     }
     const float scale = 0.5f * eps * INV81;
     float* dst = gi + (int64_t)gy * W + gx;

@@ -1,0 +1,141 @@
+#!/usr/bin/env python
+"""Per-op device timings of every kernel family on the BASELINE.json configs (CUDA events on the
+launching stream, rotating buffer sets larger than L2 where the op is HBM-bound).  Prints one JSON
+object; bench.py stays the contract benchmark, this is the per-op table that goes into profiles/.
+
+    python tools/bench_ops.py [--iters 30] [--only photometric,lcn,xcorrvol,proj_nn,nn,crosscheck]
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import connecting_the_dots_b200 as ctd  # noqa: E402
+from connecting_the_dots_b200 import _lib, synth  # noqa: E402
+
+H, W = 480, 640
+PEAK = 6453.4
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    pass
+
+
+def timeit(fn, iters, warmup=5):
+    for i in range(warmup):
+        fn(i)
+    torch.cuda.synchronize()
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
+    evs[0].record()
+    for i in range(iters):
+        fn(i)
+        evs[i + 1].record()
+    torch.cuda.synchronize()
+    ts = [evs[i].elapsed_time(evs[i + 1]) for i in range(iters)]
+    return float(np.median(ts)), float(np.min(ts))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--only", default="photometric,lcn,xcorrvol,proj_nn,nn,crosscheck,reduce")
+    ap.add_argument("--batch", type=int, default=8)
+    args = ap.parse_args()
+    only = set(args.only.split(","))
+    dev = torch.device("cuda", 0)
+    tx = ctd.torchext
+    B = args.batch
+    npx = B * H * W
+    res = {"batch": B, "height": H, "width": W, "peak_gbs": PEAK, "ops": {}}
+
+    def add(name, ms, ms_min, bytes_, px=npx, extra=None):
+        r = {"ms_median": ms, "ms_min": ms_min, "mpix_s": px / ms / 1e3, "algo_bytes": bytes_,
+             "achieved_gbs": bytes_ / ms / 1e6, "frac_hbm": bytes_ / ms / 1e6 / PEAK}
+        if extra:
+            r.update(extra)
+        res["ops"][name] = r
+        print(name, json.dumps(r), file=sys.stderr, flush=True)
+
+    NS = 5
+    base = synth.make_batch(B, H, W)
+    sets = []
+    for s in range(NS):
+        d = {k: torch.from_numpy(np.ascontiguousarray(np.roll(base[k], 5 * s, axis=2))).to(dev) for k in ("im", "es", "ta", "go", "std", "pat_lcn")}
+        d["o1"] = torch.empty(B, 1, H, W, device=dev)
+        d["o2"] = torch.empty(B, 1, H, W, device=dev)
+        sets.append(d)
+    st = torch.cuda.current_stream().cuda_stream
+
+    if "photometric" in only:
+        for ty, name in enumerate(("mse", "sad", "census_mse", "census_sad")):
+            def f(i, ty=ty):
+                d = sets[i % NS]
+                _lib.call("ctd_photometric_fwd_f32", d["es"].data_ptr(), d["ta"].data_ptr(), d["o1"].data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
+            def g(i, ty=ty):
+                d = sets[i % NS]
+                _lib.call("ctd_photometric_bwd_f32", d["es"].data_ptr(), d["ta"].data_ptr(), d["go"].data_ptr(), d["o2"].data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
+            add(name + "_fwd", *timeit(f, args.iters), 12 * npx)
+            add(name + "_bwd", *timeit(g, args.iters), 16 * npx)
+    if "lcn" in only:
+        def f(i):
+            d = sets[i % NS]
+            _lib.call("ctd_lcn_f32", d["im"].data_ptr(), d["o1"].data_ptr(), d["o2"].data_ptr(), B, H, W, 5, 0.05, st)
+        add("lcn_fwd", *timeit(f, args.iters), 12 * npx)
+    if "reduce" in only:
+        ws = torch.zeros(int(_lib.lib().ctd_masked_sums_workspace_bytes()), dtype=torch.uint8, device=dev)
+        out2 = torch.zeros(2, device=dev)
+        def f(i):
+            d = sets[i % NS]
+            _lib.call("ctd_masked_sums_f32", d["es"].data_ptr(), d["std"].data_ptr(), npx, out2.data_ptr(), ws.data_ptr(), st)
+        add("masked_sums", *timeit(f, args.iters), 8 * npx)
+    if "xcorrvol" in only:
+        D = 128
+        vols = [torch.empty(B, D, H, W, device=dev) for _ in range(2)]
+        for bs in (9, 5):
+            def f(i, bs=bs):
+                d = sets[i % NS]
+                _lib.call("ctd_xcorrvol_f32", d["ta"].data_ptr(), d["pat_lcn"].data_ptr(), vols[i % 2].data_ptr(), B, 1, H, W, D, bs, st)
+            add("xcorrvol_D128_bs%d" % bs, *timeit(f, max(3, args.iters // 6), warmup=1), (8 + 4 * D) * npx)
+        del vols
+    if "proj_nn" in only:
+        T = 4
+        xyz, K, poses = synth.make_clouds(T, H, W)
+        Kd = torch.from_numpy(K).to(dev)
+        pairs = [(i, j) for i in range(T) for j in range(T) if i != j]
+        x0 = torch.from_numpy(np.stack([synth.transform(xyz[i], poses[j]) for i, j in pairs])).to(dev)   # [12,H,W,3]
+        x1 = torch.from_numpy(np.stack([xyz[j] for i, j in pairs])).to(dev)
+        out = torch.empty(len(pairs), H, W, dtype=torch.int64, device=dev)
+        for ps in (3, 5):
+            def f(i, ps=ps):
+                _lib.call("ctd_proj_nn_f32", x0.data_ptr(), x1.data_ptr(), Kd.data_ptr(), out.data_ptr(), len(pairs), H, W, ps, st)
+            add("proj_nn_ps%d_12pairs" % ps, *timeit(f, args.iters), 32 * len(pairs) * H * W, px=len(pairs) * H * W,
+                extra={"valid_frac": float((out >= 0).float().mean())})
+        if "crosscheck" in only:
+            n = len(pairs) * H * W
+            i01 = out.view(-1)
+            i10 = out.view(len(pairs), -1).flip(0).contiguous().view(-1)
+            m = torch.empty(n, dtype=torch.uint8, device=dev)
+            def f(i):
+                _lib.call("ctd_crosscheck", i01.data_ptr(), i10.data_ptr(), m.data_ptr(), n, n, st)
+            add("crosscheck_%d" % n, *timeit(f, args.iters), 17 * n, px=n)
+    if "nn" in only:
+        n = 16384
+        rng = np.random.RandomState(0)
+        p0 = torch.from_numpy(rng.randn(n, 3).astype(np.float32)).to(dev)
+        p1 = torch.from_numpy(rng.randn(n, 3).astype(np.float32)).to(dev)
+        out = torch.empty(n, dtype=torch.int64, device=dev)
+        def f(i):
+            _lib.call("ctd_nn_f32", p0.data_ptr(), p1.data_ptr(), out.data_ptr(), n, n, st)
+        ms, mn = timeit(f, args.iters)
+        res["ops"]["nn_16384x16384"] = {"ms_median": ms, "ms_min": mn, "gpair_s": n * n / ms / 1e6}
+        print("nn", res["ops"]["nn_16384x16384"], file=sys.stderr)
+    print(json.dumps(res))
+
+
+if __name__ == "__main__":
+    main()
