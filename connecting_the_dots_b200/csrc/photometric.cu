@@ -463,33 +463,29 @@ photo_fwd_census9(const float* __restrict__ es, const float* __restrict__ ta, fl
 
 // census_sad backward takes sign(h(des) - h(dta)); the fast path evaluates the difference with
 // rsqrt.approx (|error| < ~1.2e-6 on dd = 2 * difference), so any pixel with a term closer to zero than
-// SIGN_GUARD is recomputed here with the reference's own IEEE operation sequence (ext.h:321-330): the
+// SIGN_GUARD has that window row recomputed here with the reference's own IEEE operation sequence (ext.h:321-330): the
 // sign decisions -- and therefore the gradient -- then match the CPU extension exactly.
-constexpr float SIGN_GUARD = 4e-6f;
+constexpr float SIGN_GUARD = 3e-6f;
 
-// One pixel (tile-local row yl, column xl), all 81 taps, exact signs.  mx/my: clamp multiplicity of the
-// column/row offset as base + slope * offset.  Returns the unscaled sum (caller applies eps/(2*81)).
-__device__ __noinline__ float census_sad_bwd_exact_pixel(const float* __restrict__ Es, const float* __restrict__ Ts,
-                                                         const float* __restrict__ Gs, int yl, int xl, float eps,
-                                                         float bx, float sx, float by, float sy) {
-  const float ec = Es[(yl + R9) * CE_W + xl + R9], tc = Ts[(yl + R9) * CE_W + xl + R9], gc = Gs[(yl + R9) * CE_W + xl + R9];
+// One window row (9 taps, tile row `row`) of one pixel (tile column xl, centre values ec/tc/gc) with
+// exact signs.  mx = bx + sx * offset and my are the clamp multiplicities.  Returns the unscaled sum.
+__device__ __noinline__ float census_sad_bwd_exact_row(const float* __restrict__ Es, const float* __restrict__ Ts,
+                                                       const float* __restrict__ Gs, int row, int xl, float ec,
+                                                       float tc, float gc, float eps, float bx, float sx, float my) {
   float acc = 0.f;
-  for (int dy = 0; dy < 9; ++dy) {
-    const float my = fmaf(sy, float(dy - R9), by);
-    for (int dx = 0; dx < 9; ++dx) {
-      const int o = (yl + dy) * CE_W + xl + dx;
-      const float des = ec - Es[o], dta = tc - Ts[o];
-      const float gq = Gs[o] * (my * fmaf(sx, float(dx - R9), bx));
-      const float s = __fadd_rn(__fmul_rn(des, des), eps);
-      const float q1 = __fdiv_rn(des, __fsqrt_rn(s));
-      const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
-      // this pixel as the tap of centre q (des = es_i - es_q) ...
-      const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
-      // ... and as the centre with q as the tap: des flips sign exactly, so do the quotients
-      const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
-      const float r1 = rsqrt_approx(s);
-      acc = fmaf(r1 * r1 * r1, sgn(d_tap) * gq - sgn(d_ctr) * gc, acc);
-    }
+  for (int dx = 0; dx < 9; ++dx) {
+    const int o = row * CE_W + xl + dx;
+    const float des = ec - Es[o], dta = tc - Ts[o];
+    const float gq = Gs[o] * (my * fmaf(sx, float(dx - R9), bx));
+    const float s = __fadd_rn(__fmul_rn(des, des), eps);
+    const float q1 = __fdiv_rn(des, __fsqrt_rn(s));
+    const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
+    // this pixel as the tap of centre q (des = es_i - es_q) ...
+    const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
+    // ... and as the centre with q as the tap: des flips sign exactly, so do the quotients
+    const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
+    const float r1 = rsqrt_approx(s);
+    acc = fmaf(r1 * r1 * r1, sgn(d_tap) * gq - sgn(d_ctr) * gc, acc);
   }
   return acc;
 }
@@ -517,7 +513,6 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
     const float ec[4] = {ec4.x, ec4.y, ec4.z, ec4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
     const float gc[4] = {gc4.x, gc4.y, gc4.z, gc4.w};
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float near0[4] = {1.f, 1.f, 1.f, 1.f};  // census_sad: smallest |dd| over the non-centre taps
     // clamp multiplicity of the column / row offset d (-4..4): base + slope * d
     float bx[4] = {1.f, 1.f, 1.f, 1.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, by = 1.f, sy = 0.f;
     if (BORDER) {
@@ -539,6 +534,8 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
       const bool ctr_row = dy == R9;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
+        float racc = 0.f;   // this window row's contribution to pixel k
+        float rmin = 1.f;   // census_sad: smallest |dd| in the row (centre tap excluded)
 #pragma unroll
         for (int dx = 0; dx < 9; ++dx) {
           const float des = ec[k] - e[k + dx];
@@ -550,7 +547,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
           float gq = g[k + dx];
           if (BORDER) gq *= my * fmaf(sx[k], float(dx - R9), bx[k]);
           if (TYPE == 2) {
-            acc[k] = fmaf(dd * r3, gq + gc[k], acc[k]);
+            racc = fmaf(dd * r3, gq + gc[k], racc);
           } else {
             float term = xor_sign(r3 * (gq + gc[k]), dd);
             float mag = fabsf(dd);
@@ -558,17 +555,15 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
               term = ctr_row ? 0.f : term;
               mag = ctr_row ? 1.f : mag;
             }
-            acc[k] += term;
-            near0[k] = fminf(near0[k], mag);
+            racc += term;
+            rmin = fminf(rmin, mag);
           }
         }
+        if (TYPE == 3 && rmin < SIGN_GUARD)
+          racc = census_sad_bwd_exact_row(&Es[0][0], &Ts[0][0], &Gs[0][0], yl + dy, 4 * tx + k, ec[k], tc[k], gc[k],
+                                          eps, bx[k], sx[k], my);
+        acc[k] += racc;
       }
-    }
-    if (TYPE == 3) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (near0[k] < SIGN_GUARD)
-          acc[k] = census_sad_bwd_exact_pixel(&Es[0][0], &Ts[0][0], &Gs[0][0], yl, 4 * tx + k, eps, bx[k], sx[k], by, sy);
     }
     const float scale = 0.5f * eps * INV81;
     float* dst = gi + (int64_t)gy * W + gx;
