@@ -8,6 +8,7 @@
 namespace ctd {
 
 int g_force_generic = 0;  // tests: route every op through its generic kernel
+int g_disable_tma = 0;    // tests / A-B runs: use the shared-memory tile kernels instead of the TMA ones
 static std::atomic<uint64_t> g_launches{0};
 
 char* err_buf() {
@@ -45,5 +46,43 @@ CTD_API int ctd_set_option(const char* name, int value) {
     ctd::g_force_generic = value;
     return CTD_OK;
   }
+  if (name && !strcmp(name, "disable_tma")) {
+    ctd::g_disable_tma = value;
+    return CTD_OK;
+  }
   return ctd::fail(CTD_ERR_INVALID, "ctd_set_option: unknown option '%s'", name ? name : "(null)");
 }
+
+// ---- TMA tensor-map encoder (driver entry point fetched through the runtime, no -lcuda needed)
+#include "ctd_tma.cuh"
+namespace ctd {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+bool make_plane_tensor_map(CUtensorMap* map, const float* base, int64_t planes, int64_t H, int64_t W, int box_w, int box_h) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(base) & 15) || W % 4 || planes < 1 || H < 1 || W < 4) return false;
+  if (box_w > 256 || box_h > 256 || (box_w * 4) % 16) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)planes};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace ctd

@@ -22,6 +22,10 @@
 namespace ctd {
 
 extern int g_force_generic;
+int box9_tma_fwd(const float* es, const float* ta, float* out, int64_t B, int64_t C, int64_t H, int64_t W, int type,
+                 cudaStream_t st);
+int box9_tma_bwd(const float* es, const float* ta, const float* go, float* gi, int64_t B, int64_t C, int64_t H,
+                 int64_t W, int type, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // generic kernels (any block size, channel count, size; float or double)
@@ -462,32 +466,63 @@ photo_fwd_census9(const float* __restrict__ es, const float* __restrict__ ta, fl
 }
 
 // census_sad backward takes sign(h(des) - h(dta)); the fast path evaluates the difference with
-// rsqrt.approx (|error| < ~1.2e-6 on dd = 2 * difference), so any pixel with a term closer to zero than
-// SIGN_GUARD has that window row recomputed here with the reference's own IEEE operation sequence (ext.h:321-330): the
-// sign decisions -- and therefore the gradient -- then match the CPU extension exactly.
+// rsqrt.approx (|error| < ~1.2e-6 on dd = 2 * difference).  A pixel whose window holds a term closer to
+// zero than SIGN_GUARD is not trusted: the tile kernel stores SIGN_MARKER (a NaN payload) instead, and
+// census_sad_bwd_fixup recomputes exactly those pixels with the reference's own IEEE operation
+// sequence (ext.h:321-330), one warp per pixel.  The sign decisions -- and therefore the gradient --
+// then match the CPU extension exactly, and the hot loop stays branch-free.
 constexpr float SIGN_GUARD = 3e-6f;
+constexpr unsigned SIGN_MARKER = 0x7fc5a5a5u;
 
-// One window row (9 taps, tile row `row`) of one pixel (tile column xl, centre values ec/tc/gc) with
-// exact signs.  mx = bx + sx * offset and my are the clamp multiplicities.  Returns the unscaled sum.
-__device__ __noinline__ float census_sad_bwd_exact_row(const float* __restrict__ Es, const float* __restrict__ Ts,
-                                                       const float* __restrict__ Gs, int row, int xl, float ec,
-                                                       float tc, float gc, float eps, float bx, float sx, float my) {
-  float acc = 0.f;
-  for (int dx = 0; dx < 9; ++dx) {
-    const int o = row * CE_W + xl + dx;
-    const float des = ec - Es[o], dta = tc - Ts[o];
-    const float gq = Gs[o] * (my * fmaf(sx, float(dx - R9), bx));
-    const float s = __fadd_rn(__fmul_rn(des, des), eps);
-    const float q1 = __fdiv_rn(des, __fsqrt_rn(s));
-    const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
-    // this pixel as the tap of centre q (des = es_i - es_q) ...
-    const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
-    // ... and as the centre with q as the tap: des flips sign exactly, so do the quotients
-    const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
-    const float r1 = rsqrt_approx(s);
-    acc = fmaf(r1 * r1 * r1, sgn(d_tap) * gq - sgn(d_ctr) * gc, acc);
+// grid-stride over pixel quads of grad_in [B*C, H, W]; marked pixels are recomputed by the whole warp:
+// lane l evaluates taps l, l+32, l+64 of the 9x9 window (both roles of the pixel), warp-reduced.
+__global__ void __launch_bounds__(256)
+census_sad_bwd_fixup(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
+                     float* __restrict__ gi, int64_t total, int C, int H, int W, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < total;
+       base += nwarps * 32) {
+    const int64_t idx = base + lane;
+    const bool marked = idx < total && __float_as_uint(gi[idx]) == SIGN_MARKER;
+    unsigned todo = __ballot_sync(0xffffffffu, marked);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int64_t i = base + src;
+      const int x = i % W, y = (i / W) % H;
+      const int64_t nc = i / ((int64_t)W * H);
+      const float* ep = es + nc * H * W;
+      const float* tp = ta + nc * H * W;
+      const float* gp = go + (nc / C) * H * W;
+      const float ei = __ldg(ep + (int64_t)y * W + x), ti = __ldg(tp + (int64_t)y * W + x), gc = __ldg(gp + (int64_t)y * W + x);
+      float acc = 0.f;
+      for (int t = lane; t < 81; t += 32) {
+        const int dy = t / 9 - R9, dx = t % 9 - R9;
+        const int qy = y + dy, qx = x + dx;
+        const int cy = clampi(qy, 0, H - 1), cx = clampi(qx, 0, W - 1);
+        const float des = ei - __ldg(ep + (int64_t)cy * W + cx), dta = ti - __ldg(tp + (int64_t)cy * W + cx);
+        // role "pixel is the tap of centre q": only real q, weighted by how many of q's offsets clamp onto i
+        float gq = 0.f;
+        if (qy == cy && qx == cx) {
+          const float mx = x == 0 ? float(R9 + 1 - dx) : (x == W - 1 ? float(R9 + 1 + dx) : 1.f);
+          const float my = y == 0 ? float(R9 + 1 - dy) : (y == H - 1 ? float(R9 + 1 + dy) : 1.f);
+          gq = __ldg(gp + (int64_t)cy * W + cx) * (mx * my);
+        }
+        const float s = __fadd_rn(__fmul_rn(des, des), eps);
+        const float q1 = __fdiv_rn(des, __fsqrt_rn(s));
+        const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
+        const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
+        // role "pixel is the centre, q the tap": des flips sign exactly, so do the quotients
+        const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
+        const float r1 = rsqrt_approx(s);
+        acc = fmaf(r1 * r1 * r1, sgn(d_tap) * gq - sgn(d_ctr) * gc, acc);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) gi[i] = acc * (0.5f * eps * INV81);
+    }
   }
-  return acc;
 }
 
 __device__ __forceinline__ float xor_sign(float v, float s) {  // v * sign(s) for s != 0
@@ -513,6 +548,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
     const float ec[4] = {ec4.x, ec4.y, ec4.z, ec4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
     const float gc[4] = {gc4.x, gc4.y, gc4.z, gc4.w};
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float near0[4] = {1.f, 1.f, 1.f, 1.f};  // census_sad: smallest |dd| over the window (centre tap excluded)
     // clamp multiplicity of the column / row offset d (-4..4): base + slope * d
     float bx[4] = {1.f, 1.f, 1.f, 1.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, by = 1.f, sy = 0.f;
     if (BORDER) {
@@ -534,8 +570,6 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
       const bool ctr_row = dy == R9;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float racc = 0.f;   // this window row's contribution to pixel k
-        float rmin = 1.f;   // census_sad: smallest |dd| in the row (centre tap excluded)
 #pragma unroll
         for (int dx = 0; dx < 9; ++dx) {
           const float des = ec[k] - e[k + dx];
@@ -547,7 +581,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
           float gq = g[k + dx];
           if (BORDER) gq *= my * fmaf(sx[k], float(dx - R9), bx[k]);
           if (TYPE == 2) {
-            racc = fmaf(dd * r3, gq + gc[k], racc);
+            acc[k] = fmaf(dd * r3, gq + gc[k], acc[k]);
           } else {
             float term = xor_sign(r3 * (gq + gc[k]), dd);
             float mag = fabsf(dd);
@@ -555,25 +589,26 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
               term = ctr_row ? 0.f : term;
               mag = ctr_row ? 1.f : mag;
             }
-            racc += term;
-            rmin = fminf(rmin, mag);
+            acc[k] += term;
+            near0[k] = fminf(near0[k], mag);
           }
         }
-        if (TYPE == 3 && rmin < SIGN_GUARD)
-          racc = census_sad_bwd_exact_row(&Es[0][0], &Ts[0][0], &Gs[0][0], yl + dy, 4 * tx + k, ec[k], tc[k], gc[k],
-                                          eps, bx[k], sx[k], my);
-        acc[k] += racc;
       }
     }
     const float scale = 0.5f * eps * INV81;
+    float r[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      r[k] = acc[k] * scale;
+      if (TYPE == 3 && near0[k] < SIGN_GUARD) r[k] = __uint_as_float(SIGN_MARKER);  // census_sad_bwd_fixup redoes it
+    }
     float* dst = gi + (int64_t)gy * W + gx;
     if (vec) {
-      if (gx < W)
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[0] * scale, acc[1] * scale, acc[2] * scale, acc[3] * scale);
+      if (gx < W) *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
     } else {
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (gx + k < W) dst[k] = acc[k] * scale;
+        if (gx + k < W) dst[k] = r[k];
     }
   }
 }
@@ -659,6 +694,7 @@ CTD_API int ctd_photometric_fwd_f32(const float* es, const float* ta, float* out
   cudaStream_t st = as_stream(stream);
   if (!fast9_ok(bs, H, W) || C < 1 || B < 1) return fwd_impl<float>(es, ta, out, B, C, H, W, bs, type, eps, st);
   if (int rc = check_common(es, ta, out, B, C, H, W, bs, type)) return rc;
+  if (type <= 1 && box9_tma_fwd(es, ta, out, B, C, H, W, type, st)) return check_launch("photometric_fwd(tma)");
   const int vec = vec_ok(W, es, ta, out, out);
   for (int64_t b0 = 0; b0 < B; b0 += 32768) {
     const int nb = (int)std::min<int64_t>(32768, B - b0);
@@ -691,6 +727,7 @@ CTD_API int ctd_photometric_bwd_f32(const float* es, const float* ta, const floa
   if (!fast9_ok(bs, H, W) || C < 1 || B < 1) return bwd_impl<float>(es, ta, go, gi, B, C, H, W, bs, type, eps, st);
   if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
   CTD_REQUIRE(go, "photometric_bwd: null grad_out");
+  if (type <= 1 && box9_tma_bwd(es, ta, go, gi, B, C, H, W, type, st)) return check_launch("photometric_bwd(tma)");
   const int vec = vec_ok(W, es, ta, go, gi);
   for (int64_t b0 = 0; b0 < B; b0 += 32768) {
     const int nb = (int)std::min<int64_t>(32768, B - b0);
@@ -705,7 +742,13 @@ CTD_API int ctd_photometric_bwd_f32(const float* es, const float* ta, const floa
     } else {
       dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
       if (type == 2) photo_bwd_census9<2><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec);
-      else photo_bwd_census9<3><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec);
+      else {
+        photo_bwd_census9<3><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec);
+        const int64_t total = (int64_t)nb * C * H * W;
+        const int fgrid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
+        census_sad_bwd_fixup<<<fgrid, 256, 0, st>>>(e, t, g, o, total, (int)C, (int)H, (int)W, eps);
+        count_launch();
+      }
     }
     count_launch();
   }

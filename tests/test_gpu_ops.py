@@ -391,3 +391,30 @@ def test_masked_sums(tx):
         assert torch.equal(a, b)
         want = np.array([(m.astype(np.float64) * d).sum(), m.astype(np.float64).sum()])
         assert np.abs(a.cpu().numpy() - want).max() <= 2e-6 * want.max()
+
+
+@pytest.mark.parametrize("ty", (0, 1))
+def test_box_tma_path_matches_tile_path(tx, ty):
+    """mse/sad at C=1 run persistent TMA kernels (multi-iteration ring at batch 8); the shared-memory tile
+    kernels (disable_tma) are a second implementation of the same arithmetic."""
+    from connecting_the_dots_b200 import _lib
+    torch.manual_seed(ty)
+    for shape in ((8, 1, 480, 640), (3, 1, 50, 260), (1, 1, 300, 12)):
+        es = torch.randn(*shape, device=DEV)
+        ta = torch.randn(*shape, device=DEV)
+        go = torch.rand(shape[0], 1, *shape[2:], device=DEV)
+        f1 = tx.ext_cuda.photometric_loss_forward(es, ta, 9, ty, 0.1)
+        b1 = tx.ext_cuda.photometric_loss_backward(es, ta, go, 9, ty, 0.1)
+        _lib.set_option("disable_tma", 1)
+        try:
+            f2 = tx.ext_cuda.photometric_loss_forward(es, ta, 9, ty, 0.1)
+            b2 = tx.ext_cuda.photometric_loss_backward(es, ta, go, 9, ty, 0.1)
+        finally:
+            _lib.set_option("disable_tma", 0)
+        assert_close(f1.cpu().numpy(), f2.cpu().numpy(), what="fwd %s" % (shape,))
+        assert_close(b1.cpu().numpy(), b2.cpu().numpy(), what="bwd %s" % (shape,))
+    # and against the oracle on one full-size image
+    es, ta, go = (t[:1].cpu().numpy() for t in (es, ta, go))
+    es = np.ascontiguousarray(es); ta = np.ascontiguousarray(ta); go = np.ascontiguousarray(go)
+    f = tx.ext_cuda.photometric_loss_forward(cu(es), cu(ta), 9, ty, 0.1).cpu().numpy()
+    assert_close(f, oracle.photometric_loss_forward(es, ta, 9, ty, 0.1))
