@@ -15,6 +15,7 @@
 #include <algorithm>
 
 #include "ctd_common.cuh"
+#include "ctd_tma.cuh"
 
 namespace ctd {
 
@@ -28,6 +29,7 @@ constexpr int L_SUB = 44;
 static_assert(4 * L_SUB >= L_COLS, "column store too small");
 __device__ __forceinline__ int lcol(int c) { return (c & 3) * L_SUB + (c >> 2); }
 constexpr int L_RG = 8;        // rows per shared-memory round
+extern int g_force_generic;
 constexpr int L_THREADS = 256;
 
 __device__ __forceinline__ int reflect(int i, int n) {  // torch ReflectionPad2d: no edge repeat
@@ -138,6 +140,151 @@ lcn_strip_kernel(const T* __restrict__ x, T* __restrict__ lcn, T* __restrict__ s
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// fp32, radius <= 5: persistent TMA-fed kernel.  A CTA walks a strided list of 128x16 output tiles; one
+// thread fetches each tile's 144x26 halo box with cp.async.bulk.tensor into a two-stage ring (the next
+// tile loads while this one is normalised).  Reflection padding is an index remap on the staged tile
+// (the mirrored pixels always lie inside the box).  Vertical pass: one thread per column builds fp64
+// prefix sums of x and x^2 down the box and emits 11-row window sums as differences of prefixes held
+// in a register ring; horizontal pass and epilogue as in lcn_strip_kernel.
+// ------------------------------------------------------------------------------------------
+constexpr int LTM_W = 128, LTM_H = 16, LTM_R = 5;
+constexpr int LTM_BW = 144;                       // box: columns x0-8 .. x0+135 (16-byte aligned origin)
+constexpr int LTM_BH = LTM_H + 2 * LTM_R;         // 26 rows y0-5 .. y0+20
+constexpr int LTM_XOFF = 8;                       // tile column of image column x0
+constexpr int LTM_BOX_BYTES = LTM_BW * LTM_BH * 4;  // 14976 = 117 * 128
+constexpr int LTM_SUB = 36;                       // interleaved fp64 column layout, see lcol()
+static_assert(LTM_BOX_BYTES % 128 == 0, "stage alignment");
+__device__ __forceinline__ int lcol36(int c) { return (c & 3) * LTM_SUB + (c >> 2); }
+
+struct alignas(128) LcnSmem {
+  float x[2][LTM_BH][LTM_BW];
+  double v1[LTM_H][4 * LTM_SUB];
+  double v2[LTM_H][4 * LTM_SUB];
+  uint64_t full[2];
+};
+
+template <int R>
+__global__ void __launch_bounds__(256, 3)
+lcn_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ lcn, float* __restrict__ sd_out, int H,
+               int W, float eps, int tiles_x, int tiles_y, int ntiles) {
+  extern __shared__ unsigned char smem_raw[];
+  LcnSmem& S = *reinterpret_cast<LcnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  constexpr int K = 2 * R + 1;
+  const float n = float(K * K);
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    mbar_init(&S.full[0], 1);
+    mbar_init(&S.full[1], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  int t = blockIdx.x;
+  auto coords = [&](int tt, int& x0, int& y0, int& img) {
+    x0 = (tt % tiles_x) * LTM_W;
+    y0 = ((tt / tiles_x) % tiles_y) * LTM_H;
+    img = tt / (tiles_x * tiles_y);
+  };
+  if (tid == 0 && t < ntiles) {
+    int x0, y0, img;
+    coords(t, x0, y0, img);
+    mbar_expect_tx(&S.full[0], LTM_BOX_BYTES);
+    tma_load_3d(&S.x[0][0][0], &map_x, &S.full[0], x0 - LTM_XOFF, y0 - LTM_R, img);
+  }
+  for (int it = 0; t < ntiles; ++it, t += gridDim.x) {
+    const int s = it & 1;
+    if (tid == 0 && t + (int)gridDim.x < ntiles) {
+      int x0, y0, img;
+      coords(t + gridDim.x, x0, y0, img);
+      fence_proxy_async();
+      mbar_expect_tx(&S.full[s ^ 1], LTM_BOX_BYTES);
+      tma_load_3d(&S.x[s ^ 1][0][0], &map_x, &S.full[s ^ 1], x0 - LTM_XOFF, y0 - LTM_R, img);
+    }
+    int x0, y0, img;
+    coords(t, x0, y0, img);
+    mbar_wait(&S.full[s], (it >> 1) & 1);
+    // vertical pass: thread c owns needed column c (image column x0 - R + c), 0 <= c < 128 + 2R
+    if (tid < LTM_W + 2 * R) {
+      const int cc = reflect(x0 - R + tid, W) - (x0 - LTM_XOFF);
+      double p1[K + 1], p2[K + 1];  // ring of prefix sums: slot j % (K+1) holds prefix through box row j-1
+      p1[0] = 0.0;
+      p2[0] = 0.0;
+#pragma unroll
+      for (int j = 0; j < LTM_H + 2 * R; ++j) {  // box rows y0 - R + j
+        const int rr = reflect(y0 - R + j, H) - (y0 - LTM_R);
+        const float v = S.x[s][rr][cc];
+        const int cur = (j + 1) % (K + 1), prev = j % (K + 1);
+        p1[cur] = p1[prev] + (double)v;
+        p2[cur] = p2[prev] + (double)(v * v);
+        if (j >= 2 * R) {  // rows j-2R .. j form the window of output row j - 2R
+          const int old = (j + 1 + 1) % (K + 1);  // slot holding the prefix through row j - 2R - 1
+          S.v1[j - 2 * R][lcol36(tid)] = p1[cur] - p1[old];
+          S.v2[j - 2 * R][lcol36(tid)] = p2[cur] - p2[old];
+        }
+      }
+    }
+    __syncthreads();
+    // horizontal pass + epilogue: 16 rows x 32 quads, two items per thread
+#pragma unroll 1
+    for (int item = tid; item < LTM_H * (LTM_W / 4); item += 256) {
+      const int j = item / (LTM_W / 4), q = item % (LTM_W / 4);
+      const int yy = y0 + j, xq = x0 + 4 * q;
+      if (yy >= H || xq >= W) continue;
+      const double* a1 = &S.v1[j][q];  // needed column 4q + k is a1[lcol36(k)]
+      const double* a2 = &S.v2[j][q];
+      double h1 = 0.0, h2 = 0.0;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        h1 += a1[lcol36(k)];
+        h2 += a2[lcol36(k)];
+      }
+      const float4 xv4 = *reinterpret_cast<const float4*>(&S.x[s][j + LTM_R][LTM_XOFF + 4 * q]);
+      const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+      float ol[4], os[4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        const float box = (float)h1, box2 = (float)h2;
+        const float avg = box / n;
+        const float var = box2 / n - avg * avg + 1e-6f;
+        const float sd = sqrtf(var) + eps;
+        ol[m] = (xv[m] - avg) / sd;
+        os[m] = sd;
+        if (m < 3) {
+          h1 += a1[lcol36(m + K)] - a1[lcol36(m)];
+          h2 += a2[lcol36(m + K)] - a2[lcol36(m)];
+        }
+      }
+      const int64_t off = ((int64_t)img * H + yy) * W + xq;
+      *reinterpret_cast<float4*>(lcn + off) = make_float4(ol[0], ol[1], ol[2], ol[3]);
+      *reinterpret_cast<float4*>(sd_out + off) = make_float4(os[0], os[1], os[2], os[3]);
+    }
+    __syncthreads();
+  }
+}
+
+extern int g_disable_tma;
+
+static bool lcn_tma_launch(const float* x, float* lcn, float* sd, int64_t N, int64_t H, int64_t W, int r, float eps,
+                           cudaStream_t st) {
+  if (g_disable_tma || r != LTM_R || W % 4 || H < 32 || W < 32) return false;
+  if ((reinterpret_cast<uintptr_t>(lcn) | reinterpret_cast<uintptr_t>(sd)) & 15) return false;
+  const int64_t tiles = N * cdiv(H, LTM_H) * cdiv(W, LTM_W);
+  if (tiles > INT32_MAX) return false;
+  CUtensorMap m;
+  if (!make_plane_tensor_map(&m, x, N, H, W, LTM_BW, LTM_BH)) return false;
+  const size_t smem = sizeof(LcnSmem) + 128;
+  if (cudaFuncSetAttribute(lcn_tma_kernel<LTM_R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  int dev = 0, sms = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = (int)std::min<int64_t>(tiles, (int64_t)sms * 3);
+  lcn_tma_kernel<LTM_R><<<grid, 256, smem, st>>>(m, lcn, sd, (int)H, (int)W, eps, (int)cdiv(W, LTM_W), (int)cdiv(H, LTM_H),
+                                                (int)tiles);
+  return true;
+}
+
 // any radius: one thread per pixel, direct (2r+1)^2 fp64 gather
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -167,8 +314,6 @@ lcn_generic_kernel(const T* __restrict__ x, T* __restrict__ lcn, T* __restrict__
   }
 }
 
-extern int g_force_generic;
-
 template <typename T>
 static int lcn_impl(const T* x, T* lcn, T* sd, int64_t N, int64_t H, int64_t W, int r, T eps, cudaStream_t st) {
   CTD_REQUIRE(N >= 0 && H >= 0 && W >= 0, "lcn: negative size");
@@ -179,7 +324,10 @@ static int lcn_impl(const T* x, T* lcn, T* sd, int64_t N, int64_t H, int64_t W, 
   // torch.nn.ReflectionPad2d requires the padding to be smaller than the padded dimension
   CTD_REQUIRE(r < H && r < W, "lcn: radius %d must be smaller than the image (%lld x %lld)", r, (long long)H,
               (long long)W);
-  if (g_force_generic || r > L_RMAX || N > 65535) {
+  if (sizeof(T) == 4 && !g_force_generic &&
+      lcn_tma_launch(reinterpret_cast<const float*>(x), reinterpret_cast<float*>(lcn), reinterpret_cast<float*>(sd), N, H, W,
+                     r, (float)eps, st)) {
+  } else if (g_force_generic || r > L_RMAX || N > 65535) {
     const int grid = (int)std::min<int64_t>(cdiv(N * H * W, 256), 148 * 64);
     lcn_generic_kernel<T><<<grid, 256, 0, st>>>(x, lcn, sd, N, (int)H, (int)W, r, eps);
   } else {

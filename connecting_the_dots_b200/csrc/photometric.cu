@@ -583,17 +583,21 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
           if (TYPE == 2) {
             acc[k] = fmaf(dd * r3, gq + gc[k], acc[k]);
           } else {
-            float term = xor_sign(r3 * (gq + gc[k]), dd);
+            // sign(dd) * r3: r3 > 0, so OR-ing in dd's sign bit is one LOP3.  The centre tap (dd = +0,
+            // sign(0) = 0 in the reference) comes out as +r3 * G here and is subtracted after the loop.
+            const float sr3 = __uint_as_float(__float_as_uint(r3) | (__float_as_uint(dd) & 0x80000000u));
+            acc[k] = fmaf(sr3, gq + gc[k], acc[k]);
             float mag = fabsf(dd);
-            if (dx == R9) {  // the centre tap itself: dd == 0, sign(0) = 0, and it is not a near-tie
-              term = ctr_row ? 0.f : term;
-              mag = ctr_row ? 1.f : mag;
-            }
-            acc[k] += term;
+            if (dx == R9) mag = ctr_row ? 1.f : mag;  // the centre tap is not a near-tie
             near0[k] = fminf(near0[k], mag);
           }
         }
       }
+    }
+    if (TYPE == 3) {
+      const float r0 = rsqrt_approx(eps);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[k] -= r0 * r0 * r0 * fmaf(bx[k] * by, gc[k], gc[k]);  // centre tap: M(i,i) = bx*by
     }
     const float scale = 0.5f * eps * INV81;
     float r[4];
