@@ -54,6 +54,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
 // read-only 128-bit load
 __device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
 
+// the same load pinned in program order (the compiler may not sink it towards its use)
+__device__ __forceinline__ float4 ldg4_volatile(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace ctd

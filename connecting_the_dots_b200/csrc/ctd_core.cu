@@ -8,6 +8,7 @@
 namespace ctd {
 
 int g_force_generic = 0;  // tests: route every op through its generic kernel
+int g_xcorr_direct = 0;   // tests / A-B runs: XCorrVol through the direct (centred two-pass) tile kernel
 int g_disable_tma = 0;    // tests / A-B runs: use the shared-memory tile kernels instead of the TMA ones
 static std::atomic<uint64_t> g_launches{0};
 
@@ -44,6 +45,10 @@ CTD_API uint64_t ctd_launch_count(void) { return ctd::g_launches.load(std::memor
 CTD_API int ctd_set_option(const char* name, int value) {
   if (name && !strcmp(name, "force_generic")) {
     ctd::g_force_generic = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "xcorr_direct")) {
+    ctd::g_xcorr_direct = value;
     return CTD_OK;
   }
   if (name && !strcmp(name, "disable_tma")) {

@@ -5,12 +5,14 @@
 // of in1 at (h, w-d); rows replicate-clamped, in0 columns clamped, in1 columns clamped AFTER the
 // disparity shift.  The reference has no batch dimension; here B images are one launch.
 #include <algorithm>
+#include <mutex>
 
 #include "ctd_common.cuh"
 
 namespace ctd {
 
 extern int g_force_generic;
+extern int g_xcorr_direct;
 
 // generic: any C, any block size, float or double; one thread per output, reference operation order
 // (built with -fmad=false), so it reproduces the reference's two-pass centred statistics exactly.
@@ -165,6 +167,503 @@ xcorrvol_direct(const float* __restrict__ in0, const float* __restrict__ in1, fl
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// separable kernel: C = 1, odd block size BS <= 9, fp32 -- the fast path.
+//
+//   dot(d,h,w) = sum_win (a - mu0)(b - mu1) = sum_win a*b  -  N * mu0(h,w) * mu1(h,w-d)
+//
+// so the only per-disparity work is a BS x BS box sum of the product plane a(h',x) * b(h',x-d): one
+// multiply and ~7 adds per output instead of 2*BS*BS taps.  mu and sigma of every window depend on one
+// image only and are computed once per pixel by xcorr_stats_kernel (fp64 box sums), for in1 over the
+// replicate-padded column range u = w - d in [-(D-1), W-1].
+//
+// Main kernel: a CTA owns 128 columns x XH rows x 16 disparities.  Warp g owns four disparities, lane l
+// four adjacent columns.  A thread walks down the tile rows: per row it reads 12 in0 and 16 in1 values
+// from the staged tiles (seven 128-bit shared loads) and forms the 4 x 12 products and their horizontal
+// BS-sums in registers.  The vertical BS-sum never subtracts (no sliding residue): rows are grouped in
+// blocks of BS; F is the running sum of the current block, and when a block completes its rows are
+// turned in place into suffix sums (rows j..BS-1), all in registers.  The window ending at row j of a
+// block is then suffix(j+1) of the previous block + F -- every output is an exact subset sum of its own
+// window's products.  Outputs leave as 128-bit stores of four adjacent columns, 512 B per warp and
+// disparity.
+//
+// Conditioning: the expanded form cancels when a window's spread is small against its mean.
+// xcorr_stats_kernel grades every window with L = floor(-4 log2(var / sum v^2)) (a byte per window, read
+// only by the fix-up pass).  The fast path's error is about 1.5e-7 * sqrt(S2_0 S2_1) / (sd0 sd1) =
+// 1.5e-7 * 2^((L0+L1)/8); outputs with L0 + L1 >= XS_LSUM (sd0 sd1 < 2^-4.5 sqrt(S2_0 S2_1), a few per
+// thousand on LCN'd images) are recomputed by xcorr_fixup_kernel: it walks the listed windows
+// (L >= XS_LLIST), compacts the affected outputs and evaluates them in fp64 -- or, for flat windows
+// (var < 1e-6 sum v^2), where the reference's result is its own rounding noise, with the reference's
+// centred two-pass fp32 arithmetic (ext.h:133-190).
+// ------------------------------------------------------------------------------------------
+constexpr int XS_W = 128;             // output columns per CTA (32 lanes x 4)
+constexpr int XS_DT = 16;             // disparities per CTA (4 warps x 4)
+constexpr int XS_AW = XS_W + 8;       // in0 tile: image columns x0-4 .. x0+131
+constexpr int XS_BW = XS_W + 8 + 16;  // in1 tile: image columns x0-20-d0 .. x0+131-d0 (clamped)
+constexpr int ST_W = 128, ST_H = 16;  // statistics tile
+constexpr int XS_LSUM = 36;           // L0 + L1 >= 36 <=> (sd0 sd1)^2 <= 2^-9 S2_0 S2_1: recompute in fp64
+constexpr int XS_LLIST = 18;          // max(L0, L1) >= 18 whenever L0 + L1 >= 36
+constexpr float XS_FLAT = 1e-6f;      // var < 1e-6 * sum v^2: flat window, reference arithmetic
+template <int BS>
+struct XsCfg {  // tile rows = a whole number of BS-row blocks
+  static constexpr int R = BS / 2;
+  static constexpr int NBLK = BS == 9 ? 5 : BS == 7 ? 6 : BS == 5 ? 8 : 13;
+  static constexpr int TH = BS * NBLK;    // staged rows
+  static constexpr int XH = TH - 2 * R;   // output rows per CTA (37, 36, 36, 37)
+};
+
+// reference arithmetic for one output (ext.h:133-190 with C = 1)
+template <int BS>
+__device__ __forceinline__ float xcorr_exact_one(const float* __restrict__ p0, const float* __restrict__ p1, int H, int W,
+                                                 int h, int w, int d) {
+  constexpr int R = BS / 2;
+  const float bs2 = float(BS * BS);
+  float mu0 = 0.f, mu1 = 0.f;
+  for (int bh = 0; bh < BS; ++bh) {
+    const int64_t row = (int64_t)clampi(h + bh - R, 0, H - 1) * W;
+#pragma unroll
+    for (int bw = 0; bw < BS; ++bw) {
+      const int w0 = w + bw - R;
+      mu0 += __ldg(p0 + row + clampi(w0, 0, W - 1)) / bs2;
+      mu1 += __ldg(p1 + row + clampi(w0 - d, 0, W - 1)) / bs2;
+    }
+  }
+  float s0 = 0.f, s1 = 0.f, dot = 0.f;
+  for (int bh = 0; bh < BS; ++bh) {
+    const int64_t row = (int64_t)clampi(h + bh - R, 0, H - 1) * W;
+#pragma unroll
+    for (int bw = 0; bw < BS; ++bw) {
+      const int w0 = w + bw - R;
+      const float v0 = __ldg(p0 + row + clampi(w0, 0, W - 1)) - mu0;
+      const float v1 = __ldg(p1 + row + clampi(w0 - d, 0, W - 1)) - mu1;
+      dot += v0 * v1;
+      s0 += v0 * v0;
+      s1 += v1 * v1;
+    }
+  }
+  return dot / (float)((double)sqrtf(s0 * s1) + 1e-8);
+}
+
+// the same output in fp64 (expanded sums are harmless at 53 bits): agrees with the reference to its own
+// rounding error wherever the windows are not flat; flat windows are handed to xcorr_exact_one
+template <int BS>
+__device__ __forceinline__ float xcorr_fp64_one(const float* __restrict__ p0, const float* __restrict__ p1, int H, int W,
+                                                int h, int w, int d) {
+  constexpr int R = BS / 2;
+  double sa = 0.0, sb = 0.0, saa = 0.0, sbb = 0.0, sab = 0.0;
+#pragma unroll
+  for (int bh = 0; bh < BS; ++bh) {
+    const int64_t row = (int64_t)clampi(h + bh - R, 0, H - 1) * W;
+#pragma unroll
+    for (int bw = 0; bw < BS; ++bw) {
+      const int w0 = w + bw - R;
+      const double a = (double)__ldg(p0 + row + clampi(w0, 0, W - 1));
+      const double b = (double)__ldg(p1 + row + clampi(w0 - d, 0, W - 1));
+      sa += a;
+      sb += b;
+      saa = fma(a, a, saa);
+      sbb = fma(b, b, sbb);
+      sab = fma(a, b, sab);
+    }
+  }
+  const double inv_n = 1.0 / double(BS * BS);
+  const double dot = sab - sa * sb * inv_n;
+  const double v0 = fmax(saa - sa * sa * inv_n, 0.0), v1 = fmax(sbb - sb * sb * inv_n, 0.0);
+  if (v0 < (double)XS_FLAT * saa || v1 < (double)XS_FLAT * sbb) return xcorr_exact_one<BS>(p0, p1, H, W, h, w, d);
+  return (float)(dot / (sqrt(v0 * v1) + 1e-8));
+}
+
+// Window statistics of one image over positions i = u + uoff, u = column of the window centre (may be
+// negative: replicate padding).  mu_out = scale * mean, sd_out = sqrt(sum (v - mean)^2), grade_out = L.
+// Windows with L >= XS_LLIST are appended to `list` as (side | position).
+template <int BS>
+__global__ void __launch_bounds__(256)
+xcorr_stats_kernel(const float* __restrict__ img, float* __restrict__ mu_out, float* __restrict__ sd_out,
+                   uint8_t* __restrict__ grade_out, int H, int W, int ws, int uoff, float scale, unsigned side,
+                   unsigned* __restrict__ list, unsigned* __restrict__ count) {
+  constexpr int R = BS / 2, TH = ST_H + 2 * R, TW = ST_W + 2 * R;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double(*H1)[ST_W] = reinterpret_cast<double(*)[ST_W]>(smem_raw);
+  double(*H2)[ST_W] = H1 + TH;
+  float(*T)[TW] = reinterpret_cast<float(*)[TW]>(H2 + TH);
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * ST_W, y0 = blockIdx.y * ST_H;
+  const float* src = img + (int64_t)blockIdx.z * H * W;
+  for (int i = tid; i < TH * TW; i += 256) {
+    const int r = i / TW, j = i % TW;
+    T[r][j] = __ldg(src + (int64_t)clampi(y0 - R + r, 0, H - 1) * W + clampi(i0 - uoff - R + j, 0, W - 1));
+  }
+  __syncthreads();
+  for (int it = tid; it < TH * (ST_W / 4); it += 256) {
+    const int r = it / (ST_W / 4), c = 4 * (it % (ST_W / 4));
+    double v[BS + 3];
+#pragma unroll
+    for (int j = 0; j < BS + 3; ++j) v[j] = (double)T[r][c + j];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        s1 += v[k + j];
+        s2 = fma(v[k + j], v[k + j], s2);
+      }
+      H1[r][c + k] = s1;
+      H2[r][c + k] = s2;
+    }
+  }
+  __syncthreads();
+  // thread (c, hh) produces output rows hh .. hh+7 of column c (exact subset sums, fp64)
+  const int c = tid % ST_W, hh = (tid / ST_W) * (ST_H / 2);
+  const double inv_n = 1.0 / double(BS * BS);
+#pragma unroll 2
+  for (int o = 0; o < ST_H / 2; ++o) {
+    const int y = y0 + hh + o;
+    if (y >= H || i0 + c >= ws) continue;
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      s1 += H1[hh + o + j][c];
+      s2 += H2[hh + o + j][c];
+    }
+    const float var = (float)fmax(s2 - s1 * s1 * inv_n, 0.0), e2 = (float)s2;
+    const float sd = sqrtf(var);
+    // grade: L = floor(-4 log2(var / S2)); an all-zero window is exact (every product is 0): L = 0
+    unsigned L = 0;
+    if (e2 > 0.f) L = var > 0.f ? (unsigned)min(255, max(0, (int)floorf(-4.f * log2f(var / e2)))) : 255u;
+    const int64_t off = ((int64_t)blockIdx.z * H + y) * ws + i0 + c;
+    mu_out[off] = (float)(s1 * inv_n) * scale;
+    sd_out[off] = sd;
+    grade_out[off] = (uint8_t)L;
+    if (L >= (unsigned)XS_LLIST) list[atomicAdd(count, 1u)] = side | (unsigned)off;
+  }
+}
+
+// o[k] = sum_{j=4-R+k}^{4+R+k} p[j], k = 0..3: the taps common to the four windows are summed once,
+// every o[k] is an exact subset sum of its own window (nothing slides, so no residue from other taps)
+template <int BS>
+__device__ __forceinline__ void xs_hsum(const float* p, float* o) {
+  constexpr int R = BS / 2;
+  if (BS == 9) {
+    const float mid = ((p[3] + p[4]) + (p[5] + p[6])) + (p[7] + p[8]);
+    const float l12 = p[1] + p[2], r910 = p[9] + p[10];
+    o[0] = mid + (p[0] + l12);
+    o[1] = mid + (l12 + p[9]);
+    o[2] = mid + (p[2] + r910);
+    o[3] = mid + (r910 + p[11]);
+  } else if (BS == 7) {
+    const float mid = (p[4] + p[5]) + (p[6] + p[7]);
+    o[0] = mid + ((p[1] + p[2]) + p[3]);
+    o[1] = mid + ((p[2] + p[3]) + p[8]);
+    o[2] = mid + (p[3] + (p[8] + p[9]));
+    o[3] = mid + ((p[8] + p[9]) + p[10]);
+  } else if (BS == 5) {
+    const float mid = p[5] + p[6];
+    o[0] = mid + ((p[2] + p[3]) + p[4]);
+    o[1] = mid + ((p[3] + p[4]) + p[7]);
+    o[2] = mid + (p[4] + (p[7] + p[8]));
+    o[3] = mid + ((p[7] + p[8]) + p[9]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float s = p[4 - R + k];
+#pragma unroll
+      for (int j = 5 - R + k; j <= 4 + R + k; ++j) s += p[j];
+      o[k] = s;
+    }
+  }
+}
+
+template <int BS>
+__global__ void __launch_bounds__(128, 2)
+xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
+                 const float* __restrict__ mu0, const float* __restrict__ sd0, const float* __restrict__ mu1,
+                 const float* __restrict__ sd1, int H, int W, int D, int ws0, int ws1, int uoff, int ndchunks, int vec) {
+  constexpr int R = BS / 2, TH = XsCfg<BS>::TH, XH = XsCfg<BS>::XH, NBLK = XsCfg<BS>::NBLK;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float(*At)[XS_AW] = reinterpret_cast<float(*)[XS_AW]>(smem_raw);
+  float(*Bt)[XS_BW] = reinterpret_cast<float(*)[XS_BW]>(smem_raw + sizeof(float) * TH * XS_AW);
+  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int x0 = blockIdx.x * XS_W, y0 = blockIdx.y * XH;
+  const int b = blockIdx.z / ndchunks, d0 = (blockIdx.z % ndchunks) * XS_DT;
+  const int64_t plane = (int64_t)H * W;
+  const float* p0 = in0 + b * plane;
+  const float* p1 = in1 + b * plane;
+  // stage the tiles (replicate clamp; 128-bit loads where the four columns are inside the image), four
+  // independent loads in flight per thread
+  auto fetch4 = [&](const float* img, int r, int gx) -> float4 {
+    const float* row = img + (int64_t)clampi(y0 - R + r, 0, H - 1) * W;
+    if (vec && gx >= 0 && gx + 3 < W) return ldg4(row + gx);
+    return make_float4(__ldg(row + clampi(gx, 0, W - 1)), __ldg(row + clampi(gx + 1, 0, W - 1)),
+                       __ldg(row + clampi(gx + 2, 0, W - 1)), __ldg(row + clampi(gx + 3, 0, W - 1)));
+  };
+  constexpr int NA = TH * (XS_AW / 4), NB = TH * (XS_BW / 4);
+  for (int i0 = tid; i0 < NA; i0 += 4 * 128) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * 128;
+      if (i < NA) v[k] = fetch4(p0, i / (XS_AW / 4), x0 - 4 + 4 * (i % (XS_AW / 4)));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * 128;
+      if (i < NA) *reinterpret_cast<float4*>(&At[i / (XS_AW / 4)][4 * (i % (XS_AW / 4))]) = v[k];
+    }
+  }
+  for (int i0 = tid; i0 < NB; i0 += 4 * 128) {
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * 128;
+      if (i < NB) v[k] = fetch4(p1, i / (XS_BW / 4), x0 - 20 - d0 + 4 * (i % (XS_BW / 4)));
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i = i0 + k * 128;
+      if (i < NB) *reinterpret_cast<float4*>(&Bt[i / (XS_BW / 4)][4 * (i % (XS_BW / 4))]) = v[k];
+    }
+  }
+  __syncthreads();
+  const int x = x0 + 4 * lane;
+  const int dbase = d0 + 4 * g;  // this warp's first disparity
+  if (x >= W || dbase >= D) return;  // nothing to write; no barrier follows
+  // suf[j-1][dl][k], j = 1..BS-1: sum of rows j..BS-1 of the previous block; rows < j of the current block
+  // overwrite it with their own horizontal sums as they are produced
+  float suf[BS - 1][4][4], F[4][4];
+#pragma unroll
+  for (int dl = 0; dl < 4; ++dl)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      F[dl][k] = 0.f;
+#pragma unroll
+      for (int j = 0; j < BS - 1; ++j) suf[j][dl][k] = 0.f;
+    }
+  // tile column of image column (x - 4 - d) is 4*lane + 16 - (d - d0); the aligned 16 values from
+  // 4*lane + 12 - 4g cover the four disparities of this warp
+  const float* arow = &At[0][4 * lane];
+  const float* brow = &Bt[0][4 * lane + 12 - 4 * g];
+  const float* q0p = mu0 + ((int64_t)b * H) * ws0 + x;
+  const float* s0p = sd0 + ((int64_t)b * H) * ws0 + x;
+  const float* m1p = mu1 + ((int64_t)b * H) * ws1 + (x - dbase - 4 + uoff);
+  const float* s1p = sd1 + ((int64_t)b * H) * ws1 + (x - dbase - 4 + uoff);
+  float* outp = out + (((int64_t)b * D + dbase) * H) * W + x;
+  const int64_t dstride = (int64_t)H * W;
+  // window statistics of one output row: w-side (N * mu0, sd0) of the four columns, u-side (mu1, sd1) of the
+  // eight positions u = x - dbase - 4 .. x - dbase + 3.  Fetched one row ahead (right after the previous
+  // row's last use of these registers) so the L2 round trip hides behind the next row's arithmetic.
+  float4 q4, s4, m1a, m1b, s1a, s1b;
+  auto fetch_stats = [&](int yo) {
+    q4 = ldg4_volatile(q0p + (int64_t)yo * ws0);
+    s4 = ldg4_volatile(s0p + (int64_t)yo * ws0);
+    m1a = ldg4_volatile(m1p + (int64_t)yo * ws1);
+    m1b = ldg4_volatile(m1p + (int64_t)yo * ws1 + 4);
+    s1a = ldg4_volatile(s1p + (int64_t)yo * ws1);
+    s1b = ldg4_volatile(s1p + (int64_t)yo * ws1 + 4);
+  };
+  fetch_stats(min(y0, H - 1));  // first emitting row: tile row BS - 1 <-> output row y0
+#pragma unroll 1
+  for (int blk = 0; blk < NBLK; ++blk) {
+#pragma unroll
+    for (int j = 0; j < BS; ++j) {
+      const int r = blk * BS + j;
+      float a[12], bv[16];
+      {
+        const float4* ap = reinterpret_cast<const float4*>(arow + r * XS_AW);
+        const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
+        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+        a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+        a[8] = a2.x; a[9] = a2.y; a[10] = a2.z; a[11] = a2.w;
+        const float4* bp = reinterpret_cast<const float4*>(brow + r * XS_BW);
+        const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+        bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+        bv[8] = b2.x; bv[9] = b2.y; bv[10] = b2.z; bv[11] = b2.w;
+        bv[12] = b3.x; bv[13] = b3.y; bv[14] = b3.z; bv[15] = b3.w;
+      }
+      const int yo = y0 + r - 2 * R;                       // the window ending at tile row r
+      const bool emit = (blk > 0 || j == BS - 1) && yo < H;  // warp-uniform
+#pragma unroll
+      for (int dl = 0; dl < 4; ++dl) {
+        float p[12], hs[4], S[4];
+#pragma unroll
+        for (int t = 4 - R; t <= 7 + R; ++t) p[t] = a[t] * bv[4 - dl + t];
+        xs_hsum<BS>(p, hs);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          F[dl][k] += hs[k];
+          S[k] = j == BS - 1 ? F[dl][k] : suf[j < BS - 1 ? j : 0][dl][k] + F[dl][k];  // suf[j] = rows j+1.. of the previous block
+          if (j > 0) suf[j - 1][dl][k] = hs[k];
+        }
+        if (j == BS - 1) {  // the block is complete: rows -> suffix sums, restart F
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int i = BS - 3; i >= 0; --i) suf[i][dl][k] += suf[i + 1][dl][k];
+            F[dl][k] = 0.f;
+          }
+        }
+        if (emit && dbase + dl < D) {
+          const float q0[4] = {q4.x, q4.y, q4.z, q4.w}, s0[4] = {s4.x, s4.y, s4.z, s4.w};
+          const float m1[8] = {m1a.x, m1a.y, m1a.z, m1a.w, m1b.x, m1b.y, m1b.z, m1b.w};
+          const float s1[8] = {s1a.x, s1a.y, s1a.z, s1a.w, s1b.x, s1b.y, s1b.z, s1b.w};
+          // 1e-8 routed through S: the norm must not be scheduled ahead of this row's sums, or the warp would
+          // sit on the statistics loads (issued a row ago) instead of overlapping them with the arithmetic
+          // (m1a.x, s1a.x are never used as statistics; folding them in keeps their registers reserved while the
+          // 128-bit loads are in flight -- a reuse as scratch would stall on the pending write)
+          const float eps8 = fmaf(s1a.x, 0.f, fmaf(m1a.x, 0.f, fmaf(S[0], 0.f, 1e-8f)));
+          float v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int ui = 4 + k - dl;
+            const float dot = fmaf(-q0[k], m1[ui], S[k]);
+            v[k] = dot * rcp_approx(fmaf(s0[k], s1[ui], eps8));  // untrusted outputs are overwritten by the fix-up kernel
+          }
+          float* dst = outp + dl * dstride + (int64_t)yo * W;
+          if (vec) {
+            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (x + k < W) dst[k] = v[k];
+          }
+        }
+      }
+      if (emit && yo + 1 < H && r + 1 < TH) fetch_stats(yo + 1);
+    }
+  }
+}
+
+// One warp per (listed window, 32 disparities): lane l looks at output d = 32*chunk + l.  side 0: window
+// of in0 at (h, w) -> outputs (d, h, w); side 1: window of in1 at (h, u) -> outputs (d, h, u + d) inside the
+// image.  An output is owned by the side with the larger grade (side 0 on ties) so it is done once.
+// Affected outputs are queued per warp and evaluated 32 at a time, so the expensive path runs with full
+// warps however sparse the hits are.
+template <int BS>
+__global__ void __launch_bounds__(256)
+xcorr_fixup_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
+                   const uint8_t* __restrict__ g0, const uint8_t* __restrict__ g1, const unsigned* __restrict__ list,
+                   const unsigned* __restrict__ count, int H, int W, int D, int ws0, int ws1, int uoff) {
+  __shared__ unsigned long long queue[8][64];  // output index (b*D+d)*H*W + h*W + w
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int dchunks = (D + 31) / 32;
+  const int64_t items = (int64_t)(*count) * dchunks;
+  const int64_t plane = (int64_t)H * W;
+  int nq = 0;  // warp-uniform queue length
+  auto drain = [&](int n) {  // evaluate the first n (<= 32) queued outputs, one per lane
+    if (lane < n) {
+      const int64_t o = (int64_t)queue[wl][lane];
+      const int w = (int)(o % W), h = (int)((o / W) % H);
+      const int64_t bd = o / plane;
+      const int d = (int)(bd % D);
+      const int64_t b = bd / D;
+      out[o] = xcorr_fp64_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d);
+    }
+    __syncwarp();
+  };
+  for (int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + wl; it < items; it += nwarps) {
+    const unsigned e = list[it / dchunks];
+    const int d = (int)(it % dchunks) * 32 + lane;
+    const unsigned side = e >> 31;
+    const int64_t pos = e & 0x7fffffffu;
+    const int ws = side ? ws1 : ws0;
+    const int i = (int)(pos % ws), h = (int)((pos / ws) % H);
+    const int64_t b = pos / ((int64_t)ws * H);
+    const int w = side ? i - uoff + d : i;
+    bool hit = false;
+    if (d < D && w >= 0 && w < W) {
+      const unsigned Ls = side ? g1[pos] : g0[pos];
+      const unsigned Lo = side ? g0[(b * H + h) * ws0 + w] : g1[(b * H + h) * ws1 + (w - d + uoff)];
+      hit = Ls + Lo >= (unsigned)XS_LSUM && (side ? Ls > Lo : Ls >= Lo);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int slot = nq + __popc(m & ((1u << lane) - 1u));
+      queue[wl][slot] = (unsigned long long)(((b * D + d) * H + h) * W + w);
+    }
+    nq += __popc(m);
+    __syncwarp();
+    if (nq >= 32) {
+      drain(32);
+      if (lane < nq - 32) queue[wl][lane] = queue[wl][lane + 32];
+      nq -= 32;
+      __syncwarp();
+    }
+  }
+  if (nq > 0) drain(nq);
+}
+
+// stream-ordered scratch for the statistics planes: a library-owned memory pool per device that keeps its
+// memory between calls (no torch dependency, no synchronisation, usable under CUDA-graph capture)
+static cudaMemPool_t scratch_pool() {
+  static std::mutex mtx;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mtx);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t p = nullptr;
+    if (cudaMemPoolCreate(&p, &props) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = p;
+  }
+  return pools[dev];
+}
+
+template <int BS>
+static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int64_t B, int64_t H, int64_t W, int64_t D,
+                             cudaStream_t st) {
+  constexpr int R = BS / 2, XH = XsCfg<BS>::XH, TH = XsCfg<BS>::TH;
+  const int64_t ndchunks = cdiv(D, XS_DT);
+  const int64_t uoff = ndchunks * XS_DT, ws0 = cdiv(W, 4) * 4, ws1 = uoff + ws0;
+  const int64_t n0 = B * H * ws0, n1 = B * H * ws1;
+  if (B * ndchunks > 65535 || cdiv(H, XH) > 65535 || cdiv(H, ST_H) > 65535 || n1 >= ((int64_t)1 << 31)) return false;
+  cudaMemPool_t pool = scratch_pool();
+  if (!pool) return false;
+  float* scratch = nullptr;
+  const size_t words = (size_t)(3 * n0 + 3 * n1 + 4) + (size_t)(n0 + n1 + 3) / 4;
+  if (cudaMallocFromPoolAsync((void**)&scratch, words * sizeof(float), pool, st) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  float *mu0 = scratch, *sd0 = mu0 + n0, *mu1 = sd0 + n0, *sd1 = mu1 + n1;
+  unsigned* list = reinterpret_cast<unsigned*>(sd1 + n1);
+  unsigned* count = list + n0 + n1;
+  uint8_t* g0 = reinterpret_cast<uint8_t*>(count + 4);
+  uint8_t* g1 = g0 + n0;
+  const size_t st_smem = sizeof(double) * 2 * (ST_H + 2 * R) * ST_W + sizeof(float) * (ST_H + 2 * R) * (ST_W + 2 * R);
+  const size_t smem = sizeof(float) * TH * (XS_AW + XS_BW);
+  static const bool attr_ok =
+      cudaFuncSetAttribute(xcorr_stats_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem) == cudaSuccess &&
+      cudaFuncSetAttribute(xcorr_sep_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+  if (!attr_ok || cudaMemsetAsync(count, 0, sizeof(unsigned), st) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFreeAsync(scratch, st);
+    return false;
+  }
+  xcorr_stats_kernel<BS><<<dim3((unsigned)cdiv(ws0, ST_W), (unsigned)cdiv(H, ST_H), (unsigned)B), 256, st_smem, st>>>(
+      in0, mu0, sd0, g0, (int)H, (int)W, (int)ws0, 0, float(BS * BS), 0u, list, count);
+  xcorr_stats_kernel<BS><<<dim3((unsigned)cdiv(ws1, ST_W), (unsigned)cdiv(H, ST_H), (unsigned)B), 256, st_smem, st>>>(
+      in1, mu1, sd1, g1, (int)H, (int)W, (int)ws1, (int)uoff, 1.0f, 0x80000000u, list, count);
+  const int vec = (W % 4 == 0) && !((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) |
+                                     reinterpret_cast<uintptr_t>(out)) & 15);
+  xcorr_sep_kernel<BS><<<dim3((unsigned)cdiv(W, XS_W), (unsigned)cdiv(H, XH), (unsigned)(B * ndchunks)), 128, smem, st>>>(
+      in0, in1, out, mu0, sd0, mu1, sd1, (int)H, (int)W, (int)D, (int)ws0, (int)ws1, (int)uoff, (int)ndchunks, vec);
+  xcorr_fixup_kernel<BS><<<148 * 4, 256, 0, st>>>(in0, in1, out, g0, g1, list, count, (int)H, (int)W, (int)D, (int)ws0,
+                                                 (int)ws1, (int)uoff);
+  count_launch(4);
+  cudaFreeAsync(scratch, st);
+  return true;
+}
+
 template <typename T>
 static int xcorrvol_impl(const T* in0, const T* in1, T* out, int64_t B, int64_t C, int64_t H, int64_t W, int64_t D,
                          int bs, cudaStream_t st) {
@@ -174,6 +673,16 @@ static int xcorrvol_impl(const T* in0, const T* in1, T* out, int64_t B, int64_t 
   const int64_t total = B * D * H * W;
   if (total == 0) return CTD_OK;
   CTD_REQUIRE(out && (C == 0 || (in0 && in1)), "xcorrvol: null pointer");
+  if (sizeof(T) == 4 && C == 1 && !g_force_generic && !g_xcorr_direct && (bs == 3 || bs == 5 || bs == 7 || bs == 9)) {
+    const float* f0 = reinterpret_cast<const float*>(in0);
+    const float* f1 = reinterpret_cast<const float*>(in1);
+    float* fo = reinterpret_cast<float*>(out);
+    const bool done = bs == 9   ? xcorr_sep_launch<9>(f0, f1, fo, B, H, W, D, st)
+                      : bs == 7 ? xcorr_sep_launch<7>(f0, f1, fo, B, H, W, D, st)
+                      : bs == 5 ? xcorr_sep_launch<5>(f0, f1, fo, B, H, W, D, st)
+                                : xcorr_sep_launch<3>(f0, f1, fo, B, H, W, D, st);
+    if (done) return check_launch("xcorrvol(separable)");
+  }
   if (sizeof(T) == 4 && C == 1 && !g_force_generic && (bs == 3 || bs == 5 || bs == 7 || bs == 9) && H <= 65535) {
     const int64_t nchunks = cdiv(D, XD_DC);
     for (int64_t b0 = 0; b0 < B; b0 += 1024) {  // keep gridDim.z under 65535

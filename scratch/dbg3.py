@@ -1,0 +1,12 @@
+import sys
+sys.path.insert(0, "/root/repo")
+import numpy as np, torch
+import connecting_the_dots_b200 as ctd
+from connecting_the_dots_b200 import synth
+tx = ctd.torchext
+cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+d = synth.make_batch(2, 480, 640)
+a, b = cu(d["ta"]), cu(d["pat_lcn"])
+for it in range(2):
+    o = tx.xcorrvol(a, b, 128, 9)
+torch.cuda.synchronize()

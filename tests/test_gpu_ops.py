@@ -232,6 +232,37 @@ def test_xcorrvol_vs_oracle(tx, shape):
     assert np.array_equal(one, got[0])
 
 
+def test_xcorrvol_ill_conditioned_windows(tx):
+    """Windows whose mean dominates their spread (raw intensities, constant patches, one flat image): the
+    separable kernel must hand them to its centred two-pass path and still match ext_cpu's arithmetic."""
+    rng = np.random.RandomState(7)
+    H, W, D = 40, 132, 21
+    a = (0.5 + 0.02 * rng.randn(1, 1, H, W)).astype(np.float32)
+    b = (0.5 + 0.02 * rng.randn(1, 1, H, W)).astype(np.float32)
+    a[0, 0, 5:25, 30:70] = 0.75                      # flat patch inside a textured image
+    b[0, 0, 10:30, 80:120] = rng.randn(20, 40)       # well-conditioned island in a dim image
+    got = tx.xcorrvol(cu(a), cu(b), D, 9).cpu().numpy()
+    assert_close(got[0], oracle.xcorrvol(a[0], b[0], D, 9), what="raw intensities + flat patch")
+    z = rng.randn(1, 1, H, W).astype(np.float32)
+    z[0, 0, :, 40:90] = 0.0                          # exactly zero band: sigma = 0, norm = 1e-8
+    got = tx.xcorrvol(cu(z), cu(np.roll(z, 2, axis=3)), D, 5).cpu().numpy()
+    assert_close(got[0], oracle.xcorrvol(z[0], np.roll(z, 2, axis=3)[0], D, 5), what="zero band")
+
+
+def test_xcorrvol_separable_matches_direct(tx):
+    """A/B: the separable kernel against the direct centred kernel of the same library on LCN'd data."""
+    from connecting_the_dots_b200 import _lib, synth
+    d = synth.make_pair(1, 64, 320)
+    a, b = cu(d["ta"][None]), cu(d["pat_lcn"][None])
+    fast = tx.xcorrvol(a, b, 128, 9)
+    _lib.set_option("xcorr_direct", 1)
+    try:
+        direct = tx.xcorrvol(a, b, 128, 9)
+    finally:
+        _lib.set_option("xcorr_direct", 0)
+    assert_close(fast.cpu().numpy(), direct.cpu().numpy(), what="separable vs direct")
+
+
 def test_xcorrvol_synthetic_lcn_data(tx):
     """LCN'd dot-pattern rows (the BASELINE config 3 data) on a crop the oracle finishes quickly."""
     from connecting_the_dots_b200 import synth
