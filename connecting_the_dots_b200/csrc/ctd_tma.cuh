@@ -48,6 +48,13 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       : "memory");
 }
 
+// 1-D bulk copy global -> shared (size and both addresses multiples of 16 bytes), completion on `bar`
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // Host: tensor map of a contiguous fp32 [planes, H, W] array with box (box_w, box_h, 1), zero OOB fill.
 // Returns false when TMA cannot address it (unaligned base, W not a multiple of 4, driver entry missing).
 bool make_plane_tensor_map(CUtensorMap* map, const float* base, int64_t planes, int64_t H, int64_t W, int box_w,

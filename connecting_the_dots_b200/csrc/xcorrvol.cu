@@ -8,11 +8,13 @@
 #include <mutex>
 
 #include "ctd_common.cuh"
+#include "ctd_tma.cuh"
 
 namespace ctd {
 
 extern int g_force_generic;
 extern int g_xcorr_direct;
+extern int g_xcorr_nofix;
 
 // generic: any C, any block size, float or double; one thread per output, reference operation order
 // (built with -fmad=false), so it reproduces the reference's two-pass centred statistics exactly.
@@ -204,6 +206,12 @@ constexpr int ST_W = 128, ST_H = 16;  // statistics tile
 constexpr int XS_LSUM = 36;           // L0 + L1 >= 36 <=> (sd0 sd1)^2 <= 2^-9 S2_0 S2_1: recompute in fp64
 constexpr int XS_LLIST = 18;          // max(L0, L1) >= 18 whenever L0 + L1 >= 36
 constexpr float XS_FLAT = 1e-6f;      // var < 1e-6 * sum v^2: flat window, reference arithmetic
+constexpr int XS_NST = 4;              // statistics rows in flight per warp
+struct alignas(16) XsStatRing {
+  float2 w[XS_NST][XS_W];
+  float2 u[XS_NST][XS_W + 8];
+  uint64_t full[XS_NST];
+};
 template <int BS>
 struct XsCfg {  // tile rows = a whole number of BS-row blocks
   static constexpr int R = BS / 2;
@@ -274,12 +282,11 @@ __device__ __forceinline__ float xcorr_fp64_one(const float* __restrict__ p0, co
 }
 
 // Window statistics of one image over positions i = u + uoff, u = column of the window centre (may be
-// negative: replicate padding).  mu_out = scale * mean, sd_out = sqrt(sum (v - mean)^2), grade_out = L.
+// negative: replicate padding).  st_out = {scale * mean, sqrt(sum (v - mean)^2)} interleaved, grade_out = L.
 // Windows with L >= XS_LLIST are appended to `list` as (side | position).
 template <int BS>
 __global__ void __launch_bounds__(256)
-xcorr_stats_kernel(const float* __restrict__ img, float* __restrict__ mu_out, float* __restrict__ sd_out,
-                   uint8_t* __restrict__ grade_out, int H, int W, int ws, int uoff, float scale, unsigned side,
+xcorr_stats_kernel(const float* __restrict__ img, float2* __restrict__ st_out, uint8_t* __restrict__ grade_out, int H, int W, int ws, int uoff, float scale, unsigned side,
                    unsigned* __restrict__ list, unsigned* __restrict__ count) {
   constexpr int R = BS / 2, TH = ST_H + 2 * R, TW = ST_W + 2 * R;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -331,8 +338,7 @@ xcorr_stats_kernel(const float* __restrict__ img, float* __restrict__ mu_out, fl
     unsigned L = 0;
     if (e2 > 0.f) L = var > 0.f ? (unsigned)min(255, max(0, (int)floorf(-4.f * log2f(var / e2)))) : 255u;
     const int64_t off = ((int64_t)blockIdx.z * H + y) * ws + i0 + c;
-    mu_out[off] = (float)(s1 * inv_n) * scale;
-    sd_out[off] = sd;
+    st_out[off] = make_float2((float)(s1 * inv_n) * scale, sd);
     grade_out[off] = (uint8_t)L;
     if (L >= (unsigned)XS_LLIST) list[atomicAdd(count, 1u)] = side | (unsigned)off;
   }
@@ -376,12 +382,13 @@ __device__ __forceinline__ void xs_hsum(const float* p, float* o) {
 template <int BS>
 __global__ void __launch_bounds__(128, 2)
 xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
-                 const float* __restrict__ mu0, const float* __restrict__ sd0, const float* __restrict__ mu1,
-                 const float* __restrict__ sd1, int H, int W, int D, int ws0, int ws1, int uoff, int ndchunks, int vec) {
+                 const float2* __restrict__ st0, const float2* __restrict__ st1, int H, int W, int D, int ws0, int ws1,
+                 int uoff, int ndchunks, int vec) {
   constexpr int R = BS / 2, TH = XsCfg<BS>::TH, XH = XsCfg<BS>::XH, NBLK = XsCfg<BS>::NBLK;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float(*At)[XS_AW] = reinterpret_cast<float(*)[XS_AW]>(smem_raw);
   float(*Bt)[XS_BW] = reinterpret_cast<float(*)[XS_BW]>(smem_raw + sizeof(float) * TH * XS_AW);
+  XsStatRing* rings = reinterpret_cast<XsStatRing*>(smem_raw + sizeof(float) * TH * (XS_AW + XS_BW));
   const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
   const int x0 = blockIdx.x * XS_W, y0 = blockIdx.y * XH;
   const int b = blockIdx.z / ndchunks, d0 = (blockIdx.z % ndchunks) * XS_DT;
@@ -426,7 +433,7 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   __syncthreads();
   const int x = x0 + 4 * lane;
   const int dbase = d0 + 4 * g;  // this warp's first disparity
-  if (x >= W || dbase >= D) return;  // nothing to write; no barrier follows
+  if (dbase >= D) return;  // warp-uniform: nothing to write, no CTA barrier follows
   // suf[j-1][dl][k], j = 1..BS-1: sum of rows j..BS-1 of the previous block; rows < j of the current block
   // overwrite it with their own horizontal sums as they are produced
   float suf[BS - 1][4][4], F[4][4];
@@ -442,25 +449,32 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   // 4*lane + 12 - 4g cover the four disparities of this warp
   const float* arow = &At[0][4 * lane];
   const float* brow = &Bt[0][4 * lane + 12 - 4 * g];
-  const float* q0p = mu0 + ((int64_t)b * H) * ws0 + x;
-  const float* s0p = sd0 + ((int64_t)b * H) * ws0 + x;
-  const float* m1p = mu1 + ((int64_t)b * H) * ws1 + (x - dbase - 4 + uoff);
-  const float* s1p = sd1 + ((int64_t)b * H) * ws1 + (x - dbase - 4 + uoff);
   float* outp = out + (((int64_t)b * D + dbase) * H) * W + x;
   const int64_t dstride = (int64_t)H * W;
-  // window statistics of one output row: w-side (N * mu0, sd0) of the four columns, u-side (mu1, sd1) of the
-  // eight positions u = x - dbase - 4 .. x - dbase + 3.  Fetched one row ahead (right after the previous
-  // row's last use of these registers) so the L2 round trip hides behind the next row's arithmetic.
-  float4 q4, s4, m1a, m1b, s1a, s1b;
-  auto fetch_stats = [&](int yo) {
-    q4 = ldg4_volatile(q0p + (int64_t)yo * ws0);
-    s4 = ldg4_volatile(s0p + (int64_t)yo * ws0);
-    m1a = ldg4_volatile(m1p + (int64_t)yo * ws1);
-    m1b = ldg4_volatile(m1p + (int64_t)yo * ws1 + 4);
-    s1a = ldg4_volatile(s1p + (int64_t)yo * ws1);
-    s1b = ldg4_volatile(s1p + (int64_t)yo * ws1 + 4);
+  // Window statistics of the output rows stream through a per-warp shared-memory ring: one lane fetches a
+  // row's w-side {N*mu0, sd0} (128 positions) and u-side {mu1, sd1} (136 positions u = x0-dbase-4 ..) with two
+  // cp.async.bulk copies, XS_NST rows ahead, completion on an mbarrier -- no registers are held across the
+  // arithmetic and the L2 round trip is off the critical path.
+  XsStatRing& ring = rings[g];
+  const float2* wsrc = st0 + ((int64_t)b * H) * ws0 + x0;
+  const float2* usrc = st1 + ((int64_t)b * H) * ws1 + (x0 - dbase - 4 + uoff);
+  const uint32_t wbytes = (uint32_t)min(XS_W, ws0 - x0) * 8u;
+  const uint32_t ubytes = (uint32_t)min(XS_W + 8, ws1 - (x0 - dbase - 4 + uoff)) * 8u;
+  const int nrows = min(XH, H - y0);  // output rows of this tile
+  auto issue = [&](int e) {           // lane 0: fetch the statistics of output row y0 + e into stage e % XS_NST
+    const int st = e % XS_NST;
+    fence_proxy_async();
+    mbar_expect_tx(&ring.full[st], wbytes + ubytes);
+    bulk_load(&ring.w[st][0], wsrc + (int64_t)(y0 + e) * ws0, wbytes, &ring.full[st]);
+    bulk_load(&ring.u[st][0], usrc + (int64_t)(y0 + e) * ws1, ubytes, &ring.full[st]);
   };
-  fetch_stats(min(y0, H - 1));  // first emitting row: tile row BS - 1 <-> output row y0
+  if (lane == 0) {
+#pragma unroll
+    for (int st = 0; st < XS_NST; ++st) mbar_init(&ring.full[st], 1);
+    fence_barrier_init();
+    for (int e = 0; e < XS_NST && e < nrows; ++e) issue(e);
+  }
+  __syncwarp();
 #pragma unroll 1
   for (int blk = 0; blk < NBLK; ++blk) {
 #pragma unroll
@@ -482,6 +496,20 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
       }
       const int yo = y0 + r - 2 * R;                       // the window ending at tile row r
       const bool emit = (blk > 0 || j == BS - 1) && yo < H;  // warp-uniform
+      float2 wst[4], ust[8];
+      if (emit) {  // conflict-free 128-bit reads of this row's statistics, once per row
+        const int e = r - 2 * R, st = e % XS_NST;
+        mbar_wait(&ring.full[st], (uint32_t)(e / XS_NST) & 1u);
+        const float4* wp = reinterpret_cast<const float4*>(&ring.w[st][4 * lane]);
+        const float4* up = reinterpret_cast<const float4*>(&ring.u[st][4 * lane]);
+        const float4 w01 = wp[0], w23 = wp[1], u01 = up[0], u23 = up[1], u45 = up[2], u67 = up[3];
+        wst[0] = make_float2(w01.x, w01.y); wst[1] = make_float2(w01.z, w01.w);
+        wst[2] = make_float2(w23.x, w23.y); wst[3] = make_float2(w23.z, w23.w);
+        ust[0] = make_float2(u01.x, u01.y); ust[1] = make_float2(u01.z, u01.w);
+        ust[2] = make_float2(u23.x, u23.y); ust[3] = make_float2(u23.z, u23.w);
+        ust[4] = make_float2(u45.x, u45.y); ust[5] = make_float2(u45.z, u45.w);
+        ust[6] = make_float2(u67.x, u67.y); ust[7] = make_float2(u67.z, u67.w);
+      }
 #pragma unroll
       for (int dl = 0; dl < 4; ++dl) {
         float p[12], hs[4], S[4];
@@ -503,24 +531,18 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
           }
         }
         if (emit && dbase + dl < D) {
-          const float q0[4] = {q4.x, q4.y, q4.z, q4.w}, s0[4] = {s4.x, s4.y, s4.z, s4.w};
-          const float m1[8] = {m1a.x, m1a.y, m1a.z, m1a.w, m1b.x, m1b.y, m1b.z, m1b.w};
-          const float s1[8] = {s1a.x, s1a.y, s1a.z, s1a.w, s1b.x, s1b.y, s1b.z, s1b.w};
-          // 1e-8 routed through S: the norm must not be scheduled ahead of this row's sums, or the warp would
-          // sit on the statistics loads (issued a row ago) instead of overlapping them with the arithmetic
-          // (m1a.x, s1a.x are never used as statistics; folding them in keeps their registers reserved while the
-          // 128-bit loads are in flight -- a reuse as scratch would stall on the pending write)
-          const float eps8 = fmaf(s1a.x, 0.f, fmaf(m1a.x, 0.f, fmaf(S[0], 0.f, 1e-8f)));
+          // lane's four columns: {N*mu0, sd0} pairs; its eight u positions (x - dbase - 4 ..): {mu1, sd1} pairs, of
+          // which disparity dbase + dl uses positions 4 + k - dl
           float v[4];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const int ui = 4 + k - dl;
-            const float dot = fmaf(-q0[k], m1[ui], S[k]);
-            v[k] = dot * rcp_approx(fmaf(s0[k], s1[ui], eps8));  // untrusted outputs are overwritten by the fix-up kernel
+            const float2 ws_ = wst[k], us_ = ust[4 + k - dl];
+            v[k] = fmaf(-ws_.x, us_.x, S[k]) * rcp_approx(fmaf(ws_.y, us_.y, 1e-8f));  // untrusted outputs: see fix-up
           }
           float* dst = outp + dl * dstride + (int64_t)yo * W;
-          if (vec) {
-            *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+          if (x >= W) {
+          } else if (vec) {
+            __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -528,7 +550,11 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
           }
         }
       }
-      if (emit && yo + 1 < H && r + 1 < TH) fetch_stats(yo + 1);
+      if (emit) {  // every lane has read this stage: hand it to the row XS_NST further down
+        __syncwarp();
+        const int e = r - 2 * R;
+        if (lane == 0 && e + XS_NST < nrows) issue(e + XS_NST);
+      }
     }
   }
 }
@@ -543,51 +569,56 @@ __global__ void __launch_bounds__(256)
 xcorr_fixup_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
                    const uint8_t* __restrict__ g0, const uint8_t* __restrict__ g1, const unsigned* __restrict__ list,
                    const unsigned* __restrict__ count, int H, int W, int D, int ws0, int ws1, int uoff) {
-  __shared__ unsigned long long queue[8][64];  // output index (b*D+d)*H*W + h*W + w
+  __shared__ unsigned long long queue[8][64];  // (b*D + d) << 32 | (h*W + w)
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  const int dchunks = (D + 31) / 32;
-  const int64_t items = (int64_t)(*count) * dchunks;
+  const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+  const unsigned dchunks = (unsigned)(D + 31) / 32u;
+  const unsigned n = *count;
   const int64_t plane = (int64_t)H * W;
   int nq = 0;  // warp-uniform queue length
-  auto drain = [&](int n) {  // evaluate the first n (<= 32) queued outputs, one per lane
-    if (lane < n) {
-      const int64_t o = (int64_t)queue[wl][lane];
-      const int w = (int)(o % W), h = (int)((o / W) % H);
-      const int64_t bd = o / plane;
-      const int d = (int)(bd % D);
-      const int64_t b = bd / D;
-      out[o] = xcorr_fp64_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d);
+  auto drain = [&](int m) {  // evaluate the first m (<= 32) queued outputs, one per lane
+    if (lane < m) {
+      const unsigned long long e = queue[wl][lane];
+      const unsigned hw = (unsigned)(e & 0xffffffffu), bd = (unsigned)(e >> 32);  // h*W + w, b*D + d
+      const int w = (int)(hw % (unsigned)W), h = (int)(hw / (unsigned)W);
+      const int d = (int)(bd % (unsigned)D);
+      const int64_t b = bd / (unsigned)D;
+      out[(int64_t)bd * plane + hw] = xcorr_fp64_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d);
     }
     __syncwarp();
   };
-  for (int64_t it = (int64_t)blockIdx.x * (blockDim.x >> 5) + wl; it < items; it += nwarps) {
-    const unsigned e = list[it / dchunks];
-    const int d = (int)(it % dchunks) * 32 + lane;
-    const unsigned side = e >> 31;
-    const int64_t pos = e & 0x7fffffffu;
-    const int ws = side ? ws1 : ws0;
-    const int i = (int)(pos % ws), h = (int)((pos / ws) % H);
-    const int64_t b = pos / ((int64_t)ws * H);
-    const int w = side ? i - uoff + d : i;
-    bool hit = false;
-    if (d < D && w >= 0 && w < W) {
-      const unsigned Ls = side ? g1[pos] : g0[pos];
-      const unsigned Lo = side ? g0[(b * H + h) * ws0 + w] : g1[(b * H + h) * ws1 + (w - d + uoff)];
-      hit = Ls + Lo >= (unsigned)XS_LSUM && (side ? Ls > Lo : Ls >= Lo);
-    }
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
-    if (hit) {
-      const int slot = nq + __popc(m & ((1u << lane) - 1u));
-      queue[wl][slot] = (unsigned long long)(((b * D + d) * H + h) * W + w);
-    }
-    nq += __popc(m);
-    __syncwarp();
-    if (nq >= 32) {
-      drain(32);
-      if (lane < nq - 32) queue[wl][lane] = queue[wl][lane + 32];
-      nq -= 32;
+  // listed windows are spread over the warps; a warp sweeps the disparities of its window 32 at a time
+  for (unsigned it = blockIdx.x * (blockDim.x >> 5) + wl; it < n; it += nwarps) {
+    const unsigned e = list[it];
+    const unsigned side = e >> 31, pos = e & 0x7fffffffu;
+    const unsigned ws = side ? (unsigned)ws1 : (unsigned)ws0;
+    const unsigned row = pos / ws;                 // b*H + h
+    const int i = (int)(pos - row * ws), h = (int)(row % (unsigned)H);
+    const unsigned b = row / (unsigned)H;
+    const unsigned Ls = side ? g1[pos] : g0[pos];
+    const uint8_t* other = side ? g0 + (size_t)row * ws0 : g1 + (size_t)row * ws1;
+    for (unsigned ch = 0; ch < dchunks; ++ch) {
+      const int d = (int)(ch * 32u) + lane;
+      const int w = side ? i - uoff + d : i;
+      bool hit = false;
+      if (d < D && w >= 0 && w < W) {
+        const unsigned Lo = side ? other[w] : other[w - d + uoff];
+        hit = Ls + Lo >= (unsigned)XS_LSUM && (side ? Ls > Lo : Ls >= Lo);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m == 0u) continue;
+      if (hit) {
+        const int slot = nq + __popc(m & ((1u << lane) - 1u));
+        queue[wl][slot] = ((unsigned long long)(b * (unsigned)D + (unsigned)d) << 32) | (unsigned)(h * W + w);
+      }
+      nq += __popc(m);
       __syncwarp();
+      if (nq >= 32) {
+        drain(32);
+        if (lane < nq - 32) queue[wl][lane] = queue[wl][lane + 32];
+        nq -= 32;
+        __syncwarp();
+      }
     }
   }
   if (nq > 0) drain(nq);
@@ -634,13 +665,14 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
     cudaGetLastError();
     return false;
   }
-  float *mu0 = scratch, *sd0 = mu0 + n0, *mu1 = sd0 + n0, *sd1 = mu1 + n1;
-  unsigned* list = reinterpret_cast<unsigned*>(sd1 + n1);
+  float2* st0 = reinterpret_cast<float2*>(scratch);
+  float2* st1 = st0 + n0;
+  unsigned* list = reinterpret_cast<unsigned*>(st1 + n1);
   unsigned* count = list + n0 + n1;
   uint8_t* g0 = reinterpret_cast<uint8_t*>(count + 4);
   uint8_t* g1 = g0 + n0;
   const size_t st_smem = sizeof(double) * 2 * (ST_H + 2 * R) * ST_W + sizeof(float) * (ST_H + 2 * R) * (ST_W + 2 * R);
-  const size_t smem = sizeof(float) * TH * (XS_AW + XS_BW);
+  const size_t smem = sizeof(float) * TH * (XS_AW + XS_BW) + 4 * sizeof(XsStatRing);
   static const bool attr_ok =
       cudaFuncSetAttribute(xcorr_stats_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem) == cudaSuccess &&
       cudaFuncSetAttribute(xcorr_sep_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
@@ -650,14 +682,15 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
     return false;
   }
   xcorr_stats_kernel<BS><<<dim3((unsigned)cdiv(ws0, ST_W), (unsigned)cdiv(H, ST_H), (unsigned)B), 256, st_smem, st>>>(
-      in0, mu0, sd0, g0, (int)H, (int)W, (int)ws0, 0, float(BS * BS), 0u, list, count);
+      in0, st0, g0, (int)H, (int)W, (int)ws0, 0, float(BS * BS), 0u, list, count);
   xcorr_stats_kernel<BS><<<dim3((unsigned)cdiv(ws1, ST_W), (unsigned)cdiv(H, ST_H), (unsigned)B), 256, st_smem, st>>>(
-      in1, mu1, sd1, g1, (int)H, (int)W, (int)ws1, (int)uoff, 1.0f, 0x80000000u, list, count);
+      in1, st1, g1, (int)H, (int)W, (int)ws1, (int)uoff, 1.0f, 0x80000000u, list, count);
   const int vec = (W % 4 == 0) && !((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) |
                                      reinterpret_cast<uintptr_t>(out)) & 15);
   xcorr_sep_kernel<BS><<<dim3((unsigned)cdiv(W, XS_W), (unsigned)cdiv(H, XH), (unsigned)(B * ndchunks)), 128, smem, st>>>(
-      in0, in1, out, mu0, sd0, mu1, sd1, (int)H, (int)W, (int)D, (int)ws0, (int)ws1, (int)uoff, (int)ndchunks, vec);
-  xcorr_fixup_kernel<BS><<<148 * 4, 256, 0, st>>>(in0, in1, out, g0, g1, list, count, (int)H, (int)W, (int)D, (int)ws0,
+      in0, in1, out, st0, st1, (int)H, (int)W, (int)D, (int)ws0, (int)ws1, (int)uoff, (int)ndchunks, vec);
+  if (!g_xcorr_nofix)
+    xcorr_fixup_kernel<BS><<<148 * 3, 256, 0, st>>>(in0, in1, out, g0, g1, list, count, (int)H, (int)W, (int)D, (int)ws0,
                                                  (int)ws1, (int)uoff);
   count_launch(4);
   cudaFreeAsync(scratch, st);
