@@ -248,26 +248,52 @@ def run_b200_arm(args, rank, world, local_rank):
     st = stream.cuda_stream
     OPS = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums")
 
-    def step(k, ev=None):
-        d = sets[k % NSETS]
+    def launch_chain(d, st_, mark):
         p = {n: t.data_ptr() for n, t in d.items()}
-        mark = (lambda i: ev[i].record(stream)) if ev is not None else (lambda i: None)
         mark(0)
-        _lib.call("ctd_lcn_f32", p["im"], p["lcn"], p["std"], B, H, W, LCN_R, LCN_EPS, st)
+        _lib.call("ctd_lcn_f32", p["im"], p["lcn"], p["std"], B, H, W, LCN_R, LCN_EPS, st_)
         mark(1)
-        _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_sad"], B, 1, H, W, BS, 1, EPS, st)
+        _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_sad"], B, 1, H, W, BS, 1, EPS, st_)
         mark(2)
-        _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_sad"], B, 1, H, W, BS, 1, EPS, st)
+        _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_sad"], B, 1, H, W, BS, 1, EPS, st_)
         mark(3)
-        _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_cs"], B, 1, H, W, BS, 3, EPS, st)
+        _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_cs"], B, 1, H, W, BS, 3, EPS, st_)
         mark(4)
-        _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_cs"], B, 1, H, W, BS, 3, EPS, st)
+        _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_cs"], B, 1, H, W, BS, 3, EPS, st_)
         mark(5)
-        _lib.call("ctd_masked_sums_f32", p["out_sad"], p["std"], npx, p["sums"], ws.data_ptr(), st)
-        _lib.call("ctd_masked_sums_f32", p["out_cs"], p["std"], npx, p["sums"] + 8, ws.data_ptr(), st)
+        _lib.call("ctd_masked_sums_f32", p["out_sad"], p["std"], npx, p["sums"], ws.data_ptr(), st_)
+        _lib.call("ctd_masked_sums_f32", p["out_cs"], p["std"], npx, p["sums"] + 8, ws.data_ptr(), st_)
         mark(6)
+
+    # One CUDA graph per buffer set: the step's kernels plus event-record nodes between the ops, so neither
+    # `value` nor the per-op durations contain host launch latency (the kernels are 10-200 us long).
+    set_events = [[torch.cuda.Event(enable_timing=True, external=True) for _ in range(7)] for _ in range(NSETS)]
+    graphs, use_graph = [], not args.no_graph
+    if use_graph:
+        try:
+            launch_chain(sets[0], st, lambda i: None)  # load modules / set attributes before capturing
+            torch.cuda.synchronize(dev)
+            for si in range(NSETS):
+                c0 = _lib.launch_count()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    cs = torch.cuda.current_stream(dev)
+                    launch_chain(sets[si], cs.cuda_stream, lambda i, si=si, cs=cs: set_events[si][i].record(cs))
+                graphs.append(g)
+                kernels_per_graph = _lib.launch_count() - c0  # kernel nodes captured (counted by the library)
+        except Exception as e:  # capture unsupported: fall back to stream launches (says so in config)
+            print("bench: CUDA graph capture failed (%s); timing stream launches" % e, file=sys.stderr)
+            graphs, use_graph = [], False
+            torch.cuda.synchronize(dev)
+
+    def step(k):
+        si = k % NSETS
+        if use_graph:
+            graphs[si].replay()
+        else:
+            launch_chain(sets[si], st, lambda i: set_events[si][i].record(stream))
         if world > 1:
-            dist.all_reduce(d["sums"])  # 4 floats: the only inter-GPU traffic of the path
+            dist.all_reduce(sets[si]["sums"])  # 4 floats: the only inter-GPU traffic of the path
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -279,7 +305,6 @@ def run_b200_arm(args, rank, world, local_rank):
         step(k)
     sync_all()
     launches0 = _lib.launch_count()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(7)] for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -288,18 +313,21 @@ def run_b200_arm(args, rank, world, local_rank):
     sync_all()
     e0.record(stream)
     for k in range(args.steps):
-        step(k, evs[k])
+        step(k)
     e1.record(stream)
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
-    launches = _lib.launch_count() - launches0
     total_ms = e0.elapsed_time(e1)
     t = torch.tensor([total_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
-    op_ms = {n: float(np.mean([evs[k][i].elapsed_time(evs[k][i + 1]) for k in range(args.steps)])) for i, n in enumerate(OPS)}
+    # per-op durations: the event nodes of each set keep the timestamps of its LAST replay inside the timed
+    # region; NSETS samples per op, all taken from timed steps
+    used = [si for si in range(NSETS) if si < args.steps]
+    op_ms = {n: float(np.mean([set_events[si][i].elapsed_time(set_events[si][i + 1]) for si in used])) for i, n in enumerate(OPS)}
     op_ms["masked_sums"] /= 2  # two launches in that interval
+    launches = (_lib.launch_count() - launches0) if not use_graph else kernels_per_graph * args.steps
 
     # ---- e2e leg: the C ABI's host-buffer entry points, pinned host inputs/outputs, copies timed
     P = lambda t_: ctypes.c_void_p(t_.data_ptr())
@@ -351,6 +379,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "height": H, "width": W,
                        "l2_policy": "inputs and outputs rotate over %d buffer sets, %.0f MB touched > 126 MB L2" % (NSETS, footprint_mb),
+                       "launch": "one CUDA graph replay per step (kernel + event-record nodes)" if use_graph else "stream launches",
                        "parallelism": "batch-sharded x%d, one packed 4-float NCCL all-reduce per step" % world},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * npx / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
@@ -371,6 +400,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time plain stream launches instead of CUDA graph replays")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

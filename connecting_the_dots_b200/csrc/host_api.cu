@@ -2,8 +2,12 @@
 // ext_cpu.cpp entry points (torchext/ext/ext_cpu.cpp:14-184) -- binds to.  Inputs and outputs are
 // host memory (pinned memory makes the copies asynchronous DMA); each call stages through a
 // per-thread, grow-only device workspace on the current device, runs the same kernels as the
-// device-pointer API on a private stream, copies the results back and returns once they are in host
-// memory.  There is no CPU compute path: without a CUDA device these calls fail with CTD_ERR_CUDA.
+// device-pointer API, copies the results back and returns once they are in host memory.  The image-wise
+// ops (photometric, LCN, XCorrVol) are cut into chunks of whole images and software-pipelined over three
+// private streams -- upload of chunk i+1, kernels of chunk i and download of chunk i-1 run concurrently, so
+// with pinned buffers both PCIe directions stay busy and the kernels hide behind the copies.
+// There is no CPU compute path: without a CUDA device these calls fail with CTD_ERR_CUDA.
+#include <algorithm>
 #include <vector>
 
 #include "ctd_common.cuh"
@@ -14,7 +18,10 @@ struct Workspace {
   int device = -1;
   char* base = nullptr;
   size_t cap = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;                 // compute (and, for the unpipelined ops, copies)
+  cudaStream_t s_in = nullptr, s_out = nullptr;  // upload / download streams of the chunk pipeline
+  static constexpr int MAX_CHUNKS = 16;
+  cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_run[MAX_CHUNKS] = {};
 
   int ensure(size_t bytes) {
     int dev = 0;
@@ -23,10 +30,18 @@ struct Workspace {
       release();
       device = dev;
     }
-    if (!stream) CTD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    if (!stream) {
+      CTD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+      CTD_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+      CTD_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+      for (int i = 0; i < MAX_CHUNKS; ++i) {
+        CTD_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+        CTD_CUDA(cudaEventCreateWithFlags(&ev_run[i], cudaEventDisableTiming));
+      }
+    }
     if (bytes > cap) {
       if (base) {
-        CTD_CUDA(cudaStreamSynchronize(stream));
+        CTD_CUDA(cudaDeviceSynchronize());
         cudaFree(base);
         base = nullptr;
         cap = 0;
@@ -43,7 +58,16 @@ struct Workspace {
   void release() {
     if (stream) {
       cudaStreamSynchronize(stream);
+      cudaStreamSynchronize(s_in);
+      cudaStreamSynchronize(s_out);
       cudaStreamDestroy(stream);
+      cudaStreamDestroy(s_in);
+      cudaStreamDestroy(s_out);
+      for (int i = 0; i < MAX_CHUNKS; ++i) {
+        cudaEventDestroy(ev_in[i]);
+        cudaEventDestroy(ev_run[i]);
+      }
+      s_in = s_out = nullptr;
     }
     if (base) cudaFree(base);
     base = nullptr;
@@ -67,12 +91,21 @@ struct Carver {
   }
 };
 
+// images [i0, i1) of chunk c when B images are cut into n chunks
+static inline int64_t chunk_lo(int64_t B, int n, int c) { return B * c / n; }
+extern int g_host_chunks;  // ctd_set_option("host_chunks", n): upper bound on the pipeline depth (A/B runs)
+static inline int chunk_count(int64_t B) {
+  return (int)std::min<int64_t>(std::max<int64_t>(B, 1), std::min(std::max(g_host_chunks, 1), (int)Workspace::MAX_CHUNKS));
+}
+
 }  // namespace ctd
 
 using namespace ctd;
 
 #define H2D(dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, g_ws.stream))
 #define D2H(dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, g_ws.stream))
+#define H2D_ON(st, dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (st)))
+#define D2H_ON(st, dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (st)))
 #define RUN(call)                    \
   do {                               \
     if (int rc__ = (call)) return rc__; \
@@ -87,23 +120,33 @@ static int photometric_host(const float* es, const float* ta, const float* go, f
                o_gi = cv.add(gi ? nin : 0);
   RUN(g_ws.ensure(cv.total));
   char* b = g_ws.base;
-  if (nin) {
-    CTD_REQUIRE(es && ta, "photometric: null pointer");
-    H2D(b + o_es, es, nin);
-    H2D(b + o_ta, ta, nin);
+  if (nin) CTD_REQUIRE(es && ta, "photometric: null pointer");
+  if (gi) CTD_REQUIRE(go || !nout, "photometric_bwd: null grad_out");
+  if (B == 0) return CTD_OK;
+  const int nch = chunk_count(B);
+  const size_t in_img = nin / B, out_img = nout / B;  // bytes per image
+  for (int c = 0; c < nch; ++c) {
+    const int64_t i0 = chunk_lo(B, nch, c), nb = chunk_lo(B, nch, c + 1) - i0;
+    const size_t oi = (size_t)i0 * in_img, oo = (size_t)i0 * out_img;
+    if (in_img) {
+      H2D_ON(g_ws.s_in, b + o_es + oi, (const char*)es + oi, nb * in_img);
+      H2D_ON(g_ws.s_in, b + o_ta + oi, (const char*)ta + oi, nb * in_img);
+    }
+    if (gi && out_img) H2D_ON(g_ws.s_in, b + o_go + oo, (const char*)go + oo, nb * out_img);
+    CTD_CUDA(cudaEventRecord(g_ws.ev_in[c], g_ws.s_in));
+    CTD_CUDA(cudaStreamWaitEvent(g_ws.stream, g_ws.ev_in[c], 0));
+    if (out)
+      RUN(ctd_photometric_fwd_f32((float*)(b + o_es + oi), (float*)(b + o_ta + oi), (float*)(b + o_out + oo), nb, C, H, W, bs,
+                                  type, eps, g_ws.stream));
+    if (gi)
+      RUN(ctd_photometric_bwd_f32((float*)(b + o_es + oi), (float*)(b + o_ta + oi), (float*)(b + o_go + oo),
+                                  (float*)(b + o_gi + oi), nb, C, H, W, bs, type, eps, g_ws.stream));
+    CTD_CUDA(cudaEventRecord(g_ws.ev_run[c], g_ws.stream));
+    CTD_CUDA(cudaStreamWaitEvent(g_ws.s_out, g_ws.ev_run[c], 0));
+    if (out && out_img) D2H_ON(g_ws.s_out, (char*)out + oo, b + o_out + oo, nb * out_img);
+    if (gi && in_img) D2H_ON(g_ws.s_out, (char*)gi + oi, b + o_gi + oi, nb * in_img);
   }
-  if (out) {
-    RUN(ctd_photometric_fwd_f32((float*)(b + o_es), (float*)(b + o_ta), (float*)(b + o_out), B, C, H, W, bs, type, eps,
-                                g_ws.stream));
-    if (nout) D2H(out, b + o_out, nout);
-  }
-  if (gi) {
-    CTD_REQUIRE(go || !nout, "photometric_bwd: null grad_out");
-    if (nout) H2D(b + o_go, go, nout);
-    RUN(ctd_photometric_bwd_f32((float*)(b + o_es), (float*)(b + o_ta), (float*)(b + o_go), (float*)(b + o_gi), B, C, H,
-                                W, bs, type, eps, g_ws.stream));
-    if (nin) D2H(gi, b + o_gi, nin);
-  }
+  CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
   CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
   return CTD_OK;
 }
@@ -133,16 +176,26 @@ CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out
   const size_t o0 = cv.add(nin), o1 = cv.add(nin), oo = cv.add(nout);
   RUN(g_ws.ensure(cv.total));
   char* b = g_ws.base;
-  if (nin) {
-    CTD_REQUIRE(in0 && in1, "xcorrvol: null pointer");
-    H2D(b + o0, in0, nin);
-    H2D(b + o1, in1, nin);
+  if (nin) CTD_REQUIRE(in0 && in1, "xcorrvol: null pointer");
+  if (nout) CTD_REQUIRE(out, "xcorrvol: null output");
+  if (B == 0) return CTD_OK;
+  const int nch = chunk_count(B);
+  const size_t in_img = nin / B, out_img = nout / B;
+  for (int c = 0; c < nch; ++c) {
+    const int64_t i0 = chunk_lo(B, nch, c), nb = chunk_lo(B, nch, c + 1) - i0;
+    const size_t oi = (size_t)i0 * in_img, ov = (size_t)i0 * out_img;
+    if (in_img) {
+      H2D_ON(g_ws.s_in, b + o0 + oi, (const char*)in0 + oi, nb * in_img);
+      H2D_ON(g_ws.s_in, b + o1 + oi, (const char*)in1 + oi, nb * in_img);
+    }
+    CTD_CUDA(cudaEventRecord(g_ws.ev_in[c], g_ws.s_in));
+    CTD_CUDA(cudaStreamWaitEvent(g_ws.stream, g_ws.ev_in[c], 0));
+    RUN(ctd_xcorrvol_f32((float*)(b + o0 + oi), (float*)(b + o1 + oi), (float*)(b + oo + ov), nb, C, H, W, D, bs, g_ws.stream));
+    CTD_CUDA(cudaEventRecord(g_ws.ev_run[c], g_ws.stream));
+    CTD_CUDA(cudaStreamWaitEvent(g_ws.s_out, g_ws.ev_run[c], 0));
+    if (out_img) D2H_ON(g_ws.s_out, (char*)out + ov, b + oo + ov, nb * out_img);
   }
-  RUN(ctd_xcorrvol_f32((float*)(b + o0), (float*)(b + o1), (float*)(b + oo), B, C, H, W, D, bs, g_ws.stream));
-  if (nout) {
-    CTD_REQUIRE(out, "xcorrvol: null output");
-    D2H(out, b + oo, nout);
-  }
+  CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
   CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
   return CTD_OK;
 }
@@ -218,15 +271,23 @@ CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, i
   const size_t ox = cv.add(n), ol = cv.add(n), os = cv.add(n);
   RUN(g_ws.ensure(cv.total));
   char* b = g_ws.base;
-  if (n) {
-    CTD_REQUIRE(x && lcn && sd, "lcn: null pointer");
-    H2D(b + ox, x, n);
+  if (n) CTD_REQUIRE(x && lcn && sd, "lcn: null pointer");
+  if (N == 0 || n == 0) return CTD_OK;
+  const int nch = chunk_count(N);
+  const size_t img = n / N;
+  for (int c = 0; c < nch; ++c) {
+    const int64_t i0 = chunk_lo(N, nch, c), nb = chunk_lo(N, nch, c + 1) - i0;
+    const size_t o = (size_t)i0 * img;
+    H2D_ON(g_ws.s_in, b + ox + o, (const char*)x + o, nb * img);
+    CTD_CUDA(cudaEventRecord(g_ws.ev_in[c], g_ws.s_in));
+    CTD_CUDA(cudaStreamWaitEvent(g_ws.stream, g_ws.ev_in[c], 0));
+    RUN(ctd_lcn_f32((float*)(b + ox + o), (float*)(b + ol + o), (float*)(b + os + o), nb, H, W, r, eps, g_ws.stream));
+    CTD_CUDA(cudaEventRecord(g_ws.ev_run[c], g_ws.stream));
+    CTD_CUDA(cudaStreamWaitEvent(g_ws.s_out, g_ws.ev_run[c], 0));
+    D2H_ON(g_ws.s_out, (char*)lcn + o, b + ol + o, nb * img);
+    D2H_ON(g_ws.s_out, (char*)sd + o, b + os + o, nb * img);
   }
-  RUN(ctd_lcn_f32((float*)(b + ox), (float*)(b + ol), (float*)(b + os), N, H, W, r, eps, g_ws.stream));
-  if (n) {
-    D2H(lcn, b + ol, n);
-    D2H(sd, b + os, n);
-  }
+  CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
   CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
   return CTD_OK;
 }

@@ -26,24 +26,38 @@ except Exception:
     pass
 
 
-def timeit(fn, iters, warmup=5):
+NREP = 10  # launches per graph replay (cycling over the buffer sets)
+
+
+def timeit(fn, iters, warmup=5, nrep=NREP):
+    """fn(i, stream_handle) enqueues launch i.  nrep launches are captured into one CUDA graph and the graph
+    is replayed `iters` times between events, so host launch latency is not part of the figure; returns the
+    per-launch (median, min) in ms."""
+    cur = torch.cuda.current_stream()
     for i in range(warmup):
-        fn(i)
+        fn(i, cur.cuda_stream)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        cs = torch.cuda.current_stream().cuda_stream
+        for i in range(nrep):
+            fn(i, cs)
+    g.replay()
     torch.cuda.synchronize()
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(iters + 1)]
     evs[0].record()
     for i in range(iters):
-        fn(i)
+        g.replay()
         evs[i + 1].record()
     torch.cuda.synchronize()
-    ts = [evs[i].elapsed_time(evs[i + 1]) for i in range(iters)]
+    ts = [evs[i].elapsed_time(evs[i + 1]) / nrep for i in range(iters)]
     return float(np.median(ts)), float(np.min(ts))
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--only", default="photometric,lcn,xcorrvol,proj_nn,nn,crosscheck,reduce")
+    ap.add_argument("--only", default="calib,photometric,lcn,xcorrvol,proj_nn,nn,crosscheck,reduce")
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -69,27 +83,37 @@ def main():
         d["o1"] = torch.empty(B, 1, H, W, device=dev)
         d["o2"] = torch.empty(B, 1, H, W, device=dev)
         sets.append(d)
-    st = torch.cuda.current_stream().cuda_stream
 
+    if "calib" in only:
+        # what the memory system delivers at THIS problem size (launch ramp + tail included): a plain
+        # 2-reads-1-write elementwise pass and a 1-read-1-write copy over the same tensors, torch kernels
+        def f(i, st):
+            d = sets[i % NS]
+            torch.add(d["es"], d["ta"], out=d["o1"])  # torch launches on the current (capture) stream
+        add("calib_add_2r1w", *timeit(f, args.iters), 12 * npx)
+        def f(i, st):
+            d = sets[i % NS]
+            d["o1"].copy_(d["es"])
+        add("calib_copy_1r1w", *timeit(f, args.iters), 8 * npx)
     if "photometric" in only:
         for ty, name in enumerate(("mse", "sad", "census_mse", "census_sad")):
-            def f(i, ty=ty):
+            def f(i, st, ty=ty):
                 d = sets[i % NS]
                 _lib.call("ctd_photometric_fwd_f32", d["es"].data_ptr(), d["ta"].data_ptr(), d["o1"].data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
-            def g(i, ty=ty):
+            def g(i, st, ty=ty):
                 d = sets[i % NS]
                 _lib.call("ctd_photometric_bwd_f32", d["es"].data_ptr(), d["ta"].data_ptr(), d["go"].data_ptr(), d["o2"].data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
             add(name + "_fwd", *timeit(f, args.iters), 12 * npx)
             add(name + "_bwd", *timeit(g, args.iters), 16 * npx)
     if "lcn" in only:
-        def f(i):
+        def f(i, st):
             d = sets[i % NS]
             _lib.call("ctd_lcn_f32", d["im"].data_ptr(), d["o1"].data_ptr(), d["o2"].data_ptr(), B, H, W, 5, 0.05, st)
         add("lcn_fwd", *timeit(f, args.iters), 12 * npx)
     if "reduce" in only:
         ws = torch.zeros(int(_lib.lib().ctd_masked_sums_workspace_bytes()), dtype=torch.uint8, device=dev)
         out2 = torch.zeros(2, device=dev)
-        def f(i):
+        def f(i, st):
             d = sets[i % NS]
             _lib.call("ctd_masked_sums_f32", d["es"].data_ptr(), d["std"].data_ptr(), npx, out2.data_ptr(), ws.data_ptr(), st)
         add("masked_sums", *timeit(f, args.iters), 8 * npx)
@@ -97,10 +121,10 @@ def main():
         D = 128
         vols = [torch.empty(B, D, H, W, device=dev) for _ in range(2)]
         for bs in (9, 5):
-            def f(i, bs=bs):
+            def f(i, st, bs=bs):
                 d = sets[i % NS]
                 _lib.call("ctd_xcorrvol_f32", d["ta"].data_ptr(), d["pat_lcn"].data_ptr(), vols[i % 2].data_ptr(), B, 1, H, W, D, bs, st)
-            add("xcorrvol_D128_bs%d" % bs, *timeit(f, max(3, args.iters // 6), warmup=1), (8 + 4 * D) * npx)
+            add("xcorrvol_D128_bs%d" % bs, *timeit(f, max(3, args.iters // 6), warmup=1, nrep=2), (8 + 4 * D) * npx)
         del vols
     if "proj_nn" in only:
         T = 4
@@ -111,7 +135,7 @@ def main():
         x1 = torch.from_numpy(np.stack([xyz[j] for i, j in pairs])).to(dev)
         out = torch.empty(len(pairs), H, W, dtype=torch.int64, device=dev)
         for ps in (3, 5):
-            def f(i, ps=ps):
+            def f(i, st, ps=ps):
                 _lib.call("ctd_proj_nn_f32", x0.data_ptr(), x1.data_ptr(), Kd.data_ptr(), out.data_ptr(), len(pairs), H, W, ps, st)
             add("proj_nn_ps%d_12pairs" % ps, *timeit(f, args.iters), 32 * len(pairs) * H * W, px=len(pairs) * H * W,
                 extra={"valid_frac": float((out >= 0).float().mean())})
@@ -120,7 +144,7 @@ def main():
             i01 = out.view(-1)
             i10 = out.view(len(pairs), -1).flip(0).contiguous().view(-1)
             m = torch.empty(n, dtype=torch.uint8, device=dev)
-            def f(i):
+            def f(i, st):
                 _lib.call("ctd_crosscheck", i01.data_ptr(), i10.data_ptr(), m.data_ptr(), n, n, st)
             add("crosscheck_%d" % n, *timeit(f, args.iters), 17 * n, px=n)
     if "nn" in only:
@@ -129,7 +153,7 @@ def main():
         p0 = torch.from_numpy(rng.randn(n, 3).astype(np.float32)).to(dev)
         p1 = torch.from_numpy(rng.randn(n, 3).astype(np.float32)).to(dev)
         out = torch.empty(n, dtype=torch.int64, device=dev)
-        def f(i):
+        def f(i, st):
             _lib.call("ctd_nn_f32", p0.data_ptr(), p1.data_ptr(), out.data_ptr(), n, n, st)
         ms, mn = timeit(f, args.iters)
         res["ops"]["nn_16384x16384"] = {"ms_median": ms, "ms_min": mn, "gpair_s": n * n / ms / 1e6}
