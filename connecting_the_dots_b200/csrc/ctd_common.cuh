@@ -15,6 +15,11 @@ char* err_buf();
 int fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
 
+// Stream-ordered scratch memory from a library-owned pool per device that keeps its memory between calls (no
+// torch dependency, no synchronisation, usable under CUDA-graph capture).  nullptr when unavailable.
+void* scratch_alloc(size_t bytes, cudaStream_t st);
+void scratch_free(void* p, cudaStream_t st);
+
 // Check the launch that was just issued (no synchronisation, like a normal async API).
 int check_launch(const char* what);
 

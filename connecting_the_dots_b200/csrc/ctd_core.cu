@@ -1,5 +1,6 @@
 // Library-wide state of libctd_b200: error messages, launch accounting, options.
 #include <atomic>
+#include <mutex>
 #include <stdarg.h>
 #include <string.h>
 
@@ -28,6 +29,43 @@ int fail(int code, const char* fmt, ...) {
 }
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static cudaMemPool_t scratch_pool() {
+  static std::mutex mtx;
+  static cudaMemPool_t pools[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mtx);
+  if (!pools[dev]) {
+    cudaMemPoolProps props = {};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = dev;
+    cudaMemPool_t p = nullptr;
+    if (cudaMemPoolCreate(&p, &props) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
+    pools[dev] = p;
+  }
+  return pools[dev];
+}
+
+void* scratch_alloc(size_t bytes, cudaStream_t st) {
+  cudaMemPool_t pool = scratch_pool();
+  void* p = nullptr;
+  if (!pool || cudaMallocFromPoolAsync(&p, bytes, pool, st) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+
+void scratch_free(void* p, cudaStream_t st) {
+  if (p) cudaFreeAsync(p, st);
+}
 
 int check_launch(const char* what) {
   cudaError_t e = cudaPeekAtLastError();

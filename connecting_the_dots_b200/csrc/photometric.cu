@@ -525,6 +525,52 @@ census_sad_bwd_fixup(const float* __restrict__ es, const float* __restrict__ ta,
   }
 }
 
+// the same recomputation driven by a list of pixel indices (written by the tile kernel): one warp per listed
+// pixel, so the work is balanced however the near-ties cluster (image borders, flat regions)
+__device__ __forceinline__ void census_sad_bwd_exact_pixel(const float* __restrict__ es, const float* __restrict__ ta,
+                                                           const float* __restrict__ go, float* __restrict__ gi, int64_t i,
+                                                           int C, int H, int W, float eps, int lane) {
+  const int x = i % W, y = (i / W) % H;
+  const int64_t nc = i / ((int64_t)W * H);
+  const float* ep = es + nc * H * W;
+  const float* tp = ta + nc * H * W;
+  const float* gp = go + (nc / C) * H * W;
+  const float ei = __ldg(ep + (int64_t)y * W + x), ti = __ldg(tp + (int64_t)y * W + x), gc = __ldg(gp + (int64_t)y * W + x);
+  float acc = 0.f;
+  for (int t = lane; t < 81; t += 32) {
+    const int dy = t / 9 - R9, dx = t % 9 - R9;
+    const int qy = y + dy, qx = x + dx;
+    const int cy = clampi(qy, 0, H - 1), cx = clampi(qx, 0, W - 1);
+    const float des = ei - __ldg(ep + (int64_t)cy * W + cx), dta = ti - __ldg(tp + (int64_t)cy * W + cx);
+    float gq = 0.f;
+    if (qy == cy && qx == cx) {
+      const float mx = x == 0 ? float(R9 + 1 - dx) : (x == W - 1 ? float(R9 + 1 + dx) : 1.f);
+      const float my = y == 0 ? float(R9 + 1 - dy) : (y == H - 1 ? float(R9 + 1 + dy) : 1.f);
+      gq = __ldg(gp + (int64_t)cy * W + cx) * (mx * my);
+    }
+    const float s = __fadd_rn(__fmul_rn(des, des), eps);
+    const float q1 = __fdiv_rn(des, __fsqrt_rn(s));
+    const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
+    const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
+    const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
+    const float r1 = rsqrt_approx(s);
+    acc = fmaf(r1 * r1 * r1, sgn(d_tap) * gq - sgn(d_ctr) * gc, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) gi[i] = acc * (0.5f * eps * INV81);
+}
+
+__global__ void __launch_bounds__(256)
+census_sad_bwd_fixup_list(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
+                          float* __restrict__ gi, const unsigned* __restrict__ list, const unsigned* __restrict__ count,
+                          int C, int H, int W, float eps) {
+  const int lane = threadIdx.x & 31;
+  const unsigned nwarps = gridDim.x * (blockDim.x >> 5), n = *count;
+  for (unsigned it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < n; it += nwarps)
+    census_sad_bwd_exact_pixel(es, ta, go, gi, (int64_t)list[it], C, H, W, eps, lane);
+}
+
 __device__ __forceinline__ float xor_sign(float v, float s) {  // v * sign(s) for s != 0
   return __int_as_float(__float_as_int(v) ^ (__float_as_int(s) & 0x80000000));
 }
@@ -536,7 +582,8 @@ __device__ __forceinline__ float xor_sign(float v, float s) {  // v * sign(s) fo
 template <int TYPE, bool BORDER>
 __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[CE_W], float (*Gs)[CE_W],
                                                 float* __restrict__ gi, int x0, int y0, int H, int W,
-                                                float eps, int vec, int tx, int ty) {
+                                                float eps, int vec, int tx, int ty, unsigned* __restrict__ list,
+                                                unsigned* __restrict__ count, unsigned plane_base) {
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     const int yl = ty + 16 * half;
@@ -567,7 +614,9 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
       unpack12(t, &Ts[yl + dy][4 * tx]);
       unpack12(g, &Gs[yl + dy][4 * tx]);
       const float my = BORDER ? fmaf(sy, float(dy - R9), by) : 1.f;
-      const bool ctr_row = dy == R9;
+      // rows whose clamped tap row is the pixel's own row: the centre row, and at the first / last image row
+      // every window row beyond the border
+      const bool ctr_row = dy == R9 || (BORDER && ((sy < 0.f && dy < R9) || (sy > 0.f && dy > R9)));
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
 #pragma unroll
@@ -588,23 +637,55 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
             const float sr3 = __uint_as_float(__float_as_uint(r3) | (__float_as_uint(dd) & 0x80000000u));
             acc[k] = fmaf(sr3, gq + gc[k], acc[k]);
             float mag = fabsf(dd);
-            if (dx == R9) mag = ctr_row ? 1.f : mag;  // the centre tap is not a near-tie
+            // a tap that clamps onto the pixel itself has dd = +0 exactly (sign 0 in the reference): not a
+            // near-tie; its +r3 * G contribution is taken out after the loop
+            const bool ctr_col = dx == R9 || (BORDER && (dx < R9 ? sx[k] < 0.f : sx[k] > 0.f));
+            if (dx == R9 || BORDER) mag = (ctr_row && ctr_col) ? 1.f : mag;
             near0[k] = fminf(near0[k], mag);
           }
         }
       }
     }
     if (TYPE == 3) {
+      // self taps: the centre (counted with M(i,i) = bx*by as a tap of itself, plus once as the centre) and, at
+      // the image border, the bx*by - 1 window positions outside the image that clamp back onto the pixel
+      // (no real centre there, so only the "pixel as centre" half): r0^3 * gc * (2 * bx*by) in total
       const float r0 = rsqrt_approx(eps);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) acc[k] -= r0 * r0 * r0 * fmaf(bx[k] * by, gc[k], gc[k]);  // centre tap: M(i,i) = bx*by
+      for (int k = 0; k < 4; ++k) acc[k] -= r0 * r0 * r0 * (2.f * bx[k] * by) * gc[k];
     }
     const float scale = 0.5f * eps * INV81;
     float r[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       r[k] = acc[k] * scale;
-      if (TYPE == 3 && near0[k] < SIGN_GUARD) r[k] = __uint_as_float(SIGN_MARKER);  // census_sad_bwd_fixup redoes it
+      if (TYPE == 3 && list == nullptr && near0[k] < SIGN_GUARD) r[k] = __uint_as_float(SIGN_MARKER);  // scan fix-up redoes it
+    }
+    if (TYPE == 3 && list != nullptr) {
+      // near-tie pixels go on the fix-up list: one atomic per warp (ballot + prefix over the lanes)
+      unsigned mine = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) mine |= (near0[k] < SIGN_GUARD && gx + k < W) ? (1u << k) : 0u;
+      const unsigned active = __activemask();
+      if (__any_sync(active, mine != 0u)) {
+        const int lane = threadIdx.x & 31;
+        // lanes that skipped this row (gy >= H) are not in `active`: build the prefix from the active lanes only
+        int prefix = 0, total = 0;
+        for (unsigned m = active; m; m &= m - 1) {
+          const int src = __ffs(m) - 1;
+          const int c = __shfl_sync(active, __popc(mine), src);
+          if (src < lane) prefix += c;
+          total += c;
+        }
+        unsigned base = 0;
+        const int leader = __ffs(active) - 1;
+        if (lane == leader) base = atomicAdd(count, (unsigned)total);
+        base = __shfl_sync(active, base, leader);
+        unsigned slot = base + (unsigned)prefix;
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (mine & (1u << k)) list[slot++] = plane_base + (unsigned)(gy * W + gx + k);
+      }
     }
     float* dst = gi + (int64_t)gy * W + gx;
     if (vec) {
@@ -620,7 +701,8 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
 template <int TYPE>
 __global__ void __launch_bounds__(256)
 photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
-                  float* __restrict__ gi, int C, int H, int W, float eps, int vec) {
+                  float* __restrict__ gi, int C, int H, int W, float eps, int vec, unsigned* __restrict__ list,
+                  unsigned* __restrict__ count) {
   __shared__ __align__(16) float Es[CE_H][CE_W];
   __shared__ __align__(16) float Ts[CE_H][CE_W];
   __shared__ __align__(16) float Gs[CE_H][CE_W];
@@ -637,8 +719,9 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
     load_halo_tile<true>(Ts, ta + (n * C + c) * plane, x0, y0, H, W, vec, tid);
     __syncthreads();
     float* gic = gi + (n * C + c) * plane;
-    if (border) census_bwd_tile<TYPE, true>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty);
-    else census_bwd_tile<TYPE, false>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty);
+    const unsigned pb = (unsigned)((n * C + c) * plane);
+    if (border) census_bwd_tile<TYPE, true>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb);
+    else census_bwd_tile<TYPE, false>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb);
   }
 }
 
@@ -745,12 +828,25 @@ CTD_API int ctd_photometric_bwd_f32(const float* es, const float* ta, const floa
       else photo_bwd_box9<1><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, vec);
     } else {
       dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
-      if (type == 2) photo_bwd_census9<2><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec);
+      if (type == 2) photo_bwd_census9<2><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
       else {
-        photo_bwd_census9<3><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec);
+        // near-tie pixels: listed by the tile kernel when scratch memory is available, else marked and found by a scan
         const int64_t total = (int64_t)nb * C * H * W;
-        const int fgrid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
-        census_sad_bwd_fixup<<<fgrid, 256, 0, st>>>(e, t, g, o, total, (int)C, (int)H, (int)W, eps);
+        unsigned* scratch = total < ((int64_t)1 << 32) ? static_cast<unsigned*>(scratch_alloc((size_t)(total + 1) * 4, st)) : nullptr;
+        if (scratch && cudaMemsetAsync(scratch, 0, 4, st) != cudaSuccess) {
+          cudaGetLastError();
+          scratch_free(scratch, st);
+          scratch = nullptr;
+        }
+        if (scratch) {
+          photo_bwd_census9<3><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec, scratch + 1, scratch);
+          census_sad_bwd_fixup_list<<<148 * 4, 256, 0, st>>>(e, t, g, o, scratch + 1, scratch, (int)C, (int)H, (int)W, eps);
+          scratch_free(scratch, st);
+        } else {
+          photo_bwd_census9<3><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
+          const int fgrid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
+          census_sad_bwd_fixup<<<fgrid, 256, 0, st>>>(e, t, g, o, total, (int)C, (int)H, (int)W, eps);
+        }
         count_launch();
       }
     }

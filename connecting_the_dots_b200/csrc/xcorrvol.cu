@@ -5,7 +5,6 @@
 // of in1 at (h, w-d); rows replicate-clamped, in0 columns clamped, in1 columns clamped AFTER the
 // disparity shift.  The reference has no batch dimension; here B images are one launch.
 #include <algorithm>
-#include <mutex>
 
 #include "ctd_common.cuh"
 #include "ctd_tma.cuh"
@@ -624,31 +623,6 @@ xcorr_fixup_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
   if (nq > 0) drain(nq);
 }
 
-// stream-ordered scratch for the statistics planes: a library-owned memory pool per device that keeps its
-// memory between calls (no torch dependency, no synchronisation, usable under CUDA-graph capture)
-static cudaMemPool_t scratch_pool() {
-  static std::mutex mtx;
-  static cudaMemPool_t pools[64] = {};
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
-  std::lock_guard<std::mutex> lk(mtx);
-  if (!pools[dev]) {
-    cudaMemPoolProps props = {};
-    props.allocType = cudaMemAllocationTypePinned;
-    props.location.type = cudaMemLocationTypeDevice;
-    props.location.id = dev;
-    cudaMemPool_t p = nullptr;
-    if (cudaMemPoolCreate(&p, &props) != cudaSuccess) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    uint64_t keep = UINT64_MAX;
-    cudaMemPoolSetAttribute(p, cudaMemPoolAttrReleaseThreshold, &keep);
-    pools[dev] = p;
-  }
-  return pools[dev];
-}
-
 template <int BS>
 static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int64_t B, int64_t H, int64_t W, int64_t D,
                              cudaStream_t st) {
@@ -657,14 +631,9 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
   const int64_t uoff = ndchunks * XS_DT, ws0 = cdiv(W, 4) * 4, ws1 = uoff + ws0;
   const int64_t n0 = B * H * ws0, n1 = B * H * ws1;
   if (B * ndchunks > 65535 || cdiv(H, XH) > 65535 || cdiv(H, ST_H) > 65535 || n1 >= ((int64_t)1 << 31)) return false;
-  cudaMemPool_t pool = scratch_pool();
-  if (!pool) return false;
-  float* scratch = nullptr;
   const size_t words = (size_t)(3 * n0 + 3 * n1 + 4) + (size_t)(n0 + n1 + 3) / 4;
-  if (cudaMallocFromPoolAsync((void**)&scratch, words * sizeof(float), pool, st) != cudaSuccess) {
-    cudaGetLastError();
-    return false;
-  }
+  float* scratch = static_cast<float*>(scratch_alloc(words * sizeof(float), st));
+  if (!scratch) return false;
   float2* st0 = reinterpret_cast<float2*>(scratch);
   float2* st1 = st0 + n0;
   unsigned* list = reinterpret_cast<unsigned*>(st1 + n1);
@@ -678,7 +647,7 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
       cudaFuncSetAttribute(xcorr_sep_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
   if (!attr_ok || cudaMemsetAsync(count, 0, sizeof(unsigned), st) != cudaSuccess) {
     cudaGetLastError();
-    cudaFreeAsync(scratch, st);
+    scratch_free(scratch, st);
     return false;
   }
   xcorr_stats_kernel<BS><<<dim3((unsigned)cdiv(ws0, ST_W), (unsigned)cdiv(H, ST_H), (unsigned)B), 256, st_smem, st>>>(
@@ -693,7 +662,7 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
     xcorr_fixup_kernel<BS><<<148 * 3, 256, 0, st>>>(in0, in1, out, g0, g1, list, count, (int)H, (int)W, (int)D, (int)ws0,
                                                  (int)ws1, (int)uoff);
   count_launch(4);
-  cudaFreeAsync(scratch, st);
+  scratch_free(scratch, st);
   return true;
 }
 
