@@ -12,6 +12,7 @@ int g_force_generic = 0;  // tests: route every op through its generic kernel
 int g_xcorr_direct = 0;   // tests / A-B runs: XCorrVol through the direct (centred two-pass) tile kernel
 int g_xcorr_nofix = 0;    // experiments: skip XCorrVol's fix-up pass (fast-path error measurements)
 int g_host_chunks = 4;     // host-buffer API: image chunks per call (copies below ~2 MB lose PCIe efficiency)
+extern int g_census_pairs;
 int g_disable_tma = 0;    // tests / A-B runs: use the shared-memory tile kernels instead of the TMA ones
 static std::atomic<uint64_t> g_launches{0};
 
@@ -97,6 +98,10 @@ CTD_API int ctd_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "host_chunks")) {
     ctd::g_host_chunks = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "census_pairs")) {
+    ctd::g_census_pairs = value;
     return CTD_OK;
   }
   if (name && !strcmp(name, "disable_tma")) {

@@ -26,6 +26,8 @@ int box9_tma_fwd(const float* es, const float* ta, float* out, int64_t B, int64_
                  cudaStream_t st);
 int box9_tma_bwd(const float* es, const float* ta, const float* go, float* gi, int64_t B, int64_t C, int64_t H,
                  int64_t W, int type, cudaStream_t st);
+int census_pairs_fwd(const float* es, const float* ta, float* out, int64_t B, int64_t C, int64_t H, int64_t W, int type,
+                     float eps, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // generic kernels (any block size, channel count, size; float or double)
@@ -782,6 +784,7 @@ CTD_API int ctd_photometric_fwd_f32(const float* es, const float* ta, float* out
   if (!fast9_ok(bs, H, W) || C < 1 || B < 1) return fwd_impl<float>(es, ta, out, B, C, H, W, bs, type, eps, st);
   if (int rc = check_common(es, ta, out, B, C, H, W, bs, type)) return rc;
   if (type <= 1 && box9_tma_fwd(es, ta, out, B, C, H, W, type, st)) return check_launch("photometric_fwd(tma)");
+  if (type >= 2 && census_pairs_fwd(es, ta, out, B, C, H, W, type, eps, st)) return check_launch("photometric_fwd(census pairs)");
   const int vec = vec_ok(W, es, ta, out, out);
   for (int64_t b0 = 0; b0 < B; b0 += 32768) {
     const int nb = (int)std::min<int64_t>(32768, B - b0);

@@ -60,6 +60,8 @@ SHAPES = [  # B, C, H, W, bs -- ragged widths (scalar path), multi-tile, tiny (g
     (2, 1, 33, 132, 9), (1, 1, 40, 67, 9), (1, 2, 64, 256, 9), (1, 1, 9, 9, 9), (3, 1, 70, 200, 9),
     (1, 3, 17, 23, 9), (1, 1, 5, 6, 9), (1, 1, 3, 3, 9), (2, 1, 20, 31, 5), (1, 2, 16, 16, 4), (1, 1, 12, 40, 1),
     (1, 1, 8, 300, 9), (1, 1, 300, 12, 9),
+    # census pair kernels: one full 120-column strip exactly, full + leftover strip, packed leftover strips only
+    (1, 1, 48, 120, 9), (2, 1, 40, 160, 9), (3, 1, 100, 44, 9), (1, 1, 16, 16, 9),
 ]
 
 
@@ -96,6 +98,43 @@ def test_photometric_generic_kernels_agree(tx, ty):
     fwd2, bwd2 = photometric_both(tx, es, ta, go, 9, ty, 0.3)
     assert_close(fwd2, fwd, what="fast vs generic fwd")
     assert_close(bwd2, bwd, what="fast vs generic bwd")
+
+
+@pytest.mark.parametrize("ty", (2, 3))
+def test_census_pair_kernels_match_gather_kernels(tx, ty):
+    """A/B inside the library: the pair-symmetric census kernels against the shared-memory gather kernels."""
+    from connecting_the_dots_b200 import _lib
+    rng = np.random.RandomState(11)
+    es = rng.randn(2, 1, 150, 280).astype(np.float32)
+    ta = (es + 0.5 * rng.randn(2, 1, 150, 280)).astype(np.float32)
+    go = rng.rand(2, 1, 150, 280).astype(np.float32)
+    _lib.set_option("census_pairs", 1)
+    try:
+        fwd, bwd = photometric_both(tx, es, ta, go, 9, ty, 0.5)
+        _lib.set_option("census_pairs", 0)
+        fwd0, bwd0 = photometric_both(tx, es, ta, go, 9, ty, 0.5)
+    finally:
+        _lib.set_option("census_pairs", 2)
+    assert_close(fwd, fwd0, what="pairs vs gather fwd")
+    assert_close(bwd, bwd0, what="pairs vs gather bwd")
+    assert_close(fwd, oracle.photometric_loss_forward(es, ta, 9, ty, 0.5), what="pairs vs oracle fwd")
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 48, 120), (2, 1, 40, 160), (3, 1, 100, 44), (1, 1, 16, 16), (2, 1, 33, 132)])
+def test_census_pair_kernel_strip_layouts(tx, shape):
+    """Forced pair kernel on widths that give one exact strip, a full + a leftover strip, packed leftover strips."""
+    from connecting_the_dots_b200 import _lib
+    B, C, H, W = shape
+    rng = np.random.RandomState(W)
+    es = rng.randn(B, C, H, W).astype(np.float32)
+    ta = (es + 0.7 * rng.randn(B, C, H, W)).astype(np.float32)
+    _lib.set_option("census_pairs", 1)
+    try:
+        for ty in (2, 3):
+            got = tx.photometric_loss(cu(es), cu(ta), 9, TYPES[ty], 0.5).cpu().numpy()
+            assert_close(got, oracle.photometric_loss_forward(es, ta, 9, ty, 0.5), what="pairs fwd %s" % TYPES[ty])
+    finally:
+        _lib.set_option("census_pairs", 2)
 
 
 @pytest.mark.parametrize("ty", (1, 3))
