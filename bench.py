@@ -9,8 +9,12 @@ A "step" is one pass of the hot path over one batch of synthetic 480x640 dot-pat
 (SURVEY.md section 8d data), batch 8 per GPU:
     LCN(5, 0.05) forward  ->  PhotometricLoss 'sad' ("l1") forward + backward
                           ->  PhotometricLoss 'census_sad' (the reference's structural mode, standing in
-                              for "ssim") forward + backward
+                              for "ssim") forward + backward -- through
+                              ctd_photometric_fwd_bwd_f32, which produces the loss map and the gradient in
+                              ONE kernel (grad_out = std / sum(std) is an input, as in networks.py:377)
                           ->  the caller's masked loss reduction (networks.py:377), twice
+The same chain with census_sad forward and backward as two separate calls (what torch autograd does with
+photometric_loss) is timed as well and reported as `separate_calls`.
 and, for N > 1, one packed NCCL all-reduce of the four loss scalars.  value = pixels per second through
 that whole chain (N * B * H * W / step time); per-op figures are in "ops".
 
@@ -39,9 +43,10 @@ H, W, B_PER_GPU, BS, EPS, LCN_R, LCN_EPS = 480, 640, 8, 9, 0.5, 5, 0.05
 NSETS = 4
 METRIC = "Mpix/s through LCN fwd + PhotometricLoss sad fwd+bwd + census_sad fwd+bwd (batch 8, 480x640); per-op Mpix/s in ops"
 WORKLOAD = ("configs[1]: LCN(5,0.05) fwd + PhotometricLoss l1(sad) fwd+bwd + census_sad (stands in for ssim) fwd+bwd "
-            "+ masked loss sums, batch 8 per GPU, 480x640, block 9, eps 0.5, C=1")
+            "(one fused call) + masked loss sums, batch 8 per GPU, 480x640, block 9, eps 0.5, C=1")
 # algorithmic bytes per pixel, fp32, C=1
 BYTES_PER_PX = {"lcn_fwd": 12, "sad_fwd": 12, "sad_bwd": 16, "census_sad_fwd": 12, "census_sad_bwd": 16,
+                "census_sad_fwd_bwd": 20,  # fused: es, ta, grad_out in; loss map, grad_in out -- each tensor once
                 "masked_sums": 8}
 
 
@@ -246,32 +251,46 @@ def run_b200_arm(args, rank, world, local_rank):
     footprint_mb = NSETS * 10 * npx * 4 / 1e6
     stream = torch.cuda.current_stream(dev)
     st = stream.cuda_stream
-    OPS = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums")
+    OPS = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd_bwd", "masked_sums")
+    OPS_SEP = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums")
 
-    def launch_chain(d, st_, mark):
+    def launch_chain(d, st_, mark, fused=True):
         p = {n: t.data_ptr() for n, t in d.items()}
-        mark(0)
+        i = 0
+        mark(i)
         _lib.call("ctd_lcn_f32", p["im"], p["lcn"], p["std"], B, H, W, LCN_R, LCN_EPS, st_)
-        mark(1)
+        i += 1
+        mark(i)
         _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_sad"], B, 1, H, W, BS, 1, EPS, st_)
-        mark(2)
+        i += 1
+        mark(i)
         _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_sad"], B, 1, H, W, BS, 1, EPS, st_)
-        mark(3)
-        _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_cs"], B, 1, H, W, BS, 3, EPS, st_)
-        mark(4)
-        _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_cs"], B, 1, H, W, BS, 3, EPS, st_)
-        mark(5)
+        i += 1
+        mark(i)
+        if fused:
+            _lib.call("ctd_photometric_fwd_bwd_f32", p["es"], p["ta"], p["go"], p["out_cs"], p["gi_cs"], B, 1, H, W, BS, 3, EPS, st_)
+        else:
+            _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_cs"], B, 1, H, W, BS, 3, EPS, st_)
+            i += 1
+            mark(i)
+            _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_cs"], B, 1, H, W, BS, 3, EPS, st_)
+        i += 1
+        mark(i)
         _lib.call("ctd_masked_sums_f32", p["out_sad"], p["std"], npx, p["sums"], ws.data_ptr(), st_)
         _lib.call("ctd_masked_sums_f32", p["out_cs"], p["std"], npx, p["sums"] + 8, ws.data_ptr(), st_)
-        mark(6)
+        i += 1
+        mark(i)
 
     # One CUDA graph per buffer set: the step's kernels plus event-record nodes between the ops, so neither
     # `value` nor the per-op durations contain host launch latency (the kernels are 10-200 us long).
-    set_events = [[torch.cuda.Event(enable_timing=True, external=True) for _ in range(7)] for _ in range(NSETS)]
-    graphs, use_graph = [], not args.no_graph
+    set_events = [[torch.cuda.Event(enable_timing=True, external=True) for _ in range(len(OPS) + 1)] for _ in range(NSETS)]
+    sep_events = [[torch.cuda.Event(enable_timing=True, external=True) for _ in range(len(OPS_SEP) + 1)] for _ in range(NSETS)]
+    graphs, sep_graphs, use_graph = [], [], not args.no_graph
+    kernels_per_graph = 0
     if use_graph:
         try:
             launch_chain(sets[0], st, lambda i: None)  # load modules / set attributes before capturing
+            launch_chain(sets[0], st, lambda i: None, fused=False)
             torch.cuda.synchronize(dev)
             for si in range(NSETS):
                 c0 = _lib.launch_count()
@@ -281,10 +300,24 @@ def run_b200_arm(args, rank, world, local_rank):
                     launch_chain(sets[si], cs.cuda_stream, lambda i, si=si, cs=cs: set_events[si][i].record(cs))
                 graphs.append(g)
                 kernels_per_graph = _lib.launch_count() - c0  # kernel nodes captured (counted by the library)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    cs = torch.cuda.current_stream(dev)
+                    launch_chain(sets[si], cs.cuda_stream, lambda i, si=si, cs=cs: sep_events[si][i].record(cs), fused=False)
+                sep_graphs.append(g)
         except Exception as e:  # capture unsupported: fall back to stream launches (says so in config)
             print("bench: CUDA graph capture failed (%s); timing stream launches" % e, file=sys.stderr)
-            graphs, use_graph = [], False
+            graphs, sep_graphs, use_graph = [], [], False
             torch.cuda.synchronize(dev)
+
+    def step_separate(k):
+        si = k % NSETS
+        if use_graph:
+            sep_graphs[si].replay()
+        else:
+            launch_chain(sets[si], st, lambda i: sep_events[si][i].record(stream), fused=False)
+        if world > 1:
+            dist.all_reduce(sets[si]["sums"])
 
     def step(k):
         si = k % NSETS
@@ -328,6 +361,23 @@ def run_b200_arm(args, rank, world, local_rank):
     op_ms = {n: float(np.mean([set_events[si][i].elapsed_time(set_events[si][i + 1]) for si in used])) for i, n in enumerate(OPS)}
     op_ms["masked_sums"] /= 2  # two launches in that interval
     launches = (_lib.launch_count() - launches0) if not use_graph else kernels_per_graph * args.steps
+    # the same chain with census_sad forward and backward as separate calls (the autograd path), a few steps
+    sep_steps = max(NSETS, min(args.steps, 20))
+    for k in range(3):
+        step_separate(k)
+    sync_all()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record(stream)
+    for k in range(sep_steps):
+        step_separate(k)
+    s1.record(stream)
+    sync_all()
+    t = torch.tensor([s0.elapsed_time(s1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    sep_ms_per_step = float(t.item()) / sep_steps
+    sep_ms = {n: float(np.mean([sep_events[si][i].elapsed_time(sep_events[si][i + 1]) for si in range(NSETS)])) for i, n in enumerate(OPS_SEP)}
+    op_ms["census_sad_fwd"], op_ms["census_sad_bwd"] = sep_ms["census_sad_fwd"], sep_ms["census_sad_bwd"]
 
     # ---- e2e leg: the C ABI's host-buffer entry points, pinned host inputs/outputs, copies timed
     P = lambda t_: ctypes.c_void_p(t_.data_ptr())
@@ -361,19 +411,28 @@ def run_b200_arm(args, rank, world, local_rank):
         return
     peak, peak_src = measured_peak()
     ops = {}
-    for n in OPS:
+    for n in OPS + ("census_sad_fwd", "census_sad_bwd"):
         gbs = BYTES_PER_PX[n] * npx / (op_ms[n] * 1e-3) / 1e9
         ops[n] = {"ms": op_ms[n], "mpix_s": npx / (op_ms[n] * 1e-3) / 1e6, "algo_bytes_per_px": BYTES_PER_PX[n],
-                  "achieved_gbs": gbs, "frac_hbm": gbs / peak}
-    fb = {"sad_fwd_bwd": op_ms["sad_fwd"] + op_ms["sad_bwd"], "census_sad_fwd_bwd": op_ms["census_sad_fwd"] + op_ms["census_sad_bwd"]}
-    for n, ms in fb.items():
-        gbs = 28 * npx / (ms * 1e-3) / 1e9
-        ops[n] = {"ms": ms, "mpix_s": npx / (ms * 1e-3) / 1e6, "algo_bytes_per_px": 28, "achieved_gbs": gbs, "frac_hbm": gbs / peak}
-    dom = max(OPS[:5], key=lambda n: op_ms[n])
+                  "achieved_gbs": gbs, "frac_hbm": gbs / peak, "in_step": n in OPS}
+    ms = op_ms["sad_fwd"] + op_ms["sad_bwd"]
+    gbs = 28 * npx / (ms * 1e-3) / 1e9
+    ops["sad_fwd_bwd"] = {"ms": ms, "mpix_s": npx / (ms * 1e-3) / 1e6, "algo_bytes_per_px": 28, "achieved_gbs": gbs,
+                          "frac_hbm": gbs / peak, "in_step": True}
+    dom = max(OPS[:4], key=lambda n: op_ms[n])
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj["kernels"][dom]["dram_bytes"], tj["source"]
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ops[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": ops[dom]["frac_hbm"], "traffic": None, "peak_source": peak_src,
+                "frac": ops[dom]["frac_hbm"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algo_bytes_per_launch": BYTES_PER_PX[dom] * npx, "ms_per_launch": op_ms[dom],
-                "share_of_step": op_ms[dom] / sum(op_ms[n] * (2 if n == "masked_sums" else 1) for n in OPS)}
+                "share_of_step": op_ms[dom] / sum(op_ms[n] * (2 if n == "masked_sums" else 1) for n in OPS),
+                "note": "the census kernels evaluate 162 reciprocal square roots per pixel and are bound by the XU (MUFU) "
+                        "pipe, not by HBM: ncu sm__inst_executed_pipe_xu 68-86 % of peak (profiles/), so frac stays small by design"}
     line = {"metric": METRIC, "value": world * npx / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -385,7 +444,9 @@ def run_b200_arm(args, rank, world, local_rank):
             "e2e": {"value": world * npx / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": "ctd_host_lcn_f32 + 2x ctd_host_photometric_fwd_bwd_f32, pinned host buffers"},
-            "roofline": roofline, "ops": ops}
+            "roofline": roofline, "ops": ops,
+            "separate_calls": {"ms_per_step": sep_ms_per_step, "value": world * npx / (sep_ms_per_step * 1e-3) / 1e6, "steps": sep_steps,
+                               "note": "same chain, census_sad forward and backward as two calls (torch autograd path)"}}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)

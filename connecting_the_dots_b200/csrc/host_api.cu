@@ -135,10 +135,13 @@ static int photometric_host(const float* es, const float* ta, const float* go, f
     if (gi && out_img) H2D_ON(g_ws.s_in, b + o_go + oo, (const char*)go + oo, nb * out_img);
     CTD_CUDA(cudaEventRecord(g_ws.ev_in[c], g_ws.s_in));
     CTD_CUDA(cudaStreamWaitEvent(g_ws.stream, g_ws.ev_in[c], 0));
-    if (out)
+    if (out && gi)
+      RUN(ctd_photometric_fwd_bwd_f32((float*)(b + o_es + oi), (float*)(b + o_ta + oi), (float*)(b + o_go + oo),
+                                      (float*)(b + o_out + oo), (float*)(b + o_gi + oi), nb, C, H, W, bs, type, eps, g_ws.stream));
+    else if (out)
       RUN(ctd_photometric_fwd_f32((float*)(b + o_es + oi), (float*)(b + o_ta + oi), (float*)(b + o_out + oo), nb, C, H, W, bs,
                                   type, eps, g_ws.stream));
-    if (gi)
+    else if (gi)
       RUN(ctd_photometric_bwd_f32((float*)(b + o_es + oi), (float*)(b + o_ta + oi), (float*)(b + o_go + oo),
                                   (float*)(b + o_gi + oi), nb, C, H, W, bs, type, eps, g_ws.stream));
     CTD_CUDA(cudaEventRecord(g_ws.ev_run[c], g_ws.stream));

@@ -581,11 +581,13 @@ __device__ __forceinline__ float xor_sign(float v, float s) {  // v * sign(s) fo
 // the first summand is i as a tap of centre q (M = clamp multiplicity, 1 away from the image
 // border), the second is i as the centre scattering -g back to itself; both share dd and r1
 // because h(-x) = 1 - h(x).  go is zero outside the image, es/ta are replicate-clamped.
-template <int TYPE, bool BORDER>
+// FUSE: also accumulate the forward's psi(dd) over the same 81 (replicate-clamped) taps into facc[half][k] --
+// the backward evaluates every dd the forward needs, so the loss map costs one more add per tap.
+template <int TYPE, bool BORDER, bool FUSE>
 __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[CE_W], float (*Gs)[CE_W],
                                                 float* __restrict__ gi, int x0, int y0, int H, int W,
                                                 float eps, int vec, int tx, int ty, unsigned* __restrict__ list,
-                                                unsigned* __restrict__ count, unsigned plane_base) {
+                                                unsigned* __restrict__ count, unsigned plane_base, float (*facc)[4]) {
 #pragma unroll 1
   for (int half = 0; half < 2; ++half) {
     const int yl = ty + 16 * half;
@@ -631,6 +633,10 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
           const float r3 = r1 * r1 * r1;
           float gq = g[k + dx];
           if (BORDER) gq *= my * fmaf(sx[k], float(dx - R9), bx[k]);
+          if (FUSE) {
+            if (TYPE == 2) facc[half][k] = fmaf(dd, dd, facc[half][k]);
+            else facc[half][k] += fabsf(dd);
+          }
           if (TYPE == 2) {
             acc[k] = fmaf(dd * r3, gq + gc[k], acc[k]);
           } else {
@@ -700,11 +706,11 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
   }
 }
 
-template <int TYPE>
+template <int TYPE, bool FUSE>
 __global__ void __launch_bounds__(256)
 photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
-                  float* __restrict__ gi, int C, int H, int W, float eps, int vec, unsigned* __restrict__ list,
-                  unsigned* __restrict__ count) {
+                  float* __restrict__ gi, float* __restrict__ out, int C, int H, int W, float eps, int vec,
+                  unsigned* __restrict__ list, unsigned* __restrict__ count) {
   __shared__ __align__(16) float Es[CE_H][CE_W];
   __shared__ __align__(16) float Ts[CE_H][CE_W];
   __shared__ __align__(16) float Gs[CE_H][CE_W];
@@ -714,6 +720,7 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
   const int tx = tid % 16, ty = tid / 16;
   const int64_t plane = (int64_t)H * W;
   const bool border = x0 == 0 || y0 == 0 || x0 + CT_W >= W || y0 + CT_H >= H;
+  float facc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
   load_halo_tile<false>(Gs, go + n * plane, x0, y0, H, W, vec, tid);
   for (int c = 0; c < C; ++c) {
     if (c) __syncthreads();
@@ -722,8 +729,26 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
     __syncthreads();
     float* gic = gi + (n * C + c) * plane;
     const unsigned pb = (unsigned)((n * C + c) * plane);
-    if (border) census_bwd_tile<TYPE, true>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb);
-    else census_bwd_tile<TYPE, false>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb);
+    if (border) census_bwd_tile<TYPE, true, FUSE>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb, facc);
+    else census_bwd_tile<TYPE, false, FUSE>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb, facc);
+  }
+  if (FUSE) {  // the loss map: sum over channels and taps, same scaling as photo_fwd_census9
+    const float scale = (TYPE == 2 ? 0.25f : 0.5f) * INV81;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      const int gy = y0 + ty + 16 * half, gx = x0 + 4 * tx;
+      if (gy >= H) continue;
+      float* dst = out + n * plane + (int64_t)gy * W + gx;
+      if (vec) {
+        if (gx < W)
+          *reinterpret_cast<float4*>(dst) = make_float4(facc[half][0] * scale, facc[half][1] * scale, facc[half][2] * scale,
+                                                        facc[half][3] * scale);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (gx + k < W) dst[k] = facc[half][k] * scale;
+      }
+    }
   }
 }
 
@@ -767,6 +792,36 @@ static int bwd_impl(const T* es, const T* ta, const T* go, T* gi, int64_t B, int
   photo_bwd_generic<T><<<grid, 256, 0, st>>>(es, ta, go, gi, B, (int)C, (int)H, (int)W, bs, type, (T)eps);
   count_launch();
   return check_launch("photometric_bwd(generic)");
+}
+
+// census backward (block 9) of nb images; out != nullptr: the fused forward + backward kernel
+static void census_bwd_launch(const float* e, const float* t, const float* g, float* o, float* out, int nb, int64_t C,
+                              int64_t H, int64_t W, int type, float eps, int vec, cudaStream_t st) {
+  dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
+  if (type == 2) {
+    if (out) photo_bwd_census9<2, true><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
+    else photo_bwd_census9<2, false><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
+    return;
+  }
+  // census_sad near-tie pixels: listed by the tile kernel when scratch memory is available, else marked and found by a scan
+  const int64_t total = (int64_t)nb * C * H * W;
+  unsigned* scratch = total < ((int64_t)1 << 32) ? static_cast<unsigned*>(scratch_alloc((size_t)(total + 1) * 4, st)) : nullptr;
+  if (scratch && cudaMemsetAsync(scratch, 0, 4, st) != cudaSuccess) {
+    cudaGetLastError();
+    scratch_free(scratch, st);
+    scratch = nullptr;
+  }
+  unsigned* list = scratch ? scratch + 1 : nullptr;
+  if (out) photo_bwd_census9<3, true><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, list, scratch);
+  else photo_bwd_census9<3, false><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, list, scratch);
+  if (scratch) {
+    census_sad_bwd_fixup_list<<<148 * 4, 256, 0, st>>>(e, t, g, o, list, scratch, (int)C, (int)H, (int)W, eps);
+    scratch_free(scratch, st);
+  } else {
+    const int fgrid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
+    census_sad_bwd_fixup<<<fgrid, 256, 0, st>>>(e, t, g, o, total, (int)C, (int)H, (int)W, eps);
+  }
+  count_launch();
 }
 
 static inline int vec_ok(int64_t W, const void* a, const void* b, const void* c, const void* d) {
@@ -830,32 +885,35 @@ CTD_API int ctd_photometric_bwd_f32(const float* es, const float* ta, const floa
       if (type == 0) photo_bwd_box9<0><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, vec);
       else photo_bwd_box9<1><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, vec);
     } else {
-      dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
-      if (type == 2) photo_bwd_census9<2><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
-      else {
-        // near-tie pixels: listed by the tile kernel when scratch memory is available, else marked and found by a scan
-        const int64_t total = (int64_t)nb * C * H * W;
-        unsigned* scratch = total < ((int64_t)1 << 32) ? static_cast<unsigned*>(scratch_alloc((size_t)(total + 1) * 4, st)) : nullptr;
-        if (scratch && cudaMemsetAsync(scratch, 0, 4, st) != cudaSuccess) {
-          cudaGetLastError();
-          scratch_free(scratch, st);
-          scratch = nullptr;
-        }
-        if (scratch) {
-          photo_bwd_census9<3><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec, scratch + 1, scratch);
-          census_sad_bwd_fixup_list<<<148 * 4, 256, 0, st>>>(e, t, g, o, scratch + 1, scratch, (int)C, (int)H, (int)W, eps);
-          scratch_free(scratch, st);
-        } else {
-          photo_bwd_census9<3><<<grid, 256, 0, st>>>(e, t, g, o, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
-          const int fgrid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
-          census_sad_bwd_fixup<<<fgrid, 256, 0, st>>>(e, t, g, o, total, (int)C, (int)H, (int)W, eps);
-        }
-        count_launch();
-      }
+      census_bwd_launch(e, t, g, o, nullptr, nb, C, H, W, type, eps, vec, st);
     }
     count_launch();
   }
   return check_launch("photometric_bwd");
+}
+
+// Forward and backward in one call, for callers whose grad_out does not depend on the loss map (the reference's
+// RectifiedPatternSimilarityLoss, networks.py:377: grad_out = mask / sum(mask) up to a scalar).  The census
+// modes run ONE kernel: the backward gather already forms every dd = 2 (h(des) - h(dta)) of the window, so the
+// loss map is one more add per tap instead of a second pass over 162 reciprocal square roots per pixel.
+CTD_API int ctd_photometric_fwd_bwd_f32(const float* es, const float* ta, const float* go, float* out, float* gi,
+                                           int64_t B, int64_t C, int64_t H, int64_t W, int bs, int type, float eps,
+                                           ctd_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  if (type >= 2 && type <= 3 && fast9_ok(bs, H, W) && C >= 1 && B >= 1) {
+    if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
+    CTD_REQUIRE(go && out, "photometric_fwd_bwd: null pointer");
+    const int vec = vec_ok(W, es, ta, go, gi) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+    for (int64_t b0 = 0; b0 < B; b0 += 32768) {
+      const int nb = (int)std::min<int64_t>(32768, B - b0);
+      census_bwd_launch(es + b0 * C * H * W, ta + b0 * C * H * W, go + b0 * H * W, gi + b0 * C * H * W, out + b0 * H * W, nb,
+                        C, H, W, type, eps, vec, st);
+      count_launch();
+    }
+    return check_launch("photometric_fwd_bwd(census, fused)");
+  }
+  if (int rc = ctd_photometric_fwd_f32(es, ta, out, B, C, H, W, bs, type, eps, stream)) return rc;
+  return ctd_photometric_bwd_f32(es, ta, go, gi, B, C, H, W, bs, type, eps, stream);
 }
 
 CTD_API int ctd_photometric_bwd_f64(const double* es, const double* ta, const double* go, double* gi,

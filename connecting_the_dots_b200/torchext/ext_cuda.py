@@ -146,6 +146,23 @@ def photometric_loss_backward(es, ta, grad_out, block_size, type, eps):
     return grad_in
 
 
+def photometric_loss_forward_backward(es, ta, grad_out, block_size, type, eps):
+    """Both halves in one call (ctd_photometric_fwd_bwd_f32; the census modes run a single fused kernel).
+    Returns (loss map [B,1,H,W], gradient w.r.t. es [B,C,H,W]); fp32 only."""
+    _photometric_args(es, ta, type)
+    _check(es.dtype == torch.float32, "photometric_loss_forward_backward is float32 only")
+    _check_input_cuda(grad_out, "grad_out")
+    B, C, H, W = es.shape
+    _check(grad_out.numel() == B * H * W, "grad_out has to be B x 1 x H x W")
+    _same(es, grad_out, "es", "grad_out")
+    out = torch.empty((B, 1, H, W), dtype=es.dtype, device=es.device)
+    grad_in = torch.empty((B, C, H, W), dtype=es.dtype, device=es.device)
+    with torch.cuda.device(es.device):
+        _lib.call("ctd_photometric_fwd_bwd_f32", es.data_ptr(), ta.data_ptr(), grad_out.data_ptr(), out.data_ptr(),
+                  grad_in.data_ptr(), B, C, H, W, int(block_size), int(type), float(eps), _stream(es))
+    return out, grad_in
+
+
 def lcn_forward(x, radius, epsilon):
     """model/networks.py:523-533 as one kernel.  x [N,1,H,W] -> (lcn, std), both [N,1,H,W]."""
     _check_input_cuda(x, "x")

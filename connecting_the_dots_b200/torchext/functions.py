@@ -131,6 +131,36 @@ def photometric_loss_pytorch(es, ta, block_size, type="mse", eps=0.1):
     return total / block_size ** 2
 
 
+class WeightedPhotometricLossFunction(torch.autograd.Function):
+    """`(mask * photometric_loss(es, ta)).sum() / mask.sum()` -- the way the reference's only caller consumes the
+    loss map (model/networks.py:377) -- as ONE op.  Its upstream gradient is a scalar, so grad_out = mask / sum(mask)
+    is known before the loss map exists: forward and backward of the window loss run as one fused pass
+    (ctd_photometric_fwd_bwd_f32) and autograd's backward is a scalar multiply.  SURVEY section 8(f) rank 1,
+    without the warp.  Returns (value, loss_map); mask is not differentiated (it is LCN's std in the reference)."""
+
+    @staticmethod
+    def forward(ctx, es, ta, mask, block_size, type, eps):
+        if not es.is_cuda:
+            raise RuntimeError("torchext.weighted_photometric_loss: connecting_the_dots_b200 has no CPU implementation")
+        mask = mask.detach().contiguous()
+        denom = mask.sum()
+        out, grad_es = ext_cuda.photometric_loss_forward_backward(es.detach(), ta.detach(), mask / denom, block_size, type, eps)
+        terms = ext_cuda.masked_sums(out, mask)
+        ctx.save_for_backward(grad_es)
+        ctx.mark_non_differentiable(out)
+        return terms[0] / terms[1], out
+
+    @staticmethod
+    def backward(ctx, g_val, g_map):
+        (grad_es,) = ctx.saved_tensors
+        return grad_es * g_val, None, None, None, None, None
+
+
+def weighted_photometric_loss(es, ta, mask, block_size, type="mse", eps=0.1):
+    """Masked mean of the photometric loss map and the map itself: (value, loss_map [B,1,H,W])."""
+    return WeightedPhotometricLossFunction.apply(es, ta, mask, block_size, _loss_type_id(type), eps)
+
+
 class LCNFunction(torch.autograd.Function):
     """Fused local contrast normalisation (model/networks.py:507-533); forward only -- in the
     reference the gradient flows to an input image nobody reads (exp_synph.py:80-91)."""

@@ -69,6 +69,14 @@ int ctd_photometric_bwd_f64(const double* es, const double* ta, const double* gr
                             double* grad_in, int64_t B, int64_t C, int64_t H, int64_t W,
                             int block_size, int type, float eps, ctd_stream_t stream);
 
+/* ---- forward + backward in one call (ext.h:201-344), for callers whose grad_out does not depend on the loss
+ * map -- the reference's only caller builds it from the mask alone (model/networks.py:377).  The census modes
+ * run a single fused kernel (the backward's window terms already contain the forward's); results are identical
+ * to calling ctd_photometric_fwd_f32 then ctd_photometric_bwd_f32. */
+int ctd_photometric_fwd_bwd_f32(const float* es, const float* ta, const float* grad_out, float* out,
+                                float* grad_in, int64_t B, int64_t C, int64_t H, int64_t W, int block_size,
+                                int type, float eps, ctd_stream_t stream);
+
 /* ---- XCorrVolFunctor: ext.h:120-191, ext_cuda.cpp:73-86 (xcorrvol_cuda).  The reference has no
  * batch dimension; here in0,in1 are [B,C,H,W] and out is [B,D,H,W] (B=1 is the reference call). */
 int ctd_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,

@@ -137,6 +137,36 @@ def test_census_pair_kernel_strip_layouts(tx, shape):
         _lib.set_option("census_pairs", 2)
 
 
+@pytest.mark.parametrize("shape", [(2, 1, 40, 72), (1, 2, 33, 50), (1, 1, 96, 160), (1, 1, 7, 9)])
+@pytest.mark.parametrize("ty", range(4))
+def test_photometric_fused_forward_backward(tx, shape, ty):
+    """ctd_photometric_fwd_bwd_f32 (one fused kernel for the census modes) against the oracle's two passes."""
+    B, C, H, W = shape
+    rng = np.random.RandomState(B * 100 + W)
+    es = rng.randn(B, C, H, W).astype(np.float32)
+    ta = (es + 0.6 * rng.randn(B, C, H, W)).astype(np.float32)
+    go = rng.randn(B, 1, H, W).astype(np.float32)
+    out, gi = tx.ext_cuda.photometric_loss_forward_backward(cu(es), cu(ta), cu(go), 9, ty, 0.5)
+    assert_close(out.cpu().numpy(), oracle.photometric_loss_forward(es, ta, 9, ty, 0.5), what="fused fwd")
+    assert_close(gi.cpu().numpy(), oracle.photometric_loss_backward(es, ta, go, 9, ty, 0.5), what="fused bwd")
+
+
+@pytest.mark.parametrize("ty", (1, 3))
+def test_weighted_photometric_loss_matches_composition(tx, ty):
+    """The fused masked-mean op equals photometric_loss -> (mask*d).sum()/mask.sum() with autograd, value and gradient."""
+    from connecting_the_dots_b200 import synth
+    d = synth.make_batch(2, 96, 160)
+    es = cu(d["es"]).requires_grad_(True)
+    ta, mask = cu(d["ta"]), cu(d["std"])
+    ref = (mask * tx.photometric_loss(es, ta, 9, TYPES[ty], 0.5)).sum() / mask.sum()
+    (gref,) = torch.autograd.grad(3.0 * ref, es)
+    val, loss_map = tx.weighted_photometric_loss(es, ta, mask, 9, TYPES[ty], 0.5)
+    (g,) = torch.autograd.grad(3.0 * val, es)
+    assert abs(float(val) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert_close(g.cpu().numpy(), gref.cpu().numpy(), what="weighted loss gradient")
+    assert_close(loss_map.cpu().numpy(), oracle.photometric_loss_forward(d["es"], d["ta"], 9, ty, 0.5), what="loss map")
+
+
 @pytest.mark.parametrize("ty", (1, 3))
 def test_photometric_full_size_synthetic(tx, ty):
     """BASELINE config 1/2 data: 480x640 LCN'd dot-pattern pairs, grad_out = std / sum(std)."""
