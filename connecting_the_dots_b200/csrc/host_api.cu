@@ -6,6 +6,9 @@
 // ops (photometric, LCN, XCorrVol) are cut into chunks of whole images and software-pipelined over three
 // private streams -- upload of chunk i+1, kernels of chunk i and download of chunk i-1 run concurrently, so
 // with pinned buffers both PCIe directions stay busy and the kernels hide behind the copies.
+// Between ctd_host_begin_batch() and ctd_host_end_batch() the calls only enqueue: consecutive ops then overlap as well
+// (the upload of the next call runs under the download of the previous one), results are in host memory when
+// ctd_host_end_batch() returns.
 // There is no CPU compute path: without a CUDA device these calls fail with CTD_ERR_CUDA.
 #include <algorithm>
 #include <vector>
@@ -22,6 +25,25 @@ struct Workspace {
   cudaStream_t s_in = nullptr, s_out = nullptr;  // upload / download streams of the chunk pipeline
   static constexpr int MAX_CHUNKS = 16;
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_run[MAX_CHUNKS] = {};
+  bool deferred = false;  // inside ctd_host_begin_batch / ctd_host_end_batch
+  size_t used = 0;        // bytes of the workspace owned by calls still in flight (deferred mode: no reuse)
+
+  // workspace of one call: `bytes` fresh bytes behind everything still in flight
+  int carve(size_t bytes, char** out) {
+    if (int rc = ensure(used + bytes)) return rc;
+    *out = base + used;
+    return CTD_OK;
+  }
+  // end of a call: wait for the results unless a batch is open
+  int finish(size_t bytes) {
+    if (deferred) {
+      used += bytes;
+      return CTD_OK;
+    }
+    CTD_CUDA(cudaStreamSynchronize(s_out));
+    CTD_CUDA(cudaStreamSynchronize(stream));
+    return CTD_OK;
+  }
 
   int ensure(size_t bytes) {
     int dev = 0;
@@ -41,10 +63,11 @@ struct Workspace {
     }
     if (bytes > cap) {
       if (base) {
-        CTD_CUDA(cudaDeviceSynchronize());
+        CTD_CUDA(cudaDeviceSynchronize());  // also completes every call still in flight: their results are out
         cudaFree(base);
         base = nullptr;
         cap = 0;
+        used = 0;
       }
       const size_t want = bytes + bytes / 8 + (1 << 20);
       if (cudaMalloc(&base, want) != cudaSuccess) {
@@ -94,8 +117,10 @@ struct Carver {
 // images [i0, i1) of chunk c when B images are cut into n chunks
 static inline int64_t chunk_lo(int64_t B, int n, int c) { return B * c / n; }
 extern int g_host_chunks;  // ctd_set_option("host_chunks", n): upper bound on the pipeline depth (A/B runs)
-static inline int chunk_count(int64_t B) {
-  return (int)std::min<int64_t>(std::max<int64_t>(B, 1), std::min(std::max(g_host_chunks, 1), (int)Workspace::MAX_CHUNKS));
+static inline int chunk_count(int64_t B, bool deferred) {
+  // inside a batch the neighbouring calls already overlap with this one: fewer, larger copies win (measured)
+  const int want = deferred ? std::min(g_host_chunks, 2) : g_host_chunks;
+  return (int)std::min<int64_t>(std::max<int64_t>(B, 1), std::min(std::max(want, 1), (int)Workspace::MAX_CHUNKS));
 }
 
 }  // namespace ctd
@@ -118,12 +143,12 @@ static int photometric_host(const float* es, const float* ta, const float* go, f
   Carver cv;
   const size_t o_es = cv.add(nin), o_ta = cv.add(nin), o_go = cv.add(go ? nout : 0), o_out = cv.add(out ? nout : 0),
                o_gi = cv.add(gi ? nin : 0);
-  RUN(g_ws.ensure(cv.total));
-  char* b = g_ws.base;
+  char* b = nullptr;
+  RUN(g_ws.carve(cv.total, &b));
   if (nin) CTD_REQUIRE(es && ta, "photometric: null pointer");
   if (gi) CTD_REQUIRE(go || !nout, "photometric_bwd: null grad_out");
   if (B == 0) return CTD_OK;
-  const int nch = chunk_count(B);
+  const int nch = chunk_count(B, g_ws.deferred);
   const size_t in_img = nin / B, out_img = nout / B;  // bytes per image
   for (int c = 0; c < nch; ++c) {
     const int64_t i0 = chunk_lo(B, nch, c), nb = chunk_lo(B, nch, c + 1) - i0;
@@ -149,9 +174,7 @@ static int photometric_host(const float* es, const float* ta, const float* go, f
     if (out && out_img) D2H_ON(g_ws.s_out, (char*)out + oo, b + o_out + oo, nb * out_img);
     if (gi && in_img) D2H_ON(g_ws.s_out, (char*)gi + oi, b + o_gi + oi, nb * in_img);
   }
-  CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
-  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
-  return CTD_OK;
+  return g_ws.finish(cv.total);
 }
 
 CTD_API int ctd_host_photometric_fwd_f32(const float* es, const float* ta, float* out, int64_t B, int64_t C,
@@ -177,12 +200,12 @@ CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out
   const size_t nin = (size_t)(B * C * H * W) * sizeof(float), nout = (size_t)(B * D * H * W) * sizeof(float);
   Carver cv;
   const size_t o0 = cv.add(nin), o1 = cv.add(nin), oo = cv.add(nout);
-  RUN(g_ws.ensure(cv.total));
-  char* b = g_ws.base;
+  char* b = nullptr;
+  RUN(g_ws.carve(cv.total, &b));
   if (nin) CTD_REQUIRE(in0 && in1, "xcorrvol: null pointer");
   if (nout) CTD_REQUIRE(out, "xcorrvol: null output");
   if (B == 0) return CTD_OK;
-  const int nch = chunk_count(B);
+  const int nch = chunk_count(B, g_ws.deferred);
   const size_t in_img = nin / B, out_img = nout / B;
   for (int c = 0; c < nch; ++c) {
     const int64_t i0 = chunk_lo(B, nch, c), nb = chunk_lo(B, nch, c + 1) - i0;
@@ -198,9 +221,7 @@ CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out
     CTD_CUDA(cudaStreamWaitEvent(g_ws.s_out, g_ws.ev_run[c], 0));
     if (out_img) D2H_ON(g_ws.s_out, (char*)out + ov, b + oo + ov, nb * out_img);
   }
-  CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
-  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
-  return CTD_OK;
+  return g_ws.finish(cv.total);
 }
 
 CTD_API int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const float* K, int64_t* out, int64_t B,
@@ -209,8 +230,8 @@ CTD_API int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const flo
   const size_t npt = (size_t)(B * H * W) * 3 * sizeof(float), nout = (size_t)(B * H * W) * sizeof(int64_t);
   Carver cv;
   const size_t o0 = cv.add(npt), o1 = cv.add(npt), ok = cv.add(9 * sizeof(float)), oo = cv.add(nout);
-  RUN(g_ws.ensure(cv.total));
-  char* b = g_ws.base;
+  char* b = nullptr;
+  RUN(g_ws.carve(cv.total, &b));
   if (nout) {
     CTD_REQUIRE(xyz0 && xyz1 && K && out, "proj_nn: null pointer");
     H2D(b + o0, xyz0, npt);
@@ -220,8 +241,7 @@ CTD_API int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const flo
   RUN(ctd_proj_nn_f32((float*)(b + o0), (float*)(b + o1), (float*)(b + ok), (int64_t*)(b + oo), B, H, W, ps,
                       g_ws.stream));
   if (nout) D2H(out, b + oo, nout);
-  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
-  return CTD_OK;
+  return g_ws.finish(cv.total);
 }
 
 CTD_API int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, int64_t N0, int64_t N1) {
@@ -229,8 +249,8 @@ CTD_API int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, in
   const size_t n0 = (size_t)N0 * 3 * sizeof(float), n1 = (size_t)N1 * 3 * sizeof(float), no = (size_t)N0 * sizeof(int64_t);
   Carver cv;
   const size_t o0 = cv.add(n0), o1 = cv.add(n1), oo = cv.add(no);
-  RUN(g_ws.ensure(cv.total));
-  char* b = g_ws.base;
+  char* b = nullptr;
+  RUN(g_ws.carve(cv.total, &b));
   if (n0) {
     CTD_REQUIRE(in0 && out, "nn: null pointer");
     H2D(b + o0, in0, n0);
@@ -241,8 +261,7 @@ CTD_API int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, in
   }
   RUN(ctd_nn_f32((float*)(b + o0), (float*)(b + o1), (int64_t*)(b + oo), N0, N1, g_ws.stream));
   if (no) D2H(out, b + oo, no);
-  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
-  return CTD_OK;
+  return g_ws.finish(cv.total);
 }
 
 CTD_API int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t N0, int64_t N1) {
@@ -250,8 +269,8 @@ CTD_API int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t*
   const size_t n0 = (size_t)N0 * sizeof(int64_t), n1 = (size_t)N1 * sizeof(int64_t), no = (size_t)N0;
   Carver cv;
   const size_t o0 = cv.add(n0), o1 = cv.add(n1), oo = cv.add(no);
-  RUN(g_ws.ensure(cv.total));
-  char* b = g_ws.base;
+  char* b = nullptr;
+  RUN(g_ws.carve(cv.total, &b));
   if (n0) {
     CTD_REQUIRE(in0 && out, "crosscheck: null pointer");
     H2D(b + o0, in0, n0);
@@ -262,8 +281,7 @@ CTD_API int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t*
   }
   RUN(ctd_crosscheck((int64_t*)(b + o0), (int64_t*)(b + o1), (uint8_t*)(b + oo), N0, N1, g_ws.stream));
   if (no) D2H(out, b + oo, no);
-  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
-  return CTD_OK;
+  return g_ws.finish(cv.total);
 }
 
 CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, int64_t H, int64_t W, int r,
@@ -272,11 +290,11 @@ CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, i
   const size_t n = (size_t)(N * H * W) * sizeof(float);
   Carver cv;
   const size_t ox = cv.add(n), ol = cv.add(n), os = cv.add(n);
-  RUN(g_ws.ensure(cv.total));
-  char* b = g_ws.base;
+  char* b = nullptr;
+  RUN(g_ws.carve(cv.total, &b));
   if (n) CTD_REQUIRE(x && lcn && sd, "lcn: null pointer");
   if (N == 0 || n == 0) return CTD_OK;
-  const int nch = chunk_count(N);
+  const int nch = chunk_count(N, g_ws.deferred);
   const size_t img = n / N;
   for (int c = 0; c < nch; ++c) {
     const int64_t i0 = chunk_lo(N, nch, c), nb = chunk_lo(N, nch, c + 1) - i0;
@@ -290,9 +308,30 @@ CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, i
     D2H_ON(g_ws.s_out, (char*)lcn + o, b + ol + o, nb * img);
     D2H_ON(g_ws.s_out, (char*)sd + o, b + os + o, nb * img);
   }
-  CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
-  CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
+  return g_ws.finish(cv.total);
+}
+
+CTD_API int ctd_host_begin_batch(void) {
+  CTD_REQUIRE(!g_ws.deferred, "ctd_host_begin_batch: a batch is already open on this thread");
+  g_ws.deferred = true;
+  g_ws.used = 0;
   return CTD_OK;
 }
 
-CTD_API void ctd_host_release(void) { g_ws.release(); }
+CTD_API int ctd_host_end_batch(void) {
+  CTD_REQUIRE(g_ws.deferred, "ctd_host_end_batch: no batch is open on this thread");
+  g_ws.deferred = false;
+  g_ws.used = 0;
+  if (g_ws.stream) {
+    CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
+    CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
+    CTD_CUDA(cudaStreamSynchronize(g_ws.s_in));
+  }
+  return CTD_OK;
+}
+
+CTD_API void ctd_host_release(void) {
+  g_ws.deferred = false;
+  g_ws.used = 0;
+  g_ws.release();
+}

@@ -134,6 +134,11 @@ int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, int64_t N0
 int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t N0, int64_t N1);
 int ctd_host_lcn_f32(const float* x, float* lcn, float* std, int64_t N, int64_t H, int64_t W,
                      int radius, float epsilon);
+/* Deferred mode for the calling thread: between begin and end the ctd_host_* calls only enqueue their copies and
+ * kernels (they return at once), so consecutive calls overlap on the bus; every result is in host memory when
+ * ctd_host_end_batch() returns.  Input buffers must stay untouched, output buffers unread, until then. */
+int ctd_host_begin_batch(void);
+int ctd_host_end_batch(void);
 /* release the calling thread's staging workspace */
 void ctd_host_release(void);
 

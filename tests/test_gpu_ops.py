@@ -518,3 +518,32 @@ def test_box_tma_path_matches_tile_path(tx, ty):
     es = np.ascontiguousarray(es); ta = np.ascontiguousarray(ta); go = np.ascontiguousarray(go)
     f = tx.ext_cuda.photometric_loss_forward(cu(es), cu(ta), 9, ty, 0.1).cpu().numpy()
     assert_close(f, oracle.photometric_loss_forward(es, ta, 9, ty, 0.1))
+
+
+def test_host_api_deferred_batch_matches_synchronous_calls(tx):
+    """ctd_host_begin_batch / ctd_host_end_batch: the same calls, enqueued back to back, give the same bytes."""
+    from connecting_the_dots_b200 import _lib, synth
+    d = synth.make_batch(3, 64, 96)
+    P = lambda a: ctypes.c_void_p(a.ctypes.data)
+    B, H, W = 3, 64, 96
+    res = []
+    for deferred in (False, True):
+        lcn, std = np.empty_like(d["im"]), np.empty_like(d["im"])
+        o1, g1, o3, g3 = (np.empty_like(d["es"]) for _ in range(4))
+        idx = np.empty((B, H, W), np.int64)
+        xyz, K, poses = synth.make_clouds(B, H, W)
+        xyz = np.ascontiguousarray(xyz)
+        if deferred:
+            _lib.call("ctd_host_begin_batch")
+        _lib.call("ctd_host_lcn_f32", P(d["im"]), P(lcn), P(std), B, H, W, 5, 0.05)
+        _lib.call("ctd_host_photometric_fwd_bwd_f32", P(d["es"]), P(d["ta"]), P(d["go"]), P(o1), P(g1), B, 1, H, W, 9, 1, 0.5)
+        _lib.call("ctd_host_photometric_fwd_bwd_f32", P(d["es"]), P(d["ta"]), P(d["go"]), P(o3), P(g3), B, 1, H, W, 9, 3, 0.5)
+        _lib.call("ctd_host_proj_nn_f32", P(xyz), P(xyz), P(K), P(idx), B, H, W, 3)
+        if deferred:
+            _lib.call("ctd_host_end_batch")
+        res.append((lcn, std, o1, g1, o3, g3, idx))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    assert_close(res[1][4], oracle.photometric_loss_forward(d["es"], d["ta"], 9, 3, 0.5), what="deferred census fwd")
+    with pytest.raises(Exception):
+        _lib.call("ctd_host_end_batch")  # no batch open
