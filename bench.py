@@ -230,11 +230,21 @@ def run_b200_arm(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
-    B = B_PER_GPU
+    strong = args.global_batch > 0   # configs[4]: a fixed global batch split over the ranks (shard_range)
+    if strong:
+        from connecting_the_dots_b200 import shard_range
+        lo, hi = shard_range(args.global_batch, rank, world)
+        B = hi - lo
+        assert B > 0, "global batch smaller than the number of ranks"
+    else:
+        B = B_PER_GPU
     npx = B * H * W
+    npx_global = args.global_batch * H * W if strong else world * npx
 
     # ---- inputs: NSETS distinct device-resident sets (and pinned host copies for the e2e leg)
-    base = synth.make_batch(B, H, W)
+    base = synth.make_batch(min(B, 8), H, W)
+    if B > 8:  # synthetic frames repeat beyond 8 (generation is the slow part, not the content)
+        base = {k: np.concatenate([v] * ((B + 7) // 8))[:B] for k, v in base.items()}
     sets, host_sets = [], []
     for s in range(NSETS):
         arrs = {k: np.ascontiguousarray(np.roll(base[k], 3 * s + rank, axis=2)) for k in ("im", "es", "ta", "go")}
@@ -437,19 +447,20 @@ def run_b200_arm(args, rank, world, local_rank):
                 "share_of_step": op_ms[dom] / sum(op_ms[n] * (2 if n == "masked_sums" else 1) for n in OPS),
                 "note": "the census kernels evaluate 162 reciprocal square roots per pixel and are bound by the XU (MUFU) "
                         "pipe, not by HBM: ncu sm__inst_executed_pipe_xu 68-86 % of peak (profiles/), so frac stays small by design"}
-    line = {"metric": METRIC, "value": world * npx / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
+    line = {"metric": METRIC, "value": npx_global / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "height": H, "width": W,
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD if not strong else WORKLOAD.replace("configs[1]", "configs[4] (batch %d split over the ranks)" % args.global_batch).replace("batch 8 per GPU", "batch %d on rank 0" % B),
+                       "batch_per_gpu": B, "global_batch": args.global_batch if strong else B * world, "height": H, "width": W,
                        "l2_policy": "inputs and outputs rotate over %d buffer sets, %.0f MB touched > 126 MB L2" % (NSETS, footprint_mb),
                        "launch": "one CUDA graph replay per step (kernel + event-record nodes)" if use_graph else "stream launches",
                        "parallelism": "batch-sharded x%d, one packed 4-float NCCL all-reduce per step" % world},
             "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": world * npx / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
+            "e2e": {"value": npx_global / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
                     "api": "ctd_host_begin_batch; ctd_host_lcn_f32 + 2x ctd_host_photometric_fwd_bwd_f32; ctd_host_end_batch -- pinned host buffers"},
             "roofline": roofline, "ops": ops,
-            "separate_calls": {"ms_per_step": sep_ms_per_step, "value": world * npx / (sep_ms_per_step * 1e-3) / 1e6, "steps": sep_steps,
+            "separate_calls": {"ms_per_step": sep_ms_per_step, "value": npx_global / (sep_ms_per_step * 1e-3) / 1e6, "steps": sep_steps,
                                "note": "same chain, census_sad forward and backward as two calls (torch autograd path)"}}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
@@ -466,6 +477,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time plain stream launches instead of CUDA graph replays")
+    ap.add_argument("--global-batch", type=int, default=0,
+                    help="strong scaling (BASELINE configs[4]): split this many images over the ranks instead of 8 per GPU")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

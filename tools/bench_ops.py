@@ -57,7 +57,7 @@ def timeit(fn, iters, warmup=5, nrep=NREP):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--only", default="calib,photometric,lcn,xcorrvol,proj_nn,nn,crosscheck,reduce")
+    ap.add_argument("--only", default="calib,photometric,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -147,6 +147,33 @@ def main():
             def f(i, st):
                 _lib.call("ctd_crosscheck", i01.data_ptr(), i10.data_ptr(), m.data_ptr(), n, n, st)
             add("crosscheck_%d" % n, *timeit(f, args.iters), 17 * n, px=n)
+    if "config4" in only:
+        # BASELINE configs[3]: one geometric step on a 4-frame track -- for the 6 frame pairs, ProjNN in both directions
+        # (12 image-sized queries, one batched launch), CrossCheck in both directions, and PhotometricLoss census_sad
+        # forward+backward on the 4 frames
+        T = 4
+        xyz, K, poses = synth.make_clouds(T, H, W)
+        Kd = torch.from_numpy(K).to(dev)
+        pairs = [(i, j) for i in range(T) for j in range(T) if i != j]
+        rev = [pairs.index((j, i)) for i, j in pairs]
+        x0 = torch.from_numpy(np.stack([synth.transform(xyz[i], poses[j]) for i, j in pairs])).to(dev)
+        x1 = torch.from_numpy(np.stack([xyz[j] for i, j in pairs])).to(dev)
+        idx = torch.empty(len(pairs), H, W, dtype=torch.int64, device=dev)
+        idx_rev = torch.empty_like(idx)
+        m01 = torch.empty(len(pairs) * H * W, dtype=torch.uint8, device=dev)
+        rev_t = torch.tensor(rev, device=dev)
+        f4 = {k: sets[0][k][:T].contiguous() if B >= T else sets[0][k] for k in ("es", "ta", "go")}
+        o4, g4 = torch.empty(T, 1, H, W, device=dev), torch.empty(T, 1, H, W, device=dev)
+        n = len(pairs) * H * W
+        def f(i, st):
+            _lib.call("ctd_proj_nn_f32", x0.data_ptr(), x1.data_ptr(), Kd.data_ptr(), idx.data_ptr(), len(pairs), H, W, 3, st)
+            # indices are per launch-batch flat indices (image p at offset p*H*W): crosscheck pair p against its reverse
+            torch.index_select(idx, 0, rev_t, out=idx_rev)
+            _lib.call("ctd_crosscheck", idx.data_ptr(), idx_rev.data_ptr(), m01.data_ptr(), n, n, st)
+            _lib.call("ctd_photometric_fwd_bwd_f32", f4["es"].data_ptr(), f4["ta"].data_ptr(), f4["go"].data_ptr(), o4.data_ptr(),
+                      g4.data_ptr(), T, 1, H, W, 9, 3, 0.5, st)
+        add("config4_geometric_step_4frames", *timeit(f, args.iters, nrep=4), 32 * n + 17 * n + 20 * T * H * W, px=T * H * W,
+            extra={"note": "ProjNN ps=3 on 12 ordered frame pairs + CrossCheck + census_sad fwd+bwd on 4 frames; Mpix/s counts the 4 frames"})
     if "nn" in only:
         n = 16384
         rng = np.random.RandomState(0)
