@@ -359,7 +359,12 @@ photo_bwd_box9(const float* __restrict__ es, const float* __restrict__ ta, const
 // ------------------------------------------------------------------------------------------
 // fast path, block size 9, fp32: census_mse / census_sad
 // ------------------------------------------------------------------------------------------
-constexpr int CT_W = 64, CT_H = 32;  // output tile
+#ifndef CTD_CT_H
+#define CTD_CT_H 16
+#endif
+constexpr int CT_W = 64, CT_H = CTD_CT_H;  // output tile; 16 rows of threads, CT_H / 16 passes
+constexpr int CT_NH = CT_H / 16;
+static_assert(CT_H % 16 == 0, "census tile height");
 constexpr int CE_W = CT_W + 2 * R9;  // 72
 constexpr int CE_H = CT_H + 2 * R9;  // 40
 
@@ -415,14 +420,14 @@ photo_fwd_census9(const float* __restrict__ es, const float* __restrict__ ta, fl
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
   const int64_t plane = (int64_t)H * W;
-  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float acc[CT_NH][4] = {};
   for (int c = 0; c < C; ++c) {
     if (c) __syncthreads();
     load_halo_tile<true>(Es, es + (n * C + c) * plane, x0, y0, H, W, vec, tid);
     load_halo_tile<true>(Ts, ta + (n * C + c) * plane, x0, y0, H, W, vec, tid);
     __syncthreads();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < CT_NH; ++half) {
       const int yl = ty + 16 * half;
       if (y0 + yl >= H) continue;
       const float4 ec4 = *reinterpret_cast<const float4*>(&Es[yl + R9][4 * tx + R9]);
@@ -451,7 +456,7 @@ photo_fwd_census9(const float* __restrict__ es, const float* __restrict__ ta, fl
   }
   const float scale = (TYPE == 2 ? 0.25f : 0.5f) * INV81;
 #pragma unroll
-  for (int half = 0; half < 2; ++half) {
+  for (int half = 0; half < CT_NH; ++half) {
     const int gy = y0 + ty + 16 * half, gx = x0 + 4 * tx;
     if (gy >= H) continue;
     float* dst = out + n * plane + (int64_t)gy * W + gx;
@@ -589,7 +594,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
                                                 float eps, int vec, int tx, int ty, unsigned* __restrict__ list,
                                                 unsigned* __restrict__ count, unsigned plane_base, float (*facc)[4]) {
 #pragma unroll 1
-  for (int half = 0; half < 2; ++half) {
+  for (int half = 0; half < CT_NH; ++half) {
     const int yl = ty + 16 * half;
     const int gy = y0 + yl, gx = x0 + 4 * tx;
     if (gy >= H) continue;
@@ -720,7 +725,7 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
   const int tx = tid % 16, ty = tid / 16;
   const int64_t plane = (int64_t)H * W;
   const bool border = x0 == 0 || y0 == 0 || x0 + CT_W >= W || y0 + CT_H >= H;
-  float facc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  float facc[CT_NH][4] = {};
   load_halo_tile<false>(Gs, go + n * plane, x0, y0, H, W, vec, tid);
   for (int c = 0; c < C; ++c) {
     if (c) __syncthreads();
@@ -735,7 +740,7 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
   if (FUSE) {  // the loss map: sum over channels and taps, same scaling as photo_fwd_census9
     const float scale = (TYPE == 2 ? 0.25f : 0.5f) * INV81;
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < CT_NH; ++half) {
       const int gy = y0 + ty + 16 * half, gx = x0 + 4 * tx;
       if (gy >= H) continue;
       float* dst = out + n * plane + (int64_t)gy * W + gx;

@@ -198,18 +198,26 @@ xcorrvol_direct(const float* __restrict__ in0, const float* __restrict__ in1, fl
 // centred two-pass fp32 arithmetic (ext.h:133-190).
 // ------------------------------------------------------------------------------------------
 constexpr int XS_W = 128;             // output columns per CTA (32 lanes x 4)
-constexpr int XS_DT = 16;             // disparities per CTA (4 warps x 4)
+constexpr int XS_DT = 16;             // disparities per CTA
+#ifndef CTD_XS_TD
+#define CTD_XS_TD 4
+#endif
+constexpr int XS_TD = CTD_XS_TD;      // disparities per thread (4: 4 warps per CTA, 2: 8 warps per CTA)
 constexpr int XS_AW = XS_W + 8;       // in0 tile: image columns x0-4 .. x0+131
 constexpr int XS_BW = XS_W + 8 + 16;  // in1 tile: image columns x0-20-d0 .. x0+131-d0 (clamped)
 constexpr int ST_W = 128, ST_H = 16;  // statistics tile
 constexpr int XS_LSUM = 36;           // L0 + L1 >= 36 <=> (sd0 sd1)^2 <= 2^-9 S2_0 S2_1: recompute in fp64
 constexpr int XS_LLIST = 18;          // max(L0, L1) >= 18 whenever L0 + L1 >= 36
 constexpr float XS_FLAT = 1e-6f;      // var < 1e-6 * sum v^2: flat window, reference arithmetic
-constexpr int XS_NST = 4;              // statistics rows in flight per warp
+template <int TD>
+struct XsNst {  // statistics rows in flight per warp (more warps per CTA -> shallower rings, same shared memory)
+  static constexpr int value = TD == 4 ? 4 : 2;
+};
+template <int NST>
 struct alignas(16) XsStatRing {
-  float2 w[XS_NST][XS_W];
-  float2 u[XS_NST][XS_W + 8];
-  uint64_t full[XS_NST];
+  float2 w[NST][XS_W];
+  float2 u[NST][XS_W + 8];
+  uint64_t full[NST];
 };
 template <int BS>
 struct XsCfg {  // tile rows = a whole number of BS-row blocks
@@ -378,8 +386,11 @@ __device__ __forceinline__ void xs_hsum(const float* p, float* o) {
   }
 }
 
-template <int BS>
-__global__ void __launch_bounds__(128, 2)
+// TD = disparities per thread.  TD = 4: 128 threads, 246 registers (suffix sums of 16 outputs), 8 warps/SM.
+// TD = 2: 256 threads, half the suffix registers, 16 warps/SM -- the tile and the arithmetic per output are the
+// same, the resident warps double (the kernel is latency-bound), the in1 row is read as seven 64-bit loads.
+template <int BS, int TD>
+__global__ void __launch_bounds__(512 / TD, 2)
 xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
                  const float2* __restrict__ st0, const float2* __restrict__ st1, int H, int W, int D, int ws0, int ws1,
                  int uoff, int ndchunks, int vec) {
@@ -387,7 +398,9 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float(*At)[XS_AW] = reinterpret_cast<float(*)[XS_AW]>(smem_raw);
   float(*Bt)[XS_BW] = reinterpret_cast<float(*)[XS_BW]>(smem_raw + sizeof(float) * TH * XS_AW);
-  XsStatRing* rings = reinterpret_cast<XsStatRing*>(smem_raw + sizeof(float) * TH * (XS_AW + XS_BW));
+  constexpr int NT = 512 / TD, NST = XsNst<TD>::value;
+  typedef XsStatRing<NST> Ring;
+  Ring* rings = reinterpret_cast<Ring*>(smem_raw + sizeof(float) * TH * (XS_AW + XS_BW));
   const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
   const int x0 = blockIdx.x * XS_W, y0 = blockIdx.y * XH;
   const int b = blockIdx.z / ndchunks, d0 = (blockIdx.z % ndchunks) * XS_DT;
@@ -403,65 +416,67 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
                        __ldg(row + clampi(gx + 2, 0, W - 1)), __ldg(row + clampi(gx + 3, 0, W - 1)));
   };
   constexpr int NA = TH * (XS_AW / 4), NB = TH * (XS_BW / 4);
-  for (int i0 = tid; i0 < NA; i0 += 4 * 128) {
+  for (int i0 = tid; i0 < NA; i0 += 4 * NT) {
     float4 v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * 128;
+      const int i = i0 + k * NT;
       if (i < NA) v[k] = fetch4(p0, i / (XS_AW / 4), x0 - 4 + 4 * (i % (XS_AW / 4)));
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * 128;
+      const int i = i0 + k * NT;
       if (i < NA) *reinterpret_cast<float4*>(&At[i / (XS_AW / 4)][4 * (i % (XS_AW / 4))]) = v[k];
     }
   }
-  for (int i0 = tid; i0 < NB; i0 += 4 * 128) {
+  for (int i0 = tid; i0 < NB; i0 += 4 * NT) {
     float4 v[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * 128;
+      const int i = i0 + k * NT;
       if (i < NB) v[k] = fetch4(p1, i / (XS_BW / 4), x0 - 20 - d0 + 4 * (i % (XS_BW / 4)));
     }
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int i = i0 + k * 128;
+      const int i = i0 + k * NT;
       if (i < NB) *reinterpret_cast<float4*>(&Bt[i / (XS_BW / 4)][4 * (i % (XS_BW / 4))]) = v[k];
     }
   }
   __syncthreads();
   const int x = x0 + 4 * lane;
-  const int dbase = d0 + 4 * g;  // this warp's first disparity
+  const int dbase = d0 + TD * g;  // this warp's first disparity
   if (dbase >= D) return;  // warp-uniform: nothing to write, no CTA barrier follows
   // suf[j-1][dl][k], j = 1..BS-1: sum of rows j..BS-1 of the previous block; rows < j of the current block
   // overwrite it with their own horizontal sums as they are produced
-  float suf[BS - 1][4][4], F[4][4];
+  float suf[BS - 1][TD][4], F[TD][4];
 #pragma unroll
-  for (int dl = 0; dl < 4; ++dl)
+  for (int dl = 0; dl < TD; ++dl)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       F[dl][k] = 0.f;
 #pragma unroll
       for (int j = 0; j < BS - 1; ++j) suf[j][dl][k] = 0.f;
     }
-  // tile column of image column (x - 4 - d) is 4*lane + 16 - (d - d0); the aligned 16 values from
-  // 4*lane + 12 - 4g cover the four disparities of this warp
+  // tile column of image column (x - 4 - d) is 4*lane + 16 - (d - d0).  TD = 4: the 16 values from 4*lane + 12 - 4g
+  // (128-bit aligned) cover the warp's four disparities, tap t of disparity dl is bv[4 - dl + t].  TD = 2: the 14 values
+  // from 4*lane + 14 - 2g (64-bit aligned) cover two, tap t of disparity dl is bv[2 - dl + t].
+  constexpr int BOFF = TD == 4 ? 4 : 2;
   const float* arow = &At[0][4 * lane];
-  const float* brow = &Bt[0][4 * lane + 12 - 4 * g];
+  const float* brow = &Bt[0][4 * lane + 16 - BOFF - TD * g];
   float* outp = out + (((int64_t)b * D + dbase) * H) * W + x;
   const int64_t dstride = (int64_t)H * W;
   // Window statistics of the output rows stream through a per-warp shared-memory ring: one lane fetches a
   // row's w-side {N*mu0, sd0} (128 positions) and u-side {mu1, sd1} (136 positions u = x0-dbase-4 ..) with two
-  // cp.async.bulk copies, XS_NST rows ahead, completion on an mbarrier -- no registers are held across the
+  // cp.async.bulk copies, NST rows ahead, completion on an mbarrier -- no registers are held across the
   // arithmetic and the L2 round trip is off the critical path.
-  XsStatRing& ring = rings[g];
+  Ring& ring = rings[g];
   const float2* wsrc = st0 + ((int64_t)b * H) * ws0 + x0;
   const float2* usrc = st1 + ((int64_t)b * H) * ws1 + (x0 - dbase - 4 + uoff);
   const uint32_t wbytes = (uint32_t)min(XS_W, ws0 - x0) * 8u;
   const uint32_t ubytes = (uint32_t)min(XS_W + 8, ws1 - (x0 - dbase - 4 + uoff)) * 8u;
   const int nrows = min(XH, H - y0);  // output rows of this tile
-  auto issue = [&](int e) {           // lane 0: fetch the statistics of output row y0 + e into stage e % XS_NST
-    const int st = e % XS_NST;
+  auto issue = [&](int e) {           // lane 0: fetch the statistics of output row y0 + e into stage e % NST
+    const int st = e % NST;
     fence_proxy_async();
     mbar_expect_tx(&ring.full[st], wbytes + ubytes);
     bulk_load(&ring.w[st][0], wsrc + (int64_t)(y0 + e) * ws0, wbytes, &ring.full[st]);
@@ -469,9 +484,9 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   };
   if (lane == 0) {
 #pragma unroll
-    for (int st = 0; st < XS_NST; ++st) mbar_init(&ring.full[st], 1);
+    for (int st = 0; st < NST; ++st) mbar_init(&ring.full[st], 1);
     fence_barrier_init();
-    for (int e = 0; e < XS_NST && e < nrows; ++e) issue(e);
+    for (int e = 0; e < NST && e < nrows; ++e) issue(e);
   }
   __syncwarp();
 #pragma unroll 1
@@ -486,19 +501,29 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
         a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
         a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
         a[8] = a2.x; a[9] = a2.y; a[10] = a2.z; a[11] = a2.w;
-        const float4* bp = reinterpret_cast<const float4*>(brow + r * XS_BW);
-        const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-        bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
-        bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-        bv[8] = b2.x; bv[9] = b2.y; bv[10] = b2.z; bv[11] = b2.w;
-        bv[12] = b3.x; bv[13] = b3.y; bv[14] = b3.z; bv[15] = b3.w;
+        if (TD == 4) {
+          const float4* bp = reinterpret_cast<const float4*>(brow + r * XS_BW);
+          const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+          bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+          bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+          bv[8] = b2.x; bv[9] = b2.y; bv[10] = b2.z; bv[11] = b2.w;
+          bv[12] = b3.x; bv[13] = b3.y; bv[14] = b3.z; bv[15] = b3.w;
+        } else {
+          const float2* bp = reinterpret_cast<const float2*>(brow + r * XS_BW);
+#pragma unroll
+          for (int q = 0; q < 7; ++q) {
+            const float2 v2 = bp[q];
+            bv[2 * q] = v2.x;
+            bv[2 * q + 1] = v2.y;
+          }
+        }
       }
       const int yo = y0 + r - 2 * R;                       // the window ending at tile row r
       const bool emit = (blk > 0 || j == BS - 1) && yo < H;  // warp-uniform
       float2 wst[4], ust[8];
       if (emit) {  // conflict-free 128-bit reads of this row's statistics, once per row
-        const int e = r - 2 * R, st = e % XS_NST;
-        mbar_wait(&ring.full[st], (uint32_t)(e / XS_NST) & 1u);
+        const int e = r - 2 * R, st = e % NST;
+        mbar_wait(&ring.full[st], (uint32_t)(e / NST) & 1u);
         const float4* wp = reinterpret_cast<const float4*>(&ring.w[st][4 * lane]);
         const float4* up = reinterpret_cast<const float4*>(&ring.u[st][4 * lane]);
         const float4 w01 = wp[0], w23 = wp[1], u01 = up[0], u23 = up[1], u45 = up[2], u67 = up[3];
@@ -510,10 +535,10 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
         ust[6] = make_float2(u67.x, u67.y); ust[7] = make_float2(u67.z, u67.w);
       }
 #pragma unroll
-      for (int dl = 0; dl < 4; ++dl) {
+      for (int dl = 0; dl < TD; ++dl) {
         float p[12], hs[4], S[4];
 #pragma unroll
-        for (int t = 4 - R; t <= 7 + R; ++t) p[t] = a[t] * bv[4 - dl + t];
+        for (int t = 4 - R; t <= 7 + R; ++t) p[t] = a[t] * bv[BOFF - dl + t];
         xs_hsum<BS>(p, hs);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -549,10 +574,10 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
           }
         }
       }
-      if (emit) {  // every lane has read this stage: hand it to the row XS_NST further down
+      if (emit) {  // every lane has read this stage: hand it to the row NST further down
         __syncwarp();
         const int e = r - 2 * R;
-        if (lane == 0 && e + XS_NST < nrows) issue(e + XS_NST);
+        if (lane == 0 && e + NST < nrows) issue(e + NST);
       }
     }
   }
@@ -641,10 +666,11 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
   uint8_t* g0 = reinterpret_cast<uint8_t*>(count + 4);
   uint8_t* g1 = g0 + n0;
   const size_t st_smem = sizeof(double) * 2 * (ST_H + 2 * R) * ST_W + sizeof(float) * (ST_H + 2 * R) * (ST_W + 2 * R);
-  const size_t smem = sizeof(float) * TH * (XS_AW + XS_BW) + 4 * sizeof(XsStatRing);
+  constexpr int TD = XS_TD;
+  const size_t smem = sizeof(float) * TH * (XS_AW + XS_BW) + (16 / TD) * sizeof(XsStatRing<XsNst<TD>::value>);
   static const bool attr_ok =
       cudaFuncSetAttribute(xcorr_stats_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem) == cudaSuccess &&
-      cudaFuncSetAttribute(xcorr_sep_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+      cudaFuncSetAttribute(xcorr_sep_kernel<BS, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
   if (!attr_ok || cudaMemsetAsync(count, 0, sizeof(unsigned), st) != cudaSuccess) {
     cudaGetLastError();
     scratch_free(scratch, st);
@@ -656,7 +682,7 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
       in1, st1, g1, (int)H, (int)W, (int)ws1, (int)uoff, 1.0f, 0x80000000u, list, count);
   const int vec = (W % 4 == 0) && !((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) |
                                      reinterpret_cast<uintptr_t>(out)) & 15);
-  xcorr_sep_kernel<BS><<<dim3((unsigned)cdiv(W, XS_W), (unsigned)cdiv(H, XH), (unsigned)(B * ndchunks)), 128, smem, st>>>(
+  xcorr_sep_kernel<BS, TD><<<dim3((unsigned)cdiv(W, XS_W), (unsigned)cdiv(H, XH), (unsigned)(B * ndchunks)), 512 / TD, smem, st>>>(
       in0, in1, out, st0, st1, (int)H, (int)W, (int)D, (int)ws0, (int)ws1, (int)uoff, (int)ndchunks, vec);
   if (!g_xcorr_nofix)
     xcorr_fixup_kernel<BS><<<148 * 3, 256, 0, st>>>(in0, in1, out, g0, g1, list, count, (int)H, (int)W, (int)D, (int)ws0,
