@@ -364,6 +364,10 @@ photo_bwd_box9(const float* __restrict__ es, const float* __restrict__ ta, const
 #endif
 constexpr int CT_W = 64, CT_H = CTD_CT_H;  // output tile; 16 rows of threads, CT_H / 16 passes
 constexpr int CT_NH = CT_H / 16;
+#ifndef CTD_CB_NPX
+#define CTD_CB_NPX 2
+#endif
+constexpr int CB_NPX = CTD_CB_NPX;  // pixels per thread and pass in the census backward
 static_assert(CT_H % 16 == 0, "census tile height");
 constexpr int CE_W = CT_W + 2 * R9;  // 72
 constexpr int CE_H = CT_H + 2 * R9;  // 40
@@ -588,28 +592,54 @@ __device__ __forceinline__ float xor_sign(float v, float s) {  // v * sign(s) fo
 // because h(-x) = 1 - h(x).  go is zero outside the image, es/ta are replicate-clamped.
 // FUSE: also accumulate the forward's psi(dd) over the same 81 (replicate-clamped) taps into facc[half][k] --
 // the backward evaluates every dd the forward needs, so the loss map costs one more add per tap.
-template <int TYPE, bool BORDER, bool FUSE>
+// NPX pixels per thread and pass (4: 16 rows of 16 threads, 128-bit shared loads; 2: 8 rows of 32 threads, 64-bit
+// loads, fewer registers -> three CTAs per SM).
+template <int NPX>
+__device__ __forceinline__ void unpack_row(float* d, const float* srow) {  // NPX + 8 values from column NPX * tx
+  if (NPX == 4) {
+    unpack12(d, srow);
+  } else {
+    const float2* p = reinterpret_cast<const float2*>(srow);
+#pragma unroll
+    for (int q = 0; q < (NPX + 8) / 2; ++q) {
+      const float2 v = p[q];
+      d[2 * q] = v.x;
+      d[2 * q + 1] = v.y;
+    }
+  }
+}
+
+template <int TYPE, bool BORDER, bool FUSE, int NPX>
 __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[CE_W], float (*Gs)[CE_W],
                                                 float* __restrict__ gi, int x0, int y0, int H, int W,
                                                 float eps, int vec, int tx, int ty, unsigned* __restrict__ list,
-                                                unsigned* __restrict__ count, unsigned plane_base, float (*facc)[4]) {
+                                                unsigned* __restrict__ count, unsigned plane_base, float (*facc)[NPX]) {
+  constexpr int RPP = 256 / (CT_W / NPX);  // tile rows per pass
 #pragma unroll 1
-  for (int half = 0; half < CT_NH; ++half) {
-    const int yl = ty + 16 * half;
-    const int gy = y0 + yl, gx = x0 + 4 * tx;
+  for (int half = 0; half < CT_H / RPP; ++half) {
+    const int yl = ty + RPP * half;
+    const int gy = y0 + yl, gx = x0 + NPX * tx;
     if (gy >= H) continue;
-    const float4 ec4 = *reinterpret_cast<const float4*>(&Es[yl + R9][4 * tx + R9]);
-    const float4 tc4 = *reinterpret_cast<const float4*>(&Ts[yl + R9][4 * tx + R9]);
-    const float4 gc4 = *reinterpret_cast<const float4*>(&Gs[yl + R9][4 * tx + R9]);
-    const float ec[4] = {ec4.x, ec4.y, ec4.z, ec4.w}, tc[4] = {tc4.x, tc4.y, tc4.z, tc4.w};
-    const float gc[4] = {gc4.x, gc4.y, gc4.z, gc4.w};
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    float near0[4] = {1.f, 1.f, 1.f, 1.f};  // census_sad: smallest |dd| over the window (centre tap excluded)
+    float ec[NPX], tc[NPX], gc[NPX];
+#pragma unroll
+    for (int k = 0; k < NPX; ++k) {
+      ec[k] = Es[yl + R9][NPX * tx + R9 + k];
+      tc[k] = Ts[yl + R9][NPX * tx + R9 + k];
+      gc[k] = Gs[yl + R9][NPX * tx + R9 + k];
+    }
+    float acc[NPX], near0[NPX];  // near0 (census_sad): smallest |dd| over the window (centre tap excluded)
     // clamp multiplicity of the column / row offset d (-4..4): base + slope * d
-    float bx[4] = {1.f, 1.f, 1.f, 1.f}, sx[4] = {0.f, 0.f, 0.f, 0.f}, by = 1.f, sy = 0.f;
+    float bx[NPX], sx[NPX], by = 1.f, sy = 0.f;
+#pragma unroll
+    for (int k = 0; k < NPX; ++k) {
+      acc[k] = 0.f;
+      near0[k] = 1.f;
+      bx[k] = 1.f;
+      sx[k] = 0.f;
+    }
     if (BORDER) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < NPX; ++k) {
         if (gx + k == 0) { bx[k] = 5.f; sx[k] = -1.f; }
         if (gx + k == W - 1) { bx[k] = 5.f; sx[k] = 1.f; }
       }
@@ -618,16 +648,16 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
     }
 #pragma unroll 1
     for (int dy = 0; dy < 9; ++dy) {
-      float e[12], t[12], g[12];
-      unpack12(e, &Es[yl + dy][4 * tx]);
-      unpack12(t, &Ts[yl + dy][4 * tx]);
-      unpack12(g, &Gs[yl + dy][4 * tx]);
+      float e[NPX + 8], t[NPX + 8], g[NPX + 8];
+      unpack_row<NPX>(e, &Es[yl + dy][NPX * tx]);
+      unpack_row<NPX>(t, &Ts[yl + dy][NPX * tx]);
+      unpack_row<NPX>(g, &Gs[yl + dy][NPX * tx]);
       const float my = BORDER ? fmaf(sy, float(dy - R9), by) : 1.f;
       // rows whose clamped tap row is the pixel's own row: the centre row, and at the first / last image row
       // every window row beyond the border
       const bool ctr_row = dy == R9 || (BORDER && ((sy < 0.f && dy < R9) || (sy > 0.f && dy > R9)));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < NPX; ++k) {
 #pragma unroll
         for (int dx = 0; dx < 9; ++dx) {
           const float des = ec[k] - e[k + dx];
@@ -665,12 +695,12 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
       // (no real centre there, so only the "pixel as centre" half): r0^3 * gc * (2 * bx*by) in total
       const float r0 = rsqrt_approx(eps);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) acc[k] -= r0 * r0 * r0 * (2.f * bx[k] * by) * gc[k];
+      for (int k = 0; k < NPX; ++k) acc[k] -= r0 * r0 * r0 * (2.f * bx[k] * by) * gc[k];
     }
     const float scale = 0.5f * eps * INV81;
-    float r[4];
+    float r[NPX];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < NPX; ++k) {
       r[k] = acc[k] * scale;
       if (TYPE == 3 && list == nullptr && near0[k] < SIGN_GUARD) r[k] = __uint_as_float(SIGN_MARKER);  // scan fix-up redoes it
     }
@@ -678,7 +708,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
       // near-tie pixels go on the fix-up list: one atomic per warp (ballot + prefix over the lanes)
       unsigned mine = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) mine |= (near0[k] < SIGN_GUARD && gx + k < W) ? (1u << k) : 0u;
+      for (int k = 0; k < NPX; ++k) mine |= (near0[k] < SIGN_GUARD && gx + k < W) ? (1u << k) : 0u;
       const unsigned active = __activemask();
       if (__any_sync(active, mine != 0u)) {
         const int lane = threadIdx.x & 31;
@@ -696,23 +726,26 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
         base = __shfl_sync(active, base, leader);
         unsigned slot = base + (unsigned)prefix;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < NPX; ++k)
           if (mine & (1u << k)) list[slot++] = plane_base + (unsigned)(gy * W + gx + k);
       }
     }
     float* dst = gi + (int64_t)gy * W + gx;
     if (vec) {
-      if (gx < W) *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[3]);
+      if (gx < W) {
+        if (NPX == 4) *reinterpret_cast<float4*>(dst) = make_float4(r[0], r[1], r[2], r[NPX - 1]);
+        else *reinterpret_cast<float2*>(dst) = make_float2(r[0], r[1]);
+      }
     } else {
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
+      for (int k = 0; k < NPX; ++k)
         if (gx + k < W) dst[k] = r[k];
     }
   }
 }
 
-template <int TYPE, bool FUSE>
-__global__ void __launch_bounds__(256)
+template <int TYPE, bool FUSE, int NPX>
+__global__ void __launch_bounds__(256, NPX == 4 ? 2 : 3)
 photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
                   float* __restrict__ gi, float* __restrict__ out, int C, int H, int W, float eps, int vec,
                   unsigned* __restrict__ list, unsigned* __restrict__ count) {
@@ -722,10 +755,11 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
   const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
   const int64_t n = blockIdx.z;
   const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;
+  constexpr int TXN = CT_W / NPX, RPP = 256 / TXN, NP = CT_H / RPP;
+  const int tx = tid % TXN, ty = tid / TXN;
   const int64_t plane = (int64_t)H * W;
   const bool border = x0 == 0 || y0 == 0 || x0 + CT_W >= W || y0 + CT_H >= H;
-  float facc[CT_NH][4] = {};
+  float facc[NP][NPX] = {};
   load_halo_tile<false>(Gs, go + n * plane, x0, y0, H, W, vec, tid);
   for (int c = 0; c < C; ++c) {
     if (c) __syncthreads();
@@ -734,23 +768,27 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
     __syncthreads();
     float* gic = gi + (n * C + c) * plane;
     const unsigned pb = (unsigned)((n * C + c) * plane);
-    if (border) census_bwd_tile<TYPE, true, FUSE>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb, facc);
-    else census_bwd_tile<TYPE, false, FUSE>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb, facc);
+    if (border) census_bwd_tile<TYPE, true, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb, facc);
+    else census_bwd_tile<TYPE, false, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb, facc);
   }
   if (FUSE) {  // the loss map: sum over channels and taps, same scaling as photo_fwd_census9
     const float scale = (TYPE == 2 ? 0.25f : 0.5f) * INV81;
 #pragma unroll
-    for (int half = 0; half < CT_NH; ++half) {
-      const int gy = y0 + ty + 16 * half, gx = x0 + 4 * tx;
+    for (int half = 0; half < NP; ++half) {
+      const int gy = y0 + ty + RPP * half, gx = x0 + NPX * tx;
       if (gy >= H) continue;
       float* dst = out + n * plane + (int64_t)gy * W + gx;
       if (vec) {
-        if (gx < W)
-          *reinterpret_cast<float4*>(dst) = make_float4(facc[half][0] * scale, facc[half][1] * scale, facc[half][2] * scale,
-                                                        facc[half][3] * scale);
+        if (gx < W) {
+          if (NPX == 4)
+            *reinterpret_cast<float4*>(dst) = make_float4(facc[half][0] * scale, facc[half][1] * scale, facc[half][2] * scale,
+                                                          facc[half][NPX - 1] * scale);
+          else
+            *reinterpret_cast<float2*>(dst) = make_float2(facc[half][0] * scale, facc[half][1] * scale);
+        }
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < NPX; ++k)
           if (gx + k < W) dst[k] = facc[half][k] * scale;
       }
     }
@@ -804,8 +842,8 @@ static void census_bwd_launch(const float* e, const float* t, const float* g, fl
                               int64_t H, int64_t W, int type, float eps, int vec, cudaStream_t st) {
   dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
   if (type == 2) {
-    if (out) photo_bwd_census9<2, true><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
-    else photo_bwd_census9<2, false><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
+    if (out) photo_bwd_census9<2, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
+    else photo_bwd_census9<2, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
     return;
   }
   // census_sad near-tie pixels: listed by the tile kernel when scratch memory is available, else marked and found by a scan
@@ -817,8 +855,8 @@ static void census_bwd_launch(const float* e, const float* t, const float* g, fl
     scratch = nullptr;
   }
   unsigned* list = scratch ? scratch + 1 : nullptr;
-  if (out) photo_bwd_census9<3, true><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, list, scratch);
-  else photo_bwd_census9<3, false><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, list, scratch);
+  if (out) photo_bwd_census9<3, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, list, scratch);
+  else photo_bwd_census9<3, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, list, scratch);
   if (scratch) {
     census_sad_bwd_fixup_list<<<148 * 4, 256, 0, st>>>(e, t, g, o, list, scratch, (int)C, (int)H, (int)W, eps);
     scratch_free(scratch, st);
