@@ -1,5 +1,5 @@
 import sys, time, ctypes
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 import numpy as np, torch
 from connecting_the_dots_b200 import _lib, synth
 B, H, W = 8, 480, 640

@@ -1,5 +1,5 @@
 import sys
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__)))))
 import numpy as np, torch
 import connecting_the_dots_b200 as ctd
 from connecting_the_dots_b200 import synth
