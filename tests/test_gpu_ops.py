@@ -332,6 +332,25 @@ def test_xcorrvol_separable_matches_direct(tx):
     assert_close(fast.cpu().numpy(), direct.cpu().numpy(), what="separable vs direct")
 
 
+def test_xcorrvol_full_size_properties(tx):
+    """BASELINE config 3 size (480x640, D=128, block 9), checked through size-independent properties: the volume is a
+    correlation coefficient (|.| <= 1), an image against itself scores 1 at d = 0, against a copy shifted by s pixels
+    it scores 1 at d = s, and batching does not change any image's result."""
+    from connecting_the_dots_b200 import synth
+    d = synth.make_batch(2)
+    a = cu(d["ta"])
+    s = 37
+    b = torch.roll(a, -s, dims=3)  # b[x] = a[x + s]  ->  b[w - s] = a[w]
+    vol = tx.xcorrvol(a, b, 128, 9)
+    assert vol.shape == (2, 128, 480, 640)
+    assert float(vol.abs().max()) <= 1 + 1e-5
+    assert float((vol[:, s, :, s + 8:640 - s - 8] - 1).abs().max()) <= 1e-5
+    self_vol = tx.xcorrvol(a, a, 4, 9)
+    assert float((self_vol[:, 0] - 1).abs().max()) <= 1e-5
+    one = tx.xcorrvol(a[1], b[1], 128, 9)
+    assert torch.equal(one, vol[1])
+
+
 def test_xcorrvol_synthetic_lcn_data(tx):
     """LCN'd dot-pattern rows (the BASELINE config 3 data) on a crop the oracle finishes quickly."""
     from connecting_the_dots_b200 import synth
