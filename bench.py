@@ -9,11 +9,11 @@ A "step" is one pass of the hot path over one batch of synthetic 480x640 dot-pat
 (SURVEY.md section 8d data), batch 8 per GPU:
     LCN(5, 0.05) forward  ->  PhotometricLoss 'sad' ("l1") forward + backward
                           ->  PhotometricLoss 'census_sad' (the reference's structural mode, standing in
-                              for "ssim") forward + backward -- through
+                              for "ssim") forward + backward -- each through
                               ctd_photometric_fwd_bwd_f32, which produces the loss map and the gradient in
                               ONE kernel (grad_out = std / sum(std) is an input, as in networks.py:377)
                           ->  the caller's masked loss reduction (networks.py:377), twice
-The same chain with census_sad forward and backward as two separate calls (what torch autograd does with
+The same chain with every forward and backward as two separate calls (what torch autograd does with
 photometric_loss) is timed as well and reported as `separate_calls`.
 and, for N > 1, one packed NCCL all-reduce of the four loss scalars.  value = pixels per second through
 that whole chain (N * B * H * W / step time); per-op figures are in "ops".
@@ -43,10 +43,10 @@ H, W, B_PER_GPU, BS, EPS, LCN_R, LCN_EPS = 480, 640, 8, 9, 0.5, 5, 0.05
 NSETS = 4
 METRIC = "Mpix/s through LCN fwd + PhotometricLoss sad fwd+bwd + census_sad fwd+bwd (batch 8, 480x640); per-op Mpix/s in ops"
 WORKLOAD = ("configs[1]: LCN(5,0.05) fwd + PhotometricLoss l1(sad) fwd+bwd + census_sad (stands in for ssim) fwd+bwd "
-            "(one fused call) + masked loss sums, batch 8 per GPU, 480x640, block 9, eps 0.5, C=1")
+            "(one fused call each) + masked loss sums, batch 8 per GPU, 480x640, block 9, eps 0.5, C=1")
 # algorithmic bytes per pixel, fp32, C=1
 BYTES_PER_PX = {"lcn_fwd": 12, "sad_fwd": 12, "sad_bwd": 16, "census_sad_fwd": 12, "census_sad_bwd": 16,
-                "census_sad_fwd_bwd": 20,  # fused: es, ta, grad_out in; loss map, grad_in out -- each tensor once
+                "sad_fwd_bwd": 20, "census_sad_fwd_bwd": 20,  # fused: es, ta, grad_out in; loss map, grad_in out -- each tensor once
                 "masked_sums": 8}
 
 
@@ -261,7 +261,7 @@ def run_b200_arm(args, rank, world, local_rank):
     footprint_mb = NSETS * 10 * npx * 4 / 1e6
     stream = torch.cuda.current_stream(dev)
     st = stream.cuda_stream
-    OPS = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd_bwd", "masked_sums")
+    OPS = ("lcn_fwd", "sad_fwd_bwd", "census_sad_fwd_bwd", "masked_sums")
     OPS_SEP = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums")
 
     def launch_chain(d, st_, mark, fused=True):
@@ -271,15 +271,18 @@ def run_b200_arm(args, rank, world, local_rank):
         _lib.call("ctd_lcn_f32", p["im"], p["lcn"], p["std"], B, H, W, LCN_R, LCN_EPS, st_)
         i += 1
         mark(i)
-        _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_sad"], B, 1, H, W, BS, 1, EPS, st_)
-        i += 1
-        mark(i)
-        _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_sad"], B, 1, H, W, BS, 1, EPS, st_)
-        i += 1
-        mark(i)
         if fused:
+            _lib.call("ctd_photometric_fwd_bwd_f32", p["es"], p["ta"], p["go"], p["out_sad"], p["gi_sad"], B, 1, H, W, BS, 1, EPS, st_)
+            i += 1
+            mark(i)
             _lib.call("ctd_photometric_fwd_bwd_f32", p["es"], p["ta"], p["go"], p["out_cs"], p["gi_cs"], B, 1, H, W, BS, 3, EPS, st_)
         else:
+            _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_sad"], B, 1, H, W, BS, 1, EPS, st_)
+            i += 1
+            mark(i)
+            _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], p["gi_sad"], B, 1, H, W, BS, 1, EPS, st_)
+            i += 1
+            mark(i)
             _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_cs"], B, 1, H, W, BS, 3, EPS, st_)
             i += 1
             mark(i)
@@ -387,7 +390,8 @@ def run_b200_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sep_ms_per_step = float(t.item()) / sep_steps
     sep_ms = {n: float(np.mean([sep_events[si][i].elapsed_time(sep_events[si][i + 1]) for si in range(NSETS)])) for i, n in enumerate(OPS_SEP)}
-    op_ms["census_sad_fwd"], op_ms["census_sad_bwd"] = sep_ms["census_sad_fwd"], sep_ms["census_sad_bwd"]
+    for n in ("sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd"):
+        op_ms[n] = sep_ms[n]
 
     # ---- e2e leg: the C ABI's host-buffer entry points, pinned host inputs/outputs, copies timed
     P = lambda t_: ctypes.c_void_p(t_.data_ptr())
@@ -425,15 +429,11 @@ def run_b200_arm(args, rank, world, local_rank):
         return
     peak, peak_src = measured_peak()
     ops = {}
-    for n in OPS + ("census_sad_fwd", "census_sad_bwd"):
+    for n in OPS + ("sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd"):
         gbs = BYTES_PER_PX[n] * npx / (op_ms[n] * 1e-3) / 1e9
         ops[n] = {"ms": op_ms[n], "mpix_s": npx / (op_ms[n] * 1e-3) / 1e6, "algo_bytes_per_px": BYTES_PER_PX[n],
                   "achieved_gbs": gbs, "frac_hbm": gbs / peak, "in_step": n in OPS}
-    ms = op_ms["sad_fwd"] + op_ms["sad_bwd"]
-    gbs = 28 * npx / (ms * 1e-3) / 1e9
-    ops["sad_fwd_bwd"] = {"ms": ms, "mpix_s": npx / (ms * 1e-3) / 1e6, "algo_bytes_per_px": 28, "achieved_gbs": gbs,
-                          "frac_hbm": gbs / peak, "in_step": True}
-    dom = max(OPS[:4], key=lambda n: op_ms[n])
+    dom = max(OPS[:3], key=lambda n: op_ms[n])
     traffic, traffic_src = None, None
     try:  # DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -461,7 +461,7 @@ def run_b200_arm(args, rank, world, local_rank):
                     "api": "ctd_host_begin_batch; ctd_host_lcn_f32 + 2x ctd_host_photometric_fwd_bwd_f32; ctd_host_end_batch -- pinned host buffers"},
             "roofline": roofline, "ops": ops,
             "separate_calls": {"ms_per_step": sep_ms_per_step, "value": npx_global / (sep_ms_per_step * 1e-3) / 1e6, "steps": sep_steps,
-                               "note": "same chain, census_sad forward and backward as two calls (torch autograd path)"}}
+                               "note": "same chain, forward and backward of both losses as separate calls (torch autograd path)"}}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
     print(json.dumps(line), flush=True)

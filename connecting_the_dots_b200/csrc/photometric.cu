@@ -26,6 +26,8 @@ int box9_tma_fwd(const float* es, const float* ta, float* out, int64_t B, int64_
                  cudaStream_t st);
 int box9_tma_bwd(const float* es, const float* ta, const float* go, float* gi, int64_t B, int64_t C, int64_t H,
                  int64_t W, int type, cudaStream_t st);
+int box9_tma_fwd_bwd(const float* es, const float* ta, const float* go, float* out, float* gi, int64_t B, int64_t C,
+                     int64_t H, int64_t W, int type, cudaStream_t st);
 int census_pairs_fwd(const float* es, const float* ta, float* out, int64_t B, int64_t C, int64_t H, int64_t W, int type,
                      float eps, cudaStream_t st);
 
@@ -955,6 +957,9 @@ CTD_API int ctd_photometric_fwd_bwd_f32(const float* es, const float* ta, const 
     }
     return check_launch("photometric_fwd_bwd(census, fused)");
   }
+  if (type >= 0 && type <= 1 && fast9_ok(bs, H, W) && C >= 1 && B >= 1 && es && ta && go && out && gi &&
+      box9_tma_fwd_bwd(es, ta, go, out, gi, B, C, H, W, type, st))
+    return check_launch("photometric_fwd_bwd(box, fused)");
   if (int rc = ctd_photometric_fwd_f32(es, ta, out, B, C, H, W, bs, type, eps, stream)) return rc;
   return ctd_photometric_bwd_f32(es, ta, go, gi, B, C, H, W, bs, type, eps, stream);
 }
