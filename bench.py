@@ -10,10 +10,10 @@ A "step" is one pass of the hot path over one batch of synthetic 480x640 dot-pat
     LCN(5, 0.05) forward  ->  PhotometricLoss 'sad' ("l1") forward + backward
                           ->  PhotometricLoss 'census_sad' (the reference's structural mode, standing in
                               for "ssim") forward + backward -- each through
-                              ctd_photometric_fwd_bwd_f32, which produces the loss map and the gradient in
-                              ONE kernel (grad_out = std / sum(std) is an input, as in networks.py:377)
-                          ->  the caller's masked loss reduction (networks.py:377), twice
-The same chain with every forward and backward as two separate calls (what torch autograd does with
+                              ctd_photometric_fwd_bwd_masked_f32, which produces the loss map, the gradient
+                              (grad_out = std / sum(std) is an input, as in networks.py:377) and the caller's
+                              masked loss reduction (networks.py:377) in ONE pass
+The same chain with every forward, backward and masked reduction as separate calls (what torch autograd does with
 photometric_loss) is timed as well and reported as `separate_calls`.
 and, for N > 1, one packed NCCL all-reduce of the four loss scalars.  value = pixels per second through
 that whole chain (N * B * H * W / step time); per-op figures are in "ops".
@@ -43,10 +43,10 @@ H, W, B_PER_GPU, BS, EPS, LCN_R, LCN_EPS = 480, 640, 8, 9, 0.5, 5, 0.05
 NSETS = 4
 METRIC = "Mpix/s through LCN fwd + PhotometricLoss sad fwd+bwd + census_sad fwd+bwd (batch 8, 480x640); per-op Mpix/s in ops"
 WORKLOAD = ("configs[1]: LCN(5,0.05) fwd + PhotometricLoss l1(sad) fwd+bwd + census_sad (stands in for ssim) fwd+bwd "
-            "(one fused call each) + masked loss sums, batch 8 per GPU, 480x640, block 9, eps 0.5, C=1")
+            "+ masked loss sums (one fused call per loss), batch 8 per GPU, 480x640, block 9, eps 0.5, C=1")
 # algorithmic bytes per pixel, fp32, C=1
 BYTES_PER_PX = {"lcn_fwd": 12, "sad_fwd": 12, "sad_bwd": 16, "census_sad_fwd": 12, "census_sad_bwd": 16,
-                "sad_fwd_bwd": 20, "census_sad_fwd_bwd": 20,  # fused: es, ta, grad_out in; loss map, grad_in out -- each tensor once
+                "sad_fwd_bwd": 24, "census_sad_fwd_bwd": 24,  # fused: es, ta, grad_out, mask in; loss map, grad_in out -- each tensor once
                 "masked_sums": 8}
 
 
@@ -261,7 +261,7 @@ def run_b200_arm(args, rank, world, local_rank):
     footprint_mb = NSETS * 10 * npx * 4 / 1e6
     stream = torch.cuda.current_stream(dev)
     st = stream.cuda_stream
-    OPS = ("lcn_fwd", "sad_fwd_bwd", "census_sad_fwd_bwd", "masked_sums")
+    OPS = ("lcn_fwd", "sad_fwd_bwd", "census_sad_fwd_bwd")  # the fused calls include the masked sums
     OPS_SEP = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums")
 
     def launch_chain(d, st_, mark, fused=True):
@@ -272,10 +272,15 @@ def run_b200_arm(args, rank, world, local_rank):
         i += 1
         mark(i)
         if fused:
-            _lib.call("ctd_photometric_fwd_bwd_f32", p["es"], p["ta"], p["go"], p["out_sad"], p["gi_sad"], B, 1, H, W, BS, 1, EPS, st_)
+            _lib.call("ctd_photometric_fwd_bwd_masked_f32", p["es"], p["ta"], p["go"], p["std"], p["out_sad"], p["gi_sad"], p["sums"],
+                      B, 1, H, W, BS, 1, EPS, st_)
             i += 1
             mark(i)
-            _lib.call("ctd_photometric_fwd_bwd_f32", p["es"], p["ta"], p["go"], p["out_cs"], p["gi_cs"], B, 1, H, W, BS, 3, EPS, st_)
+            _lib.call("ctd_photometric_fwd_bwd_masked_f32", p["es"], p["ta"], p["go"], p["std"], p["out_cs"], p["gi_cs"], p["sums"] + 8,
+                      B, 1, H, W, BS, 3, EPS, st_)
+            i += 1
+            mark(i)
+            return
         else:
             _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], p["out_sad"], B, 1, H, W, BS, 1, EPS, st_)
             i += 1
@@ -372,7 +377,6 @@ def run_b200_arm(args, rank, world, local_rank):
     # region; NSETS samples per op, all taken from timed steps
     used = [si for si in range(NSETS) if si < args.steps]
     op_ms = {n: float(np.mean([set_events[si][i].elapsed_time(set_events[si][i + 1]) for si in used])) for i, n in enumerate(OPS)}
-    op_ms["masked_sums"] /= 2  # two launches in that interval
     launches = (_lib.launch_count() - launches0) if not use_graph else kernels_per_graph * args.steps
     # the same chain with census_sad forward and backward as separate calls (the autograd path), a few steps
     sep_steps = max(NSETS, min(args.steps, 20))
@@ -390,8 +394,9 @@ def run_b200_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     sep_ms_per_step = float(t.item()) / sep_steps
     sep_ms = {n: float(np.mean([sep_events[si][i].elapsed_time(sep_events[si][i + 1]) for si in range(NSETS)])) for i, n in enumerate(OPS_SEP)}
-    for n in ("sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd"):
+    for n in ("sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums"):
         op_ms[n] = sep_ms[n]
+    op_ms["masked_sums"] /= 2  # two launches in that interval
 
     # ---- e2e leg: the C ABI's host-buffer entry points, pinned host inputs/outputs, copies timed
     P = lambda t_: ctypes.c_void_p(t_.data_ptr())
@@ -429,7 +434,7 @@ def run_b200_arm(args, rank, world, local_rank):
         return
     peak, peak_src = measured_peak()
     ops = {}
-    for n in OPS + ("sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd"):
+    for n in OPS + ("sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums"):
         gbs = BYTES_PER_PX[n] * npx / (op_ms[n] * 1e-3) / 1e9
         ops[n] = {"ms": op_ms[n], "mpix_s": npx / (op_ms[n] * 1e-3) / 1e6, "algo_bytes_per_px": BYTES_PER_PX[n],
                   "achieved_gbs": gbs, "frac_hbm": gbs / peak, "in_step": n in OPS}
@@ -444,7 +449,7 @@ def run_b200_arm(args, rank, world, local_rank):
     roofline = {"kernel": dom, "bound": "hbm", "achieved": ops[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": ops[dom]["frac_hbm"], "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                 "algo_bytes_per_launch": BYTES_PER_PX[dom] * npx, "ms_per_launch": op_ms[dom],
-                "share_of_step": op_ms[dom] / sum(op_ms[n] * (2 if n == "masked_sums" else 1) for n in OPS),
+                "share_of_step": op_ms[dom] / sum(op_ms[n] for n in OPS),
                 "note": "the census kernels evaluate 162 reciprocal square roots per pixel and are bound by the XU (MUFU) "
                         "pipe, not by HBM: ncu sm__inst_executed_pipe_xu 68-86 % of peak (profiles/), so frac stays small by design"}
     line = {"metric": METRIC, "value": npx_global / (ms_per_step * 1e-3) / 1e6, "unit": "Mpix/s", "n_gpus": world,

@@ -66,6 +66,70 @@ __device__ __forceinline__ float4 ldg4_volatile(const float* p) {
   return v;
 }
 
+// Two global sums (the caller's masked-mean numerator and denominator, model/networks.py:377) produced by a kernel
+// that has other work to do: every thread of a 256-thread block passes its share, the block's partial goes to
+// `partials[2 * block]`, and the last block to arrive (ticket counter, zero before the launch) adds all partials in
+// index order in fp64 and writes out2 -- deterministic for a given grid, no floating-point atomics.
+__device__ __forceinline__ void finish_masked_sums(double num, double den, double* __restrict__ partials,
+                                                   unsigned* __restrict__ ticket, float* __restrict__ out2) {
+  __shared__ double s_num[8], s_den[8];
+  __shared__ bool s_last;
+  const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+  const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    num += __shfl_xor_sync(0xffffffffu, num, o);
+    den += __shfl_xor_sync(0xffffffffu, den, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    s_num[threadIdx.x >> 5] = num;
+    s_den[threadIdx.x >> 5] = den;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+      a += s_num[w];
+      b += s_den[w];
+    }
+    partials[2 * bid] = a;
+    partials[2 * bid + 1] = b;
+    __threadfence();
+    s_last = atomicAdd(ticket, 1u) == nblocks - 1;
+  }
+  __syncthreads();
+  if (s_last) {  // block-uniform: the whole block adds the partials (fixed assignment and order)
+    __threadfence();
+    double a = 0.0, b = 0.0;
+    for (unsigned i = threadIdx.x; i < nblocks; i += blockDim.x) {
+      a += __ldcg(partials + 2 * i);
+      b += __ldcg(partials + 2 * i + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    __syncthreads();  // s_num / s_den of the first phase have been consumed
+    if ((threadIdx.x & 31) == 0) {
+      s_num[threadIdx.x >> 5] = a;
+      s_den[threadIdx.x >> 5] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      a = 0.0;
+      b = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) {
+        a += s_num[w];
+        b += s_den[w];
+      }
+      out2[0] = (float)a;
+      out2[1] = (float)b;
+      *ticket = 0;
+    }
+  }
+}
+
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 }  // namespace ctd

@@ -28,6 +28,9 @@ int box9_tma_bwd(const float* es, const float* ta, const float* go, float* gi, i
                  int64_t W, int type, cudaStream_t st);
 int box9_tma_fwd_bwd(const float* es, const float* ta, const float* go, float* out, float* gi, int64_t B, int64_t C,
                      int64_t H, int64_t W, int type, cudaStream_t st);
+void masked_sums_launch(const float* diff, const float* mask, int64_t n, float* out2, cudaStream_t st);
+int box9_tma_fwd_bwd_masked(const float* es, const float* ta, const float* go, const float* mask, float* out, float* gi,
+                            float* sums2, int64_t B, int64_t C, int64_t H, int64_t W, int type, cudaStream_t st);
 int census_pairs_fwd(const float* es, const float* ta, float* out, int64_t B, int64_t C, int64_t H, int64_t W, int type,
                      float eps, cudaStream_t st);
 
@@ -750,7 +753,8 @@ template <int TYPE, bool FUSE, int NPX>
 __global__ void __launch_bounds__(256, NPX == 4 ? 2 : 3)
 photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
                   float* __restrict__ gi, float* __restrict__ out, int C, int H, int W, float eps, int vec,
-                  unsigned* __restrict__ list, unsigned* __restrict__ count) {
+                  unsigned* __restrict__ list, unsigned* __restrict__ count, const float* __restrict__ mask,
+                  double* __restrict__ partials, unsigned* __restrict__ ticket, float* __restrict__ sums2) {
   __shared__ __align__(16) float Es[CE_H][CE_W];
   __shared__ __align__(16) float Ts[CE_H][CE_W];
   __shared__ __align__(16) float Gs[CE_H][CE_W];
@@ -775,10 +779,29 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
   }
   if (FUSE) {  // the loss map: sum over channels and taps, same scaling as photo_fwd_census9
     const float scale = (TYPE == 2 ? 0.25f : 0.5f) * INV81;
+    float mnum = 0.f, mden = 0.f;  // optional: this thread's share of sum(mask * loss) and sum(mask)
 #pragma unroll
     for (int half = 0; half < NP; ++half) {
       const int gy = y0 + ty + RPP * half, gx = x0 + NPX * tx;
       if (gy >= H) continue;
+      if (mask != nullptr) {
+        const float* mp = mask + n * plane + (int64_t)gy * W + gx;
+        float m[NPX];
+        if (vec && NPX == 2 && gx < W) {
+          const float2 m2 = __ldg(reinterpret_cast<const float2*>(mp));
+          m[0] = m2.x;
+          m[NPX - 1] = m2.y;
+        } else {
+#pragma unroll
+          for (int k = 0; k < NPX; ++k) m[k] = gx + k < W ? __ldg(mp + k) : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < NPX; ++k)
+          if (gx + k < W) {
+            mnum = fmaf(m[k], facc[half][k] * scale, mnum);
+            mden += m[k];
+          }
+      }
       float* dst = out + n * plane + (int64_t)gy * W + gx;
       if (vec) {
         if (gx < W) {
@@ -794,6 +817,7 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
           if (gx + k < W) dst[k] = facc[half][k] * scale;
       }
     }
+    if (mask != nullptr) finish_masked_sums((double)mnum, (double)mden, partials, ticket, sums2);  // block-uniform branch
   }
 }
 
@@ -839,34 +863,50 @@ static int bwd_impl(const T* es, const T* ta, const T* go, T* gi, int64_t B, int
   return check_launch("photometric_bwd(generic)");
 }
 
-// census backward (block 9) of nb images; out != nullptr: the fused forward + backward kernel
-static void census_bwd_launch(const float* e, const float* t, const float* g, float* o, float* out, int nb, int64_t C,
-                              int64_t H, int64_t W, int type, float eps, int vec, cudaStream_t st) {
+// census backward (block 9) of nb images; out != nullptr: the fused forward + backward kernel;
+// mask != nullptr (fused only): also the masked-mean terms sums2 = (sum(mask * loss), sum(mask)).
+// One scratch block per call, one memset: [near-tie count | ticket | pad to 16 B][2 doubles per block][near-tie list].
+// Returns false (nothing launched) when the masked variant cannot get scratch memory.
+static bool census_bwd_launch(const float* e, const float* t, const float* g, float* o, float* out, int nb, int64_t C,
+                              int64_t H, int64_t W, int type, float eps, int vec, cudaStream_t st,
+                              const float* mask = nullptr, float* sums2 = nullptr) {
   dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
-  if (type == 2) {
-    if (out) photo_bwd_census9<2, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
-    else photo_bwd_census9<2, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, nullptr, nullptr);
-    return;
-  }
-  // census_sad near-tie pixels: listed by the tile kernel when scratch memory is available, else marked and found by a scan
   const int64_t total = (int64_t)nb * C * H * W;
-  unsigned* scratch = total < ((int64_t)1 << 32) ? static_cast<unsigned*>(scratch_alloc((size_t)(total + 1) * 4, st)) : nullptr;
-  if (scratch && cudaMemsetAsync(scratch, 0, 4, st) != cudaSuccess) {
-    cudaGetLastError();
-    scratch_free(scratch, st);
-    scratch = nullptr;
+  const size_t nblk = (size_t)grid.x * grid.y * grid.z;
+  const bool want_list = type == 3 && total < ((int64_t)1 << 32);
+  const size_t part_bytes = mask ? nblk * 16 : 0, list_bytes = want_list ? (size_t)total * 4 : 0;
+  char* sc = nullptr;
+  if (mask || want_list) {
+    sc = static_cast<char*>(scratch_alloc(16 + part_bytes + list_bytes, st));
+    if (sc && cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
+      cudaGetLastError();
+      scratch_free(sc, st);
+      sc = nullptr;
+    }
+    if (!sc && mask) return false;
   }
-  unsigned* list = scratch ? scratch + 1 : nullptr;
-  if (out) photo_bwd_census9<3, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, list, scratch);
-  else photo_bwd_census9<3, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, (int)C, (int)H, (int)W, eps, vec, list, scratch);
-  if (scratch) {
-    census_sad_bwd_fixup_list<<<148 * 4, 256, 0, st>>>(e, t, g, o, list, scratch, (int)C, (int)H, (int)W, eps);
-    scratch_free(scratch, st);
+  unsigned* count = sc && want_list ? reinterpret_cast<unsigned*>(sc) : nullptr;
+  unsigned* ticket = sc && mask ? reinterpret_cast<unsigned*>(sc) + 1 : nullptr;
+  double* partials = sc && mask ? reinterpret_cast<double*>(sc + 16) : nullptr;
+  unsigned* list = count ? reinterpret_cast<unsigned*>(sc + 16 + part_bytes) : nullptr;
+  const int iC = (int)C, iH = (int)H, iW = (int)W;
+  if (type == 2) {
+    if (out) photo_bwd_census9<2, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, nullptr, nullptr, mask, partials, ticket, sums2);
+    else photo_bwd_census9<2, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
   } else {
-    const int fgrid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
-    census_sad_bwd_fixup<<<fgrid, 256, 0, st>>>(e, t, g, o, total, (int)C, (int)H, (int)W, eps);
+    // census_sad near-tie pixels: listed by the tile kernel when scratch memory is available, else marked and found by a scan
+    if (out) photo_bwd_census9<3, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, list, count, mask, partials, ticket, sums2);
+    else photo_bwd_census9<3, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, list, count, nullptr, nullptr, nullptr, nullptr);
+    if (list) {
+      census_sad_bwd_fixup_list<<<148 * 4, 256, 0, st>>>(e, t, g, o, list, count, iC, iH, iW, eps);
+    } else {
+      const int fgrid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
+      census_sad_bwd_fixup<<<fgrid, 256, 0, st>>>(e, t, g, o, total, iC, iH, iW, eps);
+    }
+    count_launch();
   }
-  count_launch();
+  scratch_free(sc, st);
+  return true;
 }
 
 static inline int vec_ok(int64_t W, const void* a, const void* b, const void* c, const void* d) {
@@ -962,6 +1002,34 @@ CTD_API int ctd_photometric_fwd_bwd_f32(const float* es, const float* ta, const 
     return check_launch("photometric_fwd_bwd(box, fused)");
   if (int rc = ctd_photometric_fwd_f32(es, ta, out, B, C, H, W, bs, type, eps, stream)) return rc;
   return ctd_photometric_bwd_f32(es, ta, go, gi, B, C, H, W, bs, type, eps, stream);
+}
+
+// ctd_photometric_fwd_bwd_f32 plus the caller's masked-mean terms sums2 = (sum(mask * out), sum(mask)) (model/networks.py:377)
+// from the same pass: the loss kernels reduce their own tile and the last block to finish adds the partials.
+CTD_API int ctd_photometric_fwd_bwd_masked_f32(const float* es, const float* ta, const float* go, const float* mask,
+                                                  float* out, float* gi, float* sums2, int64_t B, int64_t C, int64_t H,
+                                                  int64_t W, int bs, int type, float eps, ctd_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
+  CTD_REQUIRE(sums2 && (B * H * W == 0 || (go && mask && out)), "photometric_fwd_bwd_masked: null pointer");
+  if (B * H * W == 0) {
+    CTD_CUDA(cudaMemsetAsync(sums2, 0, 2 * sizeof(float), st));
+    return CTD_OK;
+  }
+  if (fast9_ok(bs, H, W) && C >= 1 && B >= 1 && B <= 32768) {
+    if (type <= 1 && box9_tma_fwd_bwd_masked(es, ta, go, mask, out, gi, sums2, B, C, H, W, type, st))
+      return check_launch("photometric_fwd_bwd_masked(box, fused)");
+    if (type >= 2) {
+      const int vec = vec_ok(W, es, ta, go, gi) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+      if (census_bwd_launch(es, ta, go, gi, out, (int)B, C, H, W, type, eps, vec, st, mask, sums2)) {
+        count_launch();
+        return check_launch("photometric_fwd_bwd_masked(census, fused)");
+      }
+    }
+  }
+  if (int rc = ctd_photometric_fwd_bwd_f32(es, ta, go, out, gi, B, C, H, W, bs, type, eps, stream)) return rc;
+  masked_sums_launch(out, mask, B * H * W, sums2, st);
+  return check_launch("photometric_fwd_bwd_masked(separate)");
 }
 
 CTD_API int ctd_photometric_bwd_f64(const double* es, const double* ta, const double* go, double* gi,

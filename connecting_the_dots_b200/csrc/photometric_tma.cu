@@ -260,7 +260,8 @@ template <int TYPE>
 __global__ void __launch_bounds__(256, 2)
 photo_fwd_bwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_constant__ CUtensorMap map_ta,
                        const __grid_constant__ CUtensorMap map_go, float* __restrict__ out, float* __restrict__ gi, int H, int W,
-                       int tiles_x, int tiles_y, int ntiles) {
+                       int tiles_x, int tiles_y, int ntiles, const float* __restrict__ mask, double* __restrict__ partials,
+                       unsigned* __restrict__ ticket, float* __restrict__ sums2) {
   extern __shared__ unsigned char smem_raw[];
   FbSmem& S = *reinterpret_cast<FbSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   const int tid = threadIdx.x;
@@ -279,6 +280,7 @@ photo_fwd_bwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_
   };
   int t = blockIdx.x;
   if (tid == 0 && t < ntiles) fetch(t, 0);
+  double mnum = 0.0, mden = 0.0;  // optional masked-mean terms, accumulated over this CTA's tiles
   for (int it = 0; t < ntiles; ++it, t += gridDim.x) {
     const int s = it & 1;
     if (tid == 0 && t + (int)gridDim.x < ntiles) {  // prefetch the next tile into the other stage
@@ -359,11 +361,18 @@ photo_fwd_bwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_
         }
         const int64_t off = ((int64_t)c.n * H + gy + j) * W + gx;
         *reinterpret_cast<float4*>(gi + off) = r;
-        *reinterpret_cast<float4*>(out + off) = make_float4(f[j].x * INV81, f[j].y * INV81, f[j].z * INV81, f[j].w * INV81);
+        const float4 lo = make_float4(f[j].x * INV81, f[j].y * INV81, f[j].z * INV81, f[j].w * INV81);
+        *reinterpret_cast<float4*>(out + off) = lo;
+        if (mask != nullptr) {
+          const float4 m = ldg4(mask + off);
+          mnum += (double)((m.x * lo.x + m.y * lo.y) + (m.z * lo.z + m.w * lo.w));
+          mden += (double)((m.x + m.y) + (m.z + m.w));
+        }
       }
     }
     __syncthreads();
   }
+  if (mask != nullptr) finish_masked_sums(mnum, mden, partials, ticket, sums2);
 }
 
 static int sm_count() {
@@ -419,10 +428,11 @@ int box9_tma_bwd(const float* es, const float* ta, const float* go, float* gi, i
   return 1;
 }
 
-int box9_tma_fwd_bwd(const float* es, const float* ta, const float* go, float* out, float* gi, int64_t B, int64_t C,
-                     int64_t H, int64_t W, int type, cudaStream_t st) {
+int box9_tma_fwd_bwd_masked(const float* es, const float* ta, const float* go, const float* mask, float* out, float* gi,
+                            float* sums2, int64_t B, int64_t C, int64_t H, int64_t W, int type, cudaStream_t st) {
   if (g_disable_tma || g_force_generic || C != 1 || B < 1 || W % 4 || H < 9 || W < 9) return 0;
-  if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gi)) & 15) || B * cdiv(H, TT_H) * cdiv(W, TT_W) > INT32_MAX)
+  if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gi) | reinterpret_cast<uintptr_t>(mask)) & 15) ||
+      B * cdiv(H, TT_H) * cdiv(W, TT_W) > INT32_MAX)
     return 0;
   CUtensorMap m_es, m_ta, m_go;
   if (!make_plane_tensor_map(&m_es, es, B, H, W, TB_W, TB_H) || !make_plane_tensor_map(&m_ta, ta, B, H, W, TB_W, TB_H) ||
@@ -432,12 +442,32 @@ int box9_tma_fwd_bwd(const float* es, const float* ta, const float* go, float* o
   const int grid = std::min(ntiles, sm_count() * 2);
   const size_t smem = sizeof(FbSmem) + 128;
   if (!set_smem(type == 0 ? photo_fwd_bwd_box9_tma<0> : photo_fwd_bwd_box9_tma<1>, smem)) return 0;
+  double* partials = nullptr;
+  unsigned* ticket = nullptr;
+  if (mask) {  // [ticket (16 bytes) | 2 doubles per CTA]
+    char* sc = static_cast<char*>(scratch_alloc(16 + (size_t)grid * 16, st));
+    if (!sc || cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
+      cudaGetLastError();
+      scratch_free(sc, st);
+      return 0;
+    }
+    ticket = reinterpret_cast<unsigned*>(sc);
+    partials = reinterpret_cast<double*>(sc + 16);
+  }
   if (type == 0)
-    photo_fwd_bwd_box9_tma<0><<<grid, 256, smem, st>>>(m_es, m_ta, m_go, out, gi, (int)H, (int)W, tiles_x, tiles_y, ntiles);
+    photo_fwd_bwd_box9_tma<0><<<grid, 256, smem, st>>>(m_es, m_ta, m_go, out, gi, (int)H, (int)W, tiles_x, tiles_y, ntiles, mask,
+                                                       partials, ticket, sums2);
   else
-    photo_fwd_bwd_box9_tma<1><<<grid, 256, smem, st>>>(m_es, m_ta, m_go, out, gi, (int)H, (int)W, tiles_x, tiles_y, ntiles);
+    photo_fwd_bwd_box9_tma<1><<<grid, 256, smem, st>>>(m_es, m_ta, m_go, out, gi, (int)H, (int)W, tiles_x, tiles_y, ntiles, mask,
+                                                       partials, ticket, sums2);
+  scratch_free(ticket, st);
   count_launch();
   return 1;
+}
+
+int box9_tma_fwd_bwd(const float* es, const float* ta, const float* go, float* out, float* gi, int64_t B, int64_t C,
+                     int64_t H, int64_t W, int type, cudaStream_t st) {
+  return box9_tma_fwd_bwd_masked(es, ta, go, nullptr, out, gi, nullptr, B, C, H, W, type, st);
 }
 
 }  // namespace ctd

@@ -163,6 +163,27 @@ def photometric_loss_forward_backward(es, ta, grad_out, block_size, type, eps):
     return out, grad_in
 
 
+def photometric_loss_forward_backward_masked(es, ta, grad_out, mask, block_size, type, eps):
+    """photometric_loss_forward_backward plus sums = (sum(mask * loss), sum(mask)) from the same kernels
+    (ctd_photometric_fwd_bwd_masked_f32).  Returns (loss map, gradient w.r.t. es, sums float32 [2])."""
+    _photometric_args(es, ta, type)
+    _check(es.dtype == torch.float32, "photometric_loss_forward_backward_masked is float32 only")
+    _check_input_cuda(grad_out, "grad_out")
+    _check_input_cuda(mask, "mask")
+    B, C, H, W = es.shape
+    _check(grad_out.numel() == B * H * W and mask.numel() == B * H * W, "grad_out and mask have to be B x 1 x H x W")
+    _check(mask.dtype == torch.float32 and grad_out.dtype == torch.float32, "grad_out and mask have to be float32")
+    _same(es, grad_out, "es", "grad_out")
+    _same(es, mask, "es", "mask")
+    out = torch.empty((B, 1, H, W), dtype=es.dtype, device=es.device)
+    grad_in = torch.empty((B, C, H, W), dtype=es.dtype, device=es.device)
+    sums = torch.empty(2, dtype=torch.float32, device=es.device)
+    with torch.cuda.device(es.device):
+        _lib.call("ctd_photometric_fwd_bwd_masked_f32", es.data_ptr(), ta.data_ptr(), grad_out.data_ptr(), mask.data_ptr(),
+                  out.data_ptr(), grad_in.data_ptr(), sums.data_ptr(), B, C, H, W, int(block_size), int(type), float(eps), _stream(es))
+    return out, grad_in, sums
+
+
 def lcn_forward(x, radius, epsilon):
     """model/networks.py:523-533 as one kernel.  x [N,1,H,W] -> (lcn, std), both [N,1,H,W]."""
     _check_input_cuda(x, "x")

@@ -133,27 +133,27 @@ def photometric_loss_pytorch(es, ta, block_size, type="mse", eps=0.1):
 
 class WeightedPhotometricLossFunction(torch.autograd.Function):
     """`(mask * photometric_loss(es, ta)).sum() / mask.sum()` -- the way the reference's only caller consumes the
-    loss map (model/networks.py:377) -- as ONE op.  Its upstream gradient is a scalar, so grad_out = mask / sum(mask)
-    is known before the loss map exists: forward and backward of the window loss run as one fused pass
-    (ctd_photometric_fwd_bwd_f32) and autograd's backward is a scalar multiply.  SURVEY section 8(f) rank 1,
-    without the warp.  Returns (value, loss_map); mask is not differentiated (it is LCN's std in the reference)."""
+    loss map (model/networks.py:377) -- as ONE op.  Its upstream gradient is a scalar, so the backward's grad_out is
+    the mask up to that scalar and is known before the loss map exists: loss map, gradient and both sums come out of
+    one fused pass (ctd_photometric_fwd_bwd_masked_f32, a single kernel for the census modes) and autograd's backward
+    is a scalar multiply.  SURVEY section 8(f) rank 1, without the warp.  Returns (value, loss_map); mask is not
+    differentiated (it is LCN's std in the reference)."""
 
     @staticmethod
     def forward(ctx, es, ta, mask, block_size, type, eps):
         if not es.is_cuda:
             raise RuntimeError("torchext.weighted_photometric_loss: connecting_the_dots_b200 has no CPU implementation")
         mask = mask.detach().contiguous()
-        denom = mask.sum()
-        out, grad_es = ext_cuda.photometric_loss_forward_backward(es.detach(), ta.detach(), mask / denom, block_size, type, eps)
-        terms = ext_cuda.masked_sums(out, mask)
-        ctx.save_for_backward(grad_es)
+        # grad_out = mask: the gradient comes back unnormalised and is divided by sum(mask) in backward
+        out, grad_es, sums = ext_cuda.photometric_loss_forward_backward_masked(es.detach(), ta.detach(), mask, mask, block_size, type, eps)
+        ctx.save_for_backward(grad_es, sums)
         ctx.mark_non_differentiable(out)
-        return terms[0] / terms[1], out
+        return sums[0] / sums[1], out
 
     @staticmethod
     def backward(ctx, g_val, g_map):
-        (grad_es,) = ctx.saved_tensors
-        return grad_es * g_val, None, None, None, None, None
+        grad_es, sums = ctx.saved_tensors
+        return grad_es * (g_val / sums[1]), None, None, None, None, None
 
 
 def weighted_photometric_loss(es, ta, mask, block_size, type="mse", eps=0.1):

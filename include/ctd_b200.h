@@ -77,6 +77,12 @@ int ctd_photometric_fwd_bwd_f32(const float* es, const float* ta, const float* g
                                 float* grad_in, int64_t B, int64_t C, int64_t H, int64_t W, int block_size,
                                 int type, float eps, ctd_stream_t stream);
 
+/* The same plus the caller's masked-mean terms (model/networks.py:377) from the same pass:
+ * sums2[0] = sum(mask * out), sums2[1] = sum(mask), deterministic.  mask [B,1,H,W]. */
+int ctd_photometric_fwd_bwd_masked_f32(const float* es, const float* ta, const float* grad_out, const float* mask,
+                                       float* out, float* grad_in, float* sums2, int64_t B, int64_t C, int64_t H,
+                                       int64_t W, int block_size, int type, float eps, ctd_stream_t stream);
+
 /* ---- XCorrVolFunctor: ext.h:120-191, ext_cuda.cpp:73-86 (xcorrvol_cuda).  The reference has no
  * batch dimension; here in0,in1 are [B,C,H,W] and out is [B,D,H,W] (B=1 is the reference call). */
 int ctd_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,

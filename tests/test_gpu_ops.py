@@ -151,6 +151,27 @@ def test_photometric_fused_forward_backward(tx, shape, ty):
     assert_close(gi.cpu().numpy(), oracle.photometric_loss_backward(es, ta, go, 9, ty, 0.5), what="fused bwd")
 
 
+@pytest.mark.parametrize("shape", [(2, 1, 40, 72), (1, 2, 33, 50), (3, 1, 96, 160)])
+@pytest.mark.parametrize("ty", range(4))
+def test_photometric_fused_masked_sums(tx, shape, ty):
+    """ctd_photometric_fwd_bwd_masked_f32: loss map, gradient and the masked-mean terms of one pass; run twice to
+    check that the ticket counter resets and the sums are run-to-run identical."""
+    B, C, H, W = shape
+    rng = np.random.RandomState(B * 10 + ty)
+    es = rng.randn(B, C, H, W).astype(np.float32)
+    ta = (es + 0.6 * rng.randn(B, C, H, W)).astype(np.float32)
+    go = rng.randn(B, 1, H, W).astype(np.float32)
+    mask = rng.rand(B, 1, H, W).astype(np.float32)
+    ref_out = oracle.photometric_loss_forward(es, ta, 9, ty, 0.5)
+    res = [tx.ext_cuda.photometric_loss_forward_backward_masked(cu(es), cu(ta), cu(go), cu(mask), 9, ty, 0.5) for _ in range(2)]
+    out, gi, sums = res[0]
+    assert_close(out.cpu().numpy(), ref_out, what="fused fwd")
+    assert_close(gi.cpu().numpy(), oracle.photometric_loss_backward(es, ta, go, 9, ty, 0.5), what="fused bwd")
+    num, den = float((mask.astype(np.float64) * ref_out).sum()), float(mask.astype(np.float64).sum())
+    assert abs(float(sums[0]) - num) <= 1e-5 * abs(num) and abs(float(sums[1]) - den) <= 1e-5 * den
+    assert torch.equal(res[0][2], res[1][2])
+
+
 @pytest.mark.parametrize("ty", (1, 3))
 def test_weighted_photometric_loss_matches_composition(tx, ty):
     """The fused masked-mean op equals photometric_loss -> (mask*d).sum()/mask.sum() with autograd, value and gradient."""
