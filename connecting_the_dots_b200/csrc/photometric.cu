@@ -483,108 +483,39 @@ photo_fwd_census9(const float* __restrict__ es, const float* __restrict__ ta, fl
 
 // census_sad backward takes sign(h(des) - h(dta)); the fast path evaluates the difference with
 // rsqrt.approx (|error| < ~1.2e-6 on dd = 2 * difference).  A pixel whose window holds a term closer to
-// zero than SIGN_GUARD is not trusted: the tile kernel stores SIGN_MARKER (a NaN payload) instead, and
-// census_sad_bwd_fixup recomputes exactly those pixels with the reference's own IEEE operation
-// sequence (ext.h:321-330), one warp per pixel.  The sign decisions -- and therefore the gradient --
-// then match the CPU extension exactly, and the hot loop stays branch-free.
+// zero than SIGN_GUARD is not trusted: the tile pass notes it in a shared-memory list and, once the tile is
+// done, the CTA's warps recompute exactly those pixels from the SAME staged tiles with the reference's own
+// IEEE operation sequence (ext.h:321-330), one warp per pixel, lane l evaluating taps l, l+32, l+64 of the
+// 9x9 window in both roles of the pixel.  The sign decisions -- and therefore the gradient -- then match the
+// CPU extension exactly, the hot loop stays branch-free, and no second kernel, list in global memory or
+// memset is involved (about one pixel in a thousand takes this path on the bench data).
 constexpr float SIGN_GUARD = 3e-6f;
-constexpr unsigned SIGN_MARKER = 0x7fc5a5a5u;
 
-// grid-stride over pixel quads of grad_in [B*C, H, W]; marked pixels are recomputed by the whole warp:
-// lane l evaluates taps l, l+32, l+64 of the 9x9 window (both roles of the pixel), warp-reduced.
-__global__ void __launch_bounds__(256)
-census_sad_bwd_fixup(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
-                     float* __restrict__ gi, int64_t total, int C, int H, int W, float eps) {
-  const int lane = threadIdx.x & 31;
-  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
-  for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < total;
-       base += nwarps * 32) {
-    const int64_t idx = base + lane;
-    const bool marked = idx < total && __float_as_uint(gi[idx]) == SIGN_MARKER;
-    unsigned todo = __ballot_sync(0xffffffffu, marked);
-    while (todo) {
-      const int src = __ffs(todo) - 1;
-      todo &= todo - 1;
-      const int64_t i = base + src;
-      const int x = i % W, y = (i / W) % H;
-      const int64_t nc = i / ((int64_t)W * H);
-      const float* ep = es + nc * H * W;
-      const float* tp = ta + nc * H * W;
-      const float* gp = go + (nc / C) * H * W;
-      const float ei = __ldg(ep + (int64_t)y * W + x), ti = __ldg(tp + (int64_t)y * W + x), gc = __ldg(gp + (int64_t)y * W + x);
-      float acc = 0.f;
-      for (int t = lane; t < 81; t += 32) {
-        const int dy = t / 9 - R9, dx = t % 9 - R9;
-        const int qy = y + dy, qx = x + dx;
-        const int cy = clampi(qy, 0, H - 1), cx = clampi(qx, 0, W - 1);
-        const float des = ei - __ldg(ep + (int64_t)cy * W + cx), dta = ti - __ldg(tp + (int64_t)cy * W + cx);
-        // role "pixel is the tap of centre q": only real q, weighted by how many of q's offsets clamp onto i
-        float gq = 0.f;
-        if (qy == cy && qx == cx) {
-          const float mx = x == 0 ? float(R9 + 1 - dx) : (x == W - 1 ? float(R9 + 1 + dx) : 1.f);
-          const float my = y == 0 ? float(R9 + 1 - dy) : (y == H - 1 ? float(R9 + 1 + dy) : 1.f);
-          gq = __ldg(gp + (int64_t)cy * W + cx) * (mx * my);
-        }
-        const float s = __fadd_rn(__fmul_rn(des, des), eps);
-        const float q1 = __fdiv_rn(des, __fsqrt_rn(s));
-        const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
-        const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
-        // role "pixel is the centre, q the tap": des flips sign exactly, so do the quotients
-        const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
-        const float r1 = rsqrt_approx(s);
-        acc = fmaf(r1 * r1 * r1, sgn(d_tap) * gq - sgn(d_ctr) * gc, acc);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      if (lane == 0) gi[i] = acc * (0.5f * eps * INV81);
-    }
-  }
-}
-
-// the same recomputation driven by a list of pixel indices (written by the tile kernel): one warp per listed
-// pixel, so the work is balanced however the near-ties cluster (image borders, flat regions)
-__device__ __forceinline__ void census_sad_bwd_exact_pixel(const float* __restrict__ es, const float* __restrict__ ta,
-                                                           const float* __restrict__ go, float* __restrict__ gi, int64_t i,
-                                                           int C, int H, int W, float eps, int lane) {
-  const int x = i % W, y = (i / W) % H;
-  const int64_t nc = i / ((int64_t)W * H);
-  const float* ep = es + nc * H * W;
-  const float* tp = ta + nc * H * W;
-  const float* gp = go + (nc / C) * H * W;
-  const float ei = __ldg(ep + (int64_t)y * W + x), ti = __ldg(tp + (int64_t)y * W + x), gc = __ldg(gp + (int64_t)y * W + x);
+// (xl, yl): pixel inside the CTA's tile; Es/Ts are replicate-clamped halo tiles, Gs is zero outside the image
+__device__ __forceinline__ float census_sad_bwd_exact_smem(float (*Es)[CE_W], float (*Ts)[CE_W], float (*Gs)[CE_W], int xl,
+                                                           int yl, int x, int y, int H, int W, float eps, int lane) {
+  const float ei = Es[yl + R9][xl + R9], ti = Ts[yl + R9][xl + R9], gc = Gs[yl + R9][xl + R9];
   float acc = 0.f;
   for (int t = lane; t < 81; t += 32) {
     const int dy = t / 9 - R9, dx = t % 9 - R9;
-    const int qy = y + dy, qx = x + dx;
-    const int cy = clampi(qy, 0, H - 1), cx = clampi(qx, 0, W - 1);
-    const float des = ei - __ldg(ep + (int64_t)cy * W + cx), dta = ti - __ldg(tp + (int64_t)cy * W + cx);
-    float gq = 0.f;
-    if (qy == cy && qx == cx) {
-      const float mx = x == 0 ? float(R9 + 1 - dx) : (x == W - 1 ? float(R9 + 1 + dx) : 1.f);
-      const float my = y == 0 ? float(R9 + 1 - dy) : (y == H - 1 ? float(R9 + 1 + dy) : 1.f);
-      gq = __ldg(gp + (int64_t)cy * W + cx) * (mx * my);
-    }
+    const float des = ei - Es[yl + R9 + dy][xl + R9 + dx], dta = ti - Ts[yl + R9 + dy][xl + R9 + dx];
+    // role "pixel is the tap of centre q": only real q (Gs is zero elsewhere), weighted by how many of q's
+    // offsets clamp onto the pixel
+    const float mx = x == 0 ? float(R9 + 1 - dx) : (x == W - 1 ? float(R9 + 1 + dx) : 1.f);
+    const float my = y == 0 ? float(R9 + 1 - dy) : (y == H - 1 ? float(R9 + 1 + dy) : 1.f);
+    const float gq = Gs[yl + R9 + dy][xl + R9 + dx] * (mx * my);
     const float s = __fadd_rn(__fmul_rn(des, des), eps);
     const float q1 = __fdiv_rn(des, __fsqrt_rn(s));
     const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
     const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));
+    // role "pixel is the centre, q the tap": des flips sign exactly, so do the quotients
     const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));
     const float r1 = rsqrt_approx(s);
     acc = fmaf(r1 * r1 * r1, sgn(d_tap) * gq - sgn(d_ctr) * gc, acc);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) gi[i] = acc * (0.5f * eps * INV81);
-}
-
-__global__ void __launch_bounds__(256)
-census_sad_bwd_fixup_list(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
-                          float* __restrict__ gi, const unsigned* __restrict__ list, const unsigned* __restrict__ count,
-                          int C, int H, int W, float eps) {
-  const int lane = threadIdx.x & 31;
-  const unsigned nwarps = gridDim.x * (blockDim.x >> 5), n = *count;
-  for (unsigned it = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); it < n; it += nwarps)
-    census_sad_bwd_exact_pixel(es, ta, go, gi, (int64_t)list[it], C, H, W, eps, lane);
+  return acc * (0.5f * eps * INV81);
 }
 
 __device__ __forceinline__ float xor_sign(float v, float s) {  // v * sign(s) for s != 0
@@ -617,8 +548,8 @@ __device__ __forceinline__ void unpack_row(float* d, const float* srow) {  // NP
 template <int TYPE, bool BORDER, bool FUSE, int NPX>
 __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[CE_W], float (*Gs)[CE_W],
                                                 float* __restrict__ gi, int x0, int y0, int H, int W,
-                                                float eps, int vec, int tx, int ty, unsigned* __restrict__ list,
-                                                unsigned* __restrict__ count, unsigned plane_base, float (*facc)[NPX]) {
+                                                float eps, int vec, int tx, int ty, unsigned short* s_fix, unsigned* s_nfix,
+                                                float (*facc)[NPX]) {
   constexpr int RPP = 256 / (CT_W / NPX);  // tile rows per pass
 #pragma unroll 1
   for (int half = 0; half < CT_H / RPP; ++half) {
@@ -707,33 +638,11 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
 #pragma unroll
     for (int k = 0; k < NPX; ++k) {
       r[k] = acc[k] * scale;
-      if (TYPE == 3 && list == nullptr && near0[k] < SIGN_GUARD) r[k] = __uint_as_float(SIGN_MARKER);  // scan fix-up redoes it
     }
-    if (TYPE == 3 && list != nullptr) {
-      // near-tie pixels go on the fix-up list: one atomic per warp (ballot + prefix over the lanes)
-      unsigned mine = 0;
+    if (TYPE == 3) {  // near-tie pixels: noted for the exact pass that follows the tile (rare)
 #pragma unroll
-      for (int k = 0; k < NPX; ++k) mine |= (near0[k] < SIGN_GUARD && gx + k < W) ? (1u << k) : 0u;
-      const unsigned active = __activemask();
-      if (__any_sync(active, mine != 0u)) {
-        const int lane = threadIdx.x & 31;
-        // lanes that skipped this row (gy >= H) are not in `active`: build the prefix from the active lanes only
-        int prefix = 0, total = 0;
-        for (unsigned m = active; m; m &= m - 1) {
-          const int src = __ffs(m) - 1;
-          const int c = __shfl_sync(active, __popc(mine), src);
-          if (src < lane) prefix += c;
-          total += c;
-        }
-        unsigned base = 0;
-        const int leader = __ffs(active) - 1;
-        if (lane == leader) base = atomicAdd(count, (unsigned)total);
-        base = __shfl_sync(active, base, leader);
-        unsigned slot = base + (unsigned)prefix;
-#pragma unroll
-        for (int k = 0; k < NPX; ++k)
-          if (mine & (1u << k)) list[slot++] = plane_base + (unsigned)(gy * W + gx + k);
-      }
+      for (int k = 0; k < NPX; ++k)
+        if (near0[k] < SIGN_GUARD && gx + k < W) s_fix[atomicAdd(s_nfix, 1u)] = (unsigned short)(yl * CT_W + NPX * tx + k);
     }
     float* dst = gi + (int64_t)gy * W + gx;
     if (vec) {
@@ -753,11 +662,13 @@ template <int TYPE, bool FUSE, int NPX>
 __global__ void __launch_bounds__(256, NPX == 4 ? 2 : 3)
 photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
                   float* __restrict__ gi, float* __restrict__ out, int C, int H, int W, float eps, int vec,
-                  unsigned* __restrict__ list, unsigned* __restrict__ count, const float* __restrict__ mask,
-                  double* __restrict__ partials, unsigned* __restrict__ ticket, float* __restrict__ sums2) {
+                  const float* __restrict__ mask, double* __restrict__ partials, unsigned* __restrict__ ticket,
+                  float* __restrict__ sums2) {
   __shared__ __align__(16) float Es[CE_H][CE_W];
   __shared__ __align__(16) float Ts[CE_H][CE_W];
   __shared__ __align__(16) float Gs[CE_H][CE_W];
+  __shared__ unsigned short s_fix[CT_W * CT_H];  // tile-local indices of the near-tie pixels of this channel
+  __shared__ unsigned s_nfix;
   const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
   const int64_t n = blockIdx.z;
   const int tid = threadIdx.x;
@@ -769,13 +680,22 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
   load_halo_tile<false>(Gs, go + n * plane, x0, y0, H, W, vec, tid);
   for (int c = 0; c < C; ++c) {
     if (c) __syncthreads();
+    if (tid == 0) s_nfix = 0;
     load_halo_tile<true>(Es, es + (n * C + c) * plane, x0, y0, H, W, vec, tid);
     load_halo_tile<true>(Ts, ta + (n * C + c) * plane, x0, y0, H, W, vec, tid);
     __syncthreads();
     float* gic = gi + (n * C + c) * plane;
-    const unsigned pb = (unsigned)((n * C + c) * plane);
-    if (border) census_bwd_tile<TYPE, true, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb, facc);
-    else census_bwd_tile<TYPE, false, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, list, count, pb, facc);
+    if (border) census_bwd_tile<TYPE, true, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, s_fix, &s_nfix, facc);
+    else census_bwd_tile<TYPE, false, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, s_fix, &s_nfix, facc);
+    if (TYPE == 3) {  // exact pass over the near-tie pixels of this tile, straight from the staged tiles
+      __syncthreads();
+      const unsigned nfix = s_nfix;
+      for (unsigned i = tid >> 5; i < nfix; i += 8) {
+        const int li = s_fix[i], yl = li / CT_W, xl = li % CT_W;
+        const float v = census_sad_bwd_exact_smem(Es, Ts, Gs, xl, yl, x0 + xl, y0 + yl, H, W, eps, tid & 31);
+        if ((tid & 31) == 0) gic[(int64_t)(y0 + yl) * W + x0 + xl] = v;
+      }
+    }
   }
   if (FUSE) {  // the loss map: sum over channels and taps, same scaling as photo_fwd_census9
     const float scale = (TYPE == 2 ? 0.25f : 0.5f) * INV81;
@@ -864,46 +784,31 @@ static int bwd_impl(const T* es, const T* ta, const T* go, T* gi, int64_t B, int
 }
 
 // census backward (block 9) of nb images; out != nullptr: the fused forward + backward kernel;
-// mask != nullptr (fused only): also the masked-mean terms sums2 = (sum(mask * loss), sum(mask)).
-// One scratch block per call, one memset: [near-tie count | ticket | pad to 16 B][2 doubles per block][near-tie list].
-// Returns false (nothing launched) when the masked variant cannot get scratch memory.
+// mask != nullptr (fused only): also the masked-mean terms sums2 = (sum(mask * loss), sum(mask)) -- that variant
+// needs scratch for the block partials [ticket | pad to 16 B][2 doubles per block] and returns false (nothing
+// launched) when it cannot get it.
 static bool census_bwd_launch(const float* e, const float* t, const float* g, float* o, float* out, int nb, int64_t C,
                               int64_t H, int64_t W, int type, float eps, int vec, cudaStream_t st,
                               const float* mask = nullptr, float* sums2 = nullptr) {
   dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
-  const int64_t total = (int64_t)nb * C * H * W;
-  const size_t nblk = (size_t)grid.x * grid.y * grid.z;
-  const bool want_list = type == 3 && total < ((int64_t)1 << 32);
-  const size_t part_bytes = mask ? nblk * 16 : 0, list_bytes = want_list ? (size_t)total * 4 : 0;
   char* sc = nullptr;
-  if (mask || want_list) {
-    sc = static_cast<char*>(scratch_alloc(16 + part_bytes + list_bytes, st));
-    if (sc && cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
+  if (mask) {
+    sc = static_cast<char*>(scratch_alloc(16 + (size_t)grid.x * grid.y * grid.z * 16, st));
+    if (!sc || cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
       cudaGetLastError();
       scratch_free(sc, st);
-      sc = nullptr;
+      return false;
     }
-    if (!sc && mask) return false;
   }
-  unsigned* count = sc && want_list ? reinterpret_cast<unsigned*>(sc) : nullptr;
-  unsigned* ticket = sc && mask ? reinterpret_cast<unsigned*>(sc) + 1 : nullptr;
-  double* partials = sc && mask ? reinterpret_cast<double*>(sc + 16) : nullptr;
-  unsigned* list = count ? reinterpret_cast<unsigned*>(sc + 16 + part_bytes) : nullptr;
+  unsigned* ticket = reinterpret_cast<unsigned*>(sc);
+  double* partials = sc ? reinterpret_cast<double*>(sc + 16) : nullptr;
   const int iC = (int)C, iH = (int)H, iW = (int)W;
   if (type == 2) {
-    if (out) photo_bwd_census9<2, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, nullptr, nullptr, mask, partials, ticket, sums2);
-    else photo_bwd_census9<2, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    if (out) photo_bwd_census9<2, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, mask, partials, ticket, sums2);
+    else photo_bwd_census9<2, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, nullptr, nullptr, nullptr, nullptr);
   } else {
-    // census_sad near-tie pixels: listed by the tile kernel when scratch memory is available, else marked and found by a scan
-    if (out) photo_bwd_census9<3, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, list, count, mask, partials, ticket, sums2);
-    else photo_bwd_census9<3, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, list, count, nullptr, nullptr, nullptr, nullptr);
-    if (list) {
-      census_sad_bwd_fixup_list<<<148 * 4, 256, 0, st>>>(e, t, g, o, list, count, iC, iH, iW, eps);
-    } else {
-      const int fgrid = (int)std::min<int64_t>(cdiv(total, 256), 148 * 8);
-      census_sad_bwd_fixup<<<fgrid, 256, 0, st>>>(e, t, g, o, total, iC, iH, iW, eps);
-    }
-    count_launch();
+    if (out) photo_bwd_census9<3, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, mask, partials, ticket, sums2);
+    else photo_bwd_census9<3, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, nullptr, nullptr, nullptr, nullptr);
   }
   scratch_free(sc, st);
   return true;
