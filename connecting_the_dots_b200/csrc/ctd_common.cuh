@@ -20,6 +20,11 @@ void count_launch(int n = 1);
 void* scratch_alloc(size_t bytes, cudaStream_t st);
 void scratch_free(void* p, cudaStream_t st);
 
+// Ticket + block-partial workspace for kernels that end with finish_masked_sums (see ctd_core.cu); false when the
+// grid has more than MS_MAXBLK blocks (callers then take scratch memory and zero the ticket themselves).
+constexpr int MS_SLOTS = 16, MS_MAXBLK = 4096;
+bool masked_sums_slot(size_t nblocks, unsigned** ticket, double** partials);
+
 // Check the launch that was just issued (no synchronisation, like a normal async API).
 int check_launch(const char* what);
 

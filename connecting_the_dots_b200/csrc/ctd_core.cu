@@ -54,6 +54,33 @@ static cudaMemPool_t scratch_pool() {
   return pools[dev];
 }
 
+// Workspace of finish_masked_sums (ticket + block partials): static device memory in MS_SLOTS rotating slots, so the
+// masked loss calls need no allocation, memset or free around the kernel (each of those is a graph node and ~1.5 us
+// on a 30 us kernel).  A slot's ticket is zero at load time and is reset by the block that finishes the sums.  Slots
+// are handed out round-robin: up to MS_SLOTS masked calls may be in flight at once (across all streams).
+__device__ __align__(16) unsigned char g_ms_slots[MS_SLOTS][16 + MS_MAXBLK * 16];
+
+bool masked_sums_slot(size_t nblocks, unsigned** ticket, double** partials) {
+  static std::atomic<unsigned> next{0};
+  static thread_local unsigned char* base = nullptr;
+  static thread_local int base_dev = -1;
+  int dev = 0;
+  if (nblocks > MS_MAXBLK || cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (!base || base_dev != dev) {
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_ms_slots) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    base = static_cast<unsigned char*>(p);
+    base_dev = dev;
+  }
+  unsigned char* slot = base + (size_t)(next.fetch_add(1, std::memory_order_relaxed) % MS_SLOTS) * (16 + MS_MAXBLK * 16);
+  *ticket = reinterpret_cast<unsigned*>(slot);
+  *partials = reinterpret_cast<double*>(slot + 16);
+  return true;
+}
+
 void* scratch_alloc(size_t bytes, cudaStream_t st) {
   cudaMemPool_t pool = scratch_pool();
   void* p = nullptr;

@@ -792,16 +792,19 @@ static bool census_bwd_launch(const float* e, const float* t, const float* g, fl
                               const float* mask = nullptr, float* sums2 = nullptr) {
   dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
   char* sc = nullptr;
-  if (mask) {
-    sc = static_cast<char*>(scratch_alloc(16 + (size_t)grid.x * grid.y * grid.z * 16, st));
+  unsigned* ticket = nullptr;
+  double* partials = nullptr;
+  const size_t nblk = (size_t)grid.x * grid.y * grid.z;
+  if (mask && !masked_sums_slot(nblk, &ticket, &partials)) {
+    sc = static_cast<char*>(scratch_alloc(16 + nblk * 16, st));
     if (!sc || cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
       cudaGetLastError();
       scratch_free(sc, st);
       return false;
     }
+    ticket = reinterpret_cast<unsigned*>(sc);
+    partials = reinterpret_cast<double*>(sc + 16);
   }
-  unsigned* ticket = reinterpret_cast<unsigned*>(sc);
-  double* partials = sc ? reinterpret_cast<double*>(sc + 16) : nullptr;
   const int iC = (int)C, iH = (int)H, iW = (int)W;
   if (type == 2) {
     if (out) photo_bwd_census9<2, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, mask, partials, ticket, sums2);

@@ -444,23 +444,13 @@ int box9_tma_fwd_bwd_masked(const float* es, const float* ta, const float* go, c
   if (!set_smem(type == 0 ? photo_fwd_bwd_box9_tma<0> : photo_fwd_bwd_box9_tma<1>, smem)) return 0;
   double* partials = nullptr;
   unsigned* ticket = nullptr;
-  if (mask) {  // [ticket (16 bytes) | 2 doubles per CTA]
-    char* sc = static_cast<char*>(scratch_alloc(16 + (size_t)grid * 16, st));
-    if (!sc || cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
-      cudaGetLastError();
-      scratch_free(sc, st);
-      return 0;
-    }
-    ticket = reinterpret_cast<unsigned*>(sc);
-    partials = reinterpret_cast<double*>(sc + 16);
-  }
+  if (mask && !masked_sums_slot((size_t)grid, &ticket, &partials)) return 0;  // grid <= 2 * SMs always fits a slot
   if (type == 0)
     photo_fwd_bwd_box9_tma<0><<<grid, 256, smem, st>>>(m_es, m_ta, m_go, out, gi, (int)H, (int)W, tiles_x, tiles_y, ntiles, mask,
                                                        partials, ticket, sums2);
   else
     photo_fwd_bwd_box9_tma<1><<<grid, 256, smem, st>>>(m_es, m_ta, m_go, out, gi, (int)H, (int)W, tiles_x, tiles_y, ntiles, mask,
                                                        partials, ticket, sums2);
-  scratch_free(ticket, st);
   count_launch();
   return 1;
 }
