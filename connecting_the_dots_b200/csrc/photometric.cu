@@ -373,15 +373,20 @@ constexpr int CT_NH = CT_H / 16;
 #define CTD_CB_NPX 2
 #endif
 constexpr int CB_NPX = CTD_CB_NPX;  // pixels per thread and pass in the census backward
+#ifndef CTD_CB_H
+#define CTD_CB_H 16
+#endif
+constexpr int CB_H = CTD_CB_H;        // tile rows of the census backward (64 x CB_H outputs per CTA)
+constexpr int CBE_H = CB_H + 8;       // its halo tile rows
 static_assert(CT_H % 16 == 0, "census tile height");
 constexpr int CE_W = CT_W + 2 * R9;  // 72
 constexpr int CE_H = CT_H + 2 * R9;  // 40
 
 // load a (CE_H x CE_W) halo tile; REPL: replicate-clamped (es, ta), else zero padded (grad_out)
-template <bool REPL>
+template <bool REPL, int ROWS = CE_H>
 __device__ __forceinline__ void load_halo_tile(float (*S)[CE_W], const float* __restrict__ src, int x0,
                                                int y0, int H, int W, int vec, int tid) {
-  for (int ch = tid; ch < CE_H * (CE_W / 4); ch += 256) {
+  for (int ch = tid; ch < ROWS * (CE_W / 4); ch += 256) {
     const int r = ch / (CE_W / 4), k = ch % (CE_W / 4);
     int gy = y0 - R9 + r;
     const int gx = x0 - R9 + 4 * k;
@@ -552,7 +557,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
                                                 float (*facc)[NPX]) {
   constexpr int RPP = 256 / (CT_W / NPX);  // tile rows per pass
 #pragma unroll 1
-  for (int half = 0; half < CT_H / RPP; ++half) {
+  for (int half = 0; half < CB_H / RPP; ++half) {
     const int yl = ty + RPP * half;
     const int gy = y0 + yl, gx = x0 + NPX * tx;
     if (gy >= H) continue;
@@ -664,25 +669,26 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
                   float* __restrict__ gi, float* __restrict__ out, int C, int H, int W, float eps, int vec,
                   const float* __restrict__ mask, double* __restrict__ partials, unsigned* __restrict__ ticket,
                   float* __restrict__ sums2) {
-  __shared__ __align__(16) float Es[CE_H][CE_W];
-  __shared__ __align__(16) float Ts[CE_H][CE_W];
-  __shared__ __align__(16) float Gs[CE_H][CE_W];
-  __shared__ unsigned short s_fix[CT_W * CT_H];  // tile-local indices of the near-tie pixels of this channel
+  __shared__ __align__(16) float Es[CBE_H][CE_W];
+  __shared__ __align__(16) float Ts[CBE_H][CE_W];
+  __shared__ __align__(16) float Gs[CBE_H][CE_W];
+  __shared__ unsigned short s_fix[CT_W * CB_H];  // tile-local indices of the near-tie pixels of this channel
   __shared__ unsigned s_nfix;
-  const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CT_H;
+  const int x0 = blockIdx.x * CT_W, y0 = blockIdx.y * CB_H;
   const int64_t n = blockIdx.z;
   const int tid = threadIdx.x;
-  constexpr int TXN = CT_W / NPX, RPP = 256 / TXN, NP = CT_H / RPP;
+  constexpr int TXN = CT_W / NPX, RPP = 256 / TXN, NP = CB_H / RPP;
+  static_assert(CB_H % RPP == 0, "census backward tile height");
   const int tx = tid % TXN, ty = tid / TXN;
   const int64_t plane = (int64_t)H * W;
-  const bool border = x0 == 0 || y0 == 0 || x0 + CT_W >= W || y0 + CT_H >= H;
+  const bool border = x0 == 0 || y0 == 0 || x0 + CT_W >= W || y0 + CB_H >= H;
   float facc[NP][NPX] = {};
-  load_halo_tile<false>(Gs, go + n * plane, x0, y0, H, W, vec, tid);
+  load_halo_tile<false, CBE_H>(Gs, go + n * plane, x0, y0, H, W, vec, tid);
   for (int c = 0; c < C; ++c) {
     if (c) __syncthreads();
     if (tid == 0) s_nfix = 0;
-    load_halo_tile<true>(Es, es + (n * C + c) * plane, x0, y0, H, W, vec, tid);
-    load_halo_tile<true>(Ts, ta + (n * C + c) * plane, x0, y0, H, W, vec, tid);
+    load_halo_tile<true, CBE_H>(Es, es + (n * C + c) * plane, x0, y0, H, W, vec, tid);
+    load_halo_tile<true, CBE_H>(Ts, ta + (n * C + c) * plane, x0, y0, H, W, vec, tid);
     __syncthreads();
     float* gic = gi + (n * C + c) * plane;
     if (border) census_bwd_tile<TYPE, true, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, s_fix, &s_nfix, facc);
@@ -790,7 +796,7 @@ static int bwd_impl(const T* es, const T* ta, const T* go, T* gi, int64_t B, int
 static bool census_bwd_launch(const float* e, const float* t, const float* g, float* o, float* out, int nb, int64_t C,
                               int64_t H, int64_t W, int type, float eps, int vec, cudaStream_t st,
                               const float* mask = nullptr, float* sums2 = nullptr) {
-  dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CT_H), nb);
+  dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CB_H), nb);
   char* sc = nullptr;
   unsigned* ticket = nullptr;
   double* partials = nullptr;
