@@ -10,6 +10,12 @@ namespace ctd {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// 128-byte aligned start inside a dynamic shared-memory array.  The offset is derived from the shared-window address
+// and ADDED to the array pointer, so the result is still known to point to shared memory (LDS/STS, not generic LD/ST).
+__device__ __forceinline__ unsigned char* align128_shared(unsigned char* smem_raw) {
+  return smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
+}
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }

@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256, 3)
 lcn_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ lcn, float* __restrict__ sd_out, int H,
                int W, float eps, int tiles_x, int tiles_y, int ntiles) {
   extern __shared__ unsigned char smem_raw[];
-  LcnSmem& S = *reinterpret_cast<LcnSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  LcnSmem& S = *reinterpret_cast<LcnSmem*>(align128_shared(smem_raw));
   constexpr int K = 2 * R + 1;
   const float n = float(K * K);
   const int tid = threadIdx.x;

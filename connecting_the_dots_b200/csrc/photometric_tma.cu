@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(256, 3)
 photo_fwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_constant__ CUtensorMap map_ta,
                    float* __restrict__ out, int H, int W, int tiles_x, int tiles_y, int ntiles) {
   extern __shared__ unsigned char smem_raw[];
-  FwdSmem& S = *reinterpret_cast<FwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  FwdSmem& S = *reinterpret_cast<FwdSmem*>(align128_shared(smem_raw));
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&S.full[0], 1);
@@ -161,7 +161,7 @@ photo_bwd_box9_tma(const __grid_constant__ CUtensorMap map_go, const float* __re
                    const float* __restrict__ ta, float* __restrict__ gi, int H, int W, int tiles_x, int tiles_y,
                    int ntiles) {
   extern __shared__ unsigned char smem_raw[];
-  BwdSmem& S = *reinterpret_cast<BwdSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  BwdSmem& S = *reinterpret_cast<BwdSmem*>(align128_shared(smem_raw));
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&S.full[0], 1);
@@ -263,7 +263,7 @@ photo_fwd_bwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_
                        int tiles_x, int tiles_y, int ntiles, const float* __restrict__ mask, double* __restrict__ partials,
                        unsigned* __restrict__ ticket, float* __restrict__ sums2) {
   extern __shared__ unsigned char smem_raw[];
-  FbSmem& S = *reinterpret_cast<FbSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  FbSmem& S = *reinterpret_cast<FbSmem*>(align128_shared(smem_raw));
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&S.full[0], 1);
