@@ -13,13 +13,32 @@ rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
 ix = {h: i for i, h in enumerate(hdr)}
 SCALE = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-NAMES = {"lcn_tma_kernel": "lcn_fwd", "photo_fwd_box9_tma": "sad_fwd", "photo_bwd_box9_tma": "sad_bwd",
-         "photo_fwd_census9": "census_sad_fwd", "photo_bwd_census9<3, false>": "census_sad_bwd",
-         "photo_bwd_census9<3, true>": "census_sad_fwd_bwd", "masked_sums_kernel": "masked_sums"}
+import re
+
+def op_name(kernel):
+    """bench.py's op name for a kernel of the chain (None = not part of it)."""
+    k = re.sub(r"\((int|bool|unsigned int)\)", "", kernel).replace(" ", "")
+    if "lcn_tma_kernel" in k:
+        return "lcn_fwd"
+    if "photo_fwd_bwd_box9_tma" in k:
+        return "sad_fwd_bwd"
+    if "photo_fwd_box9_tma" in k:
+        return "sad_fwd"
+    if "photo_bwd_box9_tma" in k:
+        return "sad_bwd"
+    if "photo_fwd_census9" in k:
+        return "census_sad_fwd"
+    m = re.search(r"photo_bwd_census9<3,(\w+),", k)
+    if m:
+        return "census_sad_fwd_bwd" if m.group(1) in ("1", "true") else "census_sad_bwd"
+    if "masked_sums_kernel" in k:
+        return "masked_sums"
+    return None
+
 out = {}
 for r in rows[2:]:
     name = r[ix["Kernel Name"]]
-    key = next((v for k, v in NAMES.items() if k.split("<")[0] in name and (("<" not in k) or k.split("<")[1].rstrip(">") in name.replace("(int)", "").replace("(bool)", "").replace("1", "true").replace("0", "false"))), None)
+    key = op_name(name)
     if key is None or key in out:
         continue
     rd = float(r[ix["dram__bytes_read.sum"]]) * SCALE[units[ix["dram__bytes_read.sum"]]]

@@ -16,6 +16,9 @@ for rnd in range(2):
     _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], o[3].data_ptr(), B, 1, H, W, 9, 1, 0.5, st)
     _lib.call("ctd_photometric_fwd_f32", p["es"], p["ta"], o[4].data_ptr(), B, 1, H, W, 9, 3, 0.5, st)
     _lib.call("ctd_photometric_bwd_f32", p["es"], p["ta"], p["go"], o[5].data_ptr(), B, 1, H, W, 9, 3, 0.5, st)
-    _lib.call("ctd_photometric_fwd_bwd_f32", p["es"], p["ta"], p["go"], o[4].data_ptr(), o[5].data_ptr(), B, 1, H, W, 9, 3, 0.5, st)
+    _lib.call("ctd_photometric_fwd_bwd_masked_f32", p["es"], p["ta"], p["go"], p["std"], o[2].data_ptr(), o[3].data_ptr(), sums.data_ptr(),
+              B, 1, H, W, 9, 1, 0.5, st)
+    _lib.call("ctd_photometric_fwd_bwd_masked_f32", p["es"], p["ta"], p["go"], p["std"], o[4].data_ptr(), o[5].data_ptr(), sums.data_ptr(),
+              B, 1, H, W, 9, 3, 0.5, st)
     _lib.call("ctd_masked_sums_f32", o[4].data_ptr(), p["std"], B * H * W, sums.data_ptr(), ws.data_ptr(), st)
     torch.cuda.synchronize()
