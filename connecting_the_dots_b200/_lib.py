@@ -17,6 +17,8 @@ SIGNATURES = {
     "ctd_photometric_bwd_f64": [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _f32, _ptr],
     "ctd_photometric_fwd_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _f32, _ptr],
     "ctd_photometric_fwd_bwd_masked_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _f32, _ptr],
+    "ctd_warp_pattern_fwd_f32": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr],
+    "ctd_warp_pattern_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _ptr],
     "ctd_xcorrvol_f32": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int, _ptr],
     "ctd_xcorrvol_f64": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int, _ptr],
     "ctd_proj_nn_f32": [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _ptr],

@@ -184,6 +184,41 @@ def photometric_loss_forward_backward_masked(es, ta, grad_out, mask, block_size,
     return out, grad_in, sums
 
 
+def _warp_args(pattern, disp):
+    _check_input_cuda(pattern, "pattern")
+    _check_input_cuda(disp, "disp")
+    _check(pattern.dim() == 4 and pattern.size(1) == 1, "pattern has to be Bp x 1 x Hp x Wp")
+    _check(disp.dim() == 4 and disp.size(1) == 1, "disp has to be B x 1 x H x W")
+    _check(pattern.size(0) in (1, disp.size(0)), "pattern batch has to be 1 or the batch of disp")
+    _check(pattern.dtype == torch.float32 and disp.dtype == torch.float32, "warp_pattern is float32 only")
+    _same(pattern, disp, "pattern", "disp")
+
+
+def warp_pattern_forward(pattern, disp):
+    """model/networks.py:362-371: grid_sample(pattern, grid(disp), padding_mode='border') -> [B,1,H,W]."""
+    _warp_args(pattern, disp)
+    B, _, H, W = disp.shape
+    Bp, _, Hp, Wp = pattern.shape
+    out = torch.empty_like(disp)
+    with torch.cuda.device(disp.device):
+        _lib.call("ctd_warp_pattern_fwd_f32", pattern.data_ptr(), disp.data_ptr(), out.data_ptr(), B, Bp, Hp, Wp, H, W, _stream(disp))
+    return out
+
+
+def warp_pattern_backward(pattern, disp, grad_out):
+    """Gradient of warp_pattern_forward w.r.t. disp."""
+    _warp_args(pattern, disp)
+    _check_input_cuda(grad_out, "grad_out")
+    _check(grad_out.numel() == disp.numel() and grad_out.dtype == torch.float32, "grad_out has to match disp")
+    B, _, H, W = disp.shape
+    Bp, _, Hp, Wp = pattern.shape
+    gd = torch.empty_like(disp)
+    with torch.cuda.device(disp.device):
+        _lib.call("ctd_warp_pattern_bwd_f32", pattern.data_ptr(), disp.data_ptr(), grad_out.data_ptr(), gd.data_ptr(), B, Bp, Hp, Wp,
+                  H, W, _stream(disp))
+    return gd
+
+
 def lcn_forward(x, radius, epsilon):
     """model/networks.py:523-533 as one kernel.  x [N,1,H,W] -> (lcn, std), both [N,1,H,W]."""
     _check_input_cuda(x, "x")

@@ -161,6 +161,38 @@ def weighted_photometric_loss(es, ta, mask, block_size, type="mse", eps=0.1):
     return WeightedPhotometricLossFunction.apply(es, ta, mask, block_size, _loss_type_id(type), eps)
 
 
+class WarpPatternFunction(torch.autograd.Function):
+    """The disparity warp of the reference pattern (model/networks.py:362-371): one gather kernel instead of
+    building uv grids and calling grid_sample; differentiable w.r.t. disp."""
+
+    @staticmethod
+    def forward(ctx, pattern, disp):
+        if not disp.is_cuda:
+            raise RuntimeError("torchext.warp_pattern: connecting_the_dots_b200 has no CPU implementation")
+        pattern, disp = pattern.detach().contiguous(), disp.detach().contiguous()
+        ctx.save_for_backward(pattern, disp)
+        return ext_cuda.warp_pattern_forward(pattern, disp)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        pattern, disp = ctx.saved_tensors
+        return None, ext_cuda.warp_pattern_backward(pattern, disp, grad_out.contiguous())
+
+
+def warp_pattern(pattern, disp):
+    """pattern [Bp,1,Hp,Wp] sampled at (u - disp, v) with the reference's grid convention -> [B,1,H,W]."""
+    return WarpPatternFunction.apply(pattern, disp)
+
+
+def pattern_similarity_loss(disp, pattern, im, std=None, loss_type="census_sad", loss_eps=0.5, block_size=9):
+    """RectifiedPatternSimilarityLoss.tforward (model/networks.py:358-378) as three kernels: warp, fused loss
+    forward+backward+masked mean, and (in autograd's backward) the warp's gradient.  Returns (val, pattern_proj)."""
+    pattern_proj = warp_pattern(pattern, disp)
+    mask = torch.ones_like(im) if std is None else std
+    val, _ = weighted_photometric_loss(pattern_proj, im.contiguous(), mask, block_size, loss_type, loss_eps)
+    return val, pattern_proj
+
+
 class LCNFunction(torch.autograd.Function):
     """Fused local contrast normalisation (model/networks.py:507-533); forward only -- in the
     reference the gradient flows to an input image nobody reads (exp_synph.py:80-91)."""

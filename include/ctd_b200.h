@@ -83,6 +83,15 @@ int ctd_photometric_fwd_bwd_masked_f32(const float* es, const float* ta, const f
                                        float* out, float* grad_in, float* sums2, int64_t B, int64_t C, int64_t H,
                                        int64_t W, int block_size, int type, float eps, ctd_stream_t stream);
 
+/* ---- the disparity warp in front of the loss: model/networks.py:362-371 (RectifiedPatternSimilarityLoss.tforward),
+ * grid_sample(pattern, grid(disp), bilinear, padding_mode='border', align_corners=False) with the reference's (W-1)
+ * grid normalisation.  pattern [Bp,1,Hp,Wp] (Bp = 1 or B), disp [B,1,H,W] -> out [B,1,H,W]; backward: gradient
+ * w.r.t. disp (the pattern is a constant of the model). */
+int ctd_warp_pattern_fwd_f32(const float* pattern, const float* disp, float* out, int64_t B, int64_t Bp, int64_t Hp,
+                             int64_t Wp, int64_t H, int64_t W, ctd_stream_t stream);
+int ctd_warp_pattern_bwd_f32(const float* pattern, const float* disp, const float* grad_out, float* grad_disp,
+                             int64_t B, int64_t Bp, int64_t Hp, int64_t Wp, int64_t H, int64_t W, ctd_stream_t stream);
+
 /* ---- XCorrVolFunctor: ext.h:120-191, ext_cuda.cpp:73-86 (xcorrvol_cuda).  The reference has no
  * batch dimension; here in0,in1 are [B,C,H,W] and out is [B,D,H,W] (B=1 is the reference call). */
 int ctd_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,

@@ -183,7 +183,7 @@ def test_weighted_photometric_loss_matches_composition(tx, ty):
     (gref,) = torch.autograd.grad(3.0 * ref, es)
     val, loss_map = tx.weighted_photometric_loss(es, ta, mask, 9, TYPES[ty], 0.5)
     (g,) = torch.autograd.grad(3.0 * val, es)
-    assert abs(float(val) - float(ref)) <= 1e-5 * abs(float(ref))
+    assert abs(val.item() - ref.item()) <= 1e-5 * abs(ref.item())
     assert_close(g.cpu().numpy(), gref.cpu().numpy(), what="weighted loss gradient")
     assert_close(loss_map.cpu().numpy(), oracle.photometric_loss_forward(d["es"], d["ta"], 9, ty, 0.5), what="loss map")
 
@@ -587,3 +587,55 @@ def test_host_api_deferred_batch_matches_synchronous_calls(tx):
     assert_close(res[1][4], oracle.photometric_loss_forward(d["es"], d["ta"], 9, 3, 0.5), what="deferred census fwd")
     with pytest.raises(Exception):
         _lib.call("ctd_host_end_batch")  # no batch open
+
+
+# ---------------------------------------------------------------- warp + fused loss
+def _reference_pattern_loss(disp, pattern, im, std, loss_type, eps, tx):
+    """model/networks.py:358-378 with torch ops (grid_sample on the GPU) and the drop-in photometric_loss."""
+    B, _, H, W = disp.shape
+    v, u = torch.meshgrid(torch.arange(H, device=disp.device, dtype=torch.float32),
+                          torch.arange(W, device=disp.device, dtype=torch.float32), indexing="ij")
+    uv1 = torch.empty(B, H * W, 2, device=disp.device)
+    uv1[..., 0] = u.reshape(1, -1) - disp.contiguous().view(B, -1)
+    uv1[..., 1] = v.reshape(1, -1)
+    uv1[..., 0] = 2 * (uv1[..., 0] / (W - 1) - 0.5)
+    uv1[..., 1] = 2 * (uv1[..., 1] / (H - 1) - 0.5)
+    uv1 = uv1.view(-1, H, W, 2).clone()
+    pat = pattern.expand(B, *pattern.shape[1:])
+    proj = torch.nn.functional.grid_sample(pat, uv1, padding_mode="border", align_corners=False)
+    diff = tx.photometric_loss(proj.contiguous(), im.contiguous(), 9, loss_type, eps)
+    return (std * diff).sum() / std.sum(), proj
+
+
+@pytest.mark.parametrize("shape", [(2, 96, 160, 96, 160), (1, 60, 80, 120, 160), (3, 33, 50, 33, 50)])
+def test_warp_pattern_matches_grid_sample(tx, shape):
+    """warp_pattern against torch's CUDA grid_sample fed the reference's grid, values and d/d disp."""
+    B, H, W, Hp, Wp = shape
+    g = torch.Generator(device="cpu").manual_seed(H)
+    pattern = torch.randn(1, 1, Hp, Wp, generator=g).to(DEV)
+    disp = (torch.rand(B, 1, H, W, generator=g) * (W * 0.4) - 4).to(DEV).requires_grad_(True)   # some samples leave the image
+    go = torch.randn(B, 1, H, W, generator=g).to(DEV)
+    ones = torch.ones(B, 1, H, W, device=DEV)
+    _, proj_ref = _reference_pattern_loss(disp, pattern, ones, ones, "sad", 0.5, tx)
+    (gref,) = torch.autograd.grad(proj_ref, disp, go)
+    proj = tx.warp_pattern(pattern, disp)
+    (g_,) = torch.autograd.grad(proj, disp, go)
+    assert_close(proj.detach().cpu().numpy(), proj_ref.detach().cpu().numpy(), what="warp forward")
+    assert_close(g_.cpu().numpy(), gref.cpu().numpy(), what="warp backward")
+
+
+@pytest.mark.parametrize("loss_type", ("census_sad", "sad"))
+def test_pattern_similarity_loss_matches_reference_recipe(tx, loss_type):
+    """The whole RectifiedPatternSimilarityLoss.tforward: value, pattern_proj and the gradient w.r.t. the disparity."""
+    from connecting_the_dots_b200 import synth
+    d = synth.make_batch(2, 96, 160)
+    pattern = cu(d["pat_lcn"][:1])
+    im, std = cu(d["ta"]), cu(d["std"])
+    disp = cu(d["disp"] if d["disp"].ndim == 4 else d["disp"][:, None]).clone().requires_grad_(True)
+    ref, proj_ref = _reference_pattern_loss(disp, pattern, im, std, loss_type, 0.5, tx)
+    (gref,) = torch.autograd.grad(ref, disp)
+    val, proj = tx.pattern_similarity_loss(disp, pattern, im, std, loss_type, 0.5)
+    (g_,) = torch.autograd.grad(val, disp)
+    assert abs(val.item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert_close(proj.detach().cpu().numpy(), proj_ref.detach().cpu().numpy(), what="pattern_proj")
+    assert_close(g_.cpu().numpy(), gref.cpu().numpy(), what="d loss / d disp")

@@ -57,7 +57,7 @@ def timeit(fn, iters, warmup=5, nrep=NREP):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--only", default="calib,photometric,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
+    ap.add_argument("--only", default="calib,photometric,warp,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -79,7 +79,7 @@ def main():
     base = synth.make_batch(B, H, W)
     sets = []
     for s in range(NS):
-        d = {k: torch.from_numpy(np.ascontiguousarray(np.roll(base[k], 5 * s, axis=2))).to(dev) for k in ("im", "es", "ta", "go", "std", "pat_lcn")}
+        d = {k: torch.from_numpy(np.ascontiguousarray(np.roll(base[k], 5 * s, axis=2))).to(dev) for k in ("im", "es", "ta", "go", "std", "pat_lcn", "disp")}
         d["o1"] = torch.empty(B, 1, H, W, device=dev)
         d["o2"] = torch.empty(B, 1, H, W, device=dev)
         sets.append(d)
@@ -105,6 +105,29 @@ def main():
                 _lib.call("ctd_photometric_bwd_f32", d["es"].data_ptr(), d["ta"].data_ptr(), d["go"].data_ptr(), d["o2"].data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
             add(name + "_fwd", *timeit(f, args.iters), 12 * npx)
             add(name + "_bwd", *timeit(g, args.iters), 16 * npx)
+    if "warp" in only:
+        # the disparity warp in front of the loss, and the whole RectifiedPatternSimilarityLoss step
+        # (warp -> fused census_sad loss forward+backward+masked mean -> warp backward)
+        pat = torch.from_numpy(np.ascontiguousarray(base["pat_lcn"][:1])).to(dev)
+        disps = [torch.from_numpy(np.ascontiguousarray(np.roll(base["disp"], 5 * s, axis=2))).to(dev) for s in range(NS)]
+        sums = torch.zeros(2, device=dev)
+        def f(i, st):
+            d = sets[i % NS]
+            _lib.call("ctd_warp_pattern_fwd_f32", pat.data_ptr(), disps[i % NS].data_ptr(), d["o1"].data_ptr(), B, 1, H, W, H, W, st)
+        add("warp_fwd", *timeit(f, args.iters), 8 * npx)
+        def f(i, st):
+            d = sets[i % NS]
+            _lib.call("ctd_warp_pattern_bwd_f32", pat.data_ptr(), disps[i % NS].data_ptr(), d["go"].data_ptr(), d["o2"].data_ptr(), B, 1, H, W, H, W, st)
+        add("warp_bwd", *timeit(f, args.iters), 12 * npx)
+        gis = [torch.empty(B, 1, H, W, device=dev) for _ in range(NS)]
+        def f(i, st):
+            d = sets[i % NS]
+            _lib.call("ctd_warp_pattern_fwd_f32", pat.data_ptr(), disps[i % NS].data_ptr(), d["o1"].data_ptr(), B, 1, H, W, H, W, st)
+            _lib.call("ctd_photometric_fwd_bwd_masked_f32", d["o1"].data_ptr(), d["ta"].data_ptr(), d["std"].data_ptr(), d["std"].data_ptr(),
+                      d["o2"].data_ptr(), gis[i % NS].data_ptr(), sums.data_ptr(), B, 1, H, W, 9, 3, 0.5, st)
+            _lib.call("ctd_warp_pattern_bwd_f32", pat.data_ptr(), disps[i % NS].data_ptr(), gis[i % NS].data_ptr(), d["o2"].data_ptr(), B, 1, H, W, H, W, st)
+        add("pattern_similarity_loss_step", *timeit(f, args.iters), (8 + 24 + 12) * npx,
+            extra={"note": "RectifiedPatternSimilarityLoss.tforward + backward to the disparity: warp, fused census_sad loss, warp gradient"})
     if "lcn" in only:
         def f(i, st):
             d = sets[i % NS]
