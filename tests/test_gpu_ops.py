@@ -639,3 +639,31 @@ def test_pattern_similarity_loss_matches_reference_recipe(tx, loss_type):
     assert abs(val.item() - ref.item()) <= 1e-5 * abs(ref.item())
     assert_close(proj.detach().cpu().numpy(), proj_ref.detach().cpu().numpy(), what="pattern_proj")
     assert_close(g_.cpu().numpy(), gref.cpu().numpy(), what="d loss / d disp")
+
+
+def test_loss_path_is_cuda_graph_capturable(tx):
+    """Every call of the loss path (LCN, warp, fused masked loss, warp gradient) can be captured into one CUDA graph
+    (scratch comes from a stream-ordered pool / static slots, nothing synchronises); a replay reproduces the eager
+    results bit for bit."""
+    from connecting_the_dots_b200 import synth
+    d = synth.make_batch(2, 96, 160)
+    pattern = cu(d["pat_lcn"][:1])
+    im_raw, disp = cu(d["im"]), cu(d["disp"])
+
+    def run():
+        lcn, std = tx.ext_cuda.lcn_forward(im_raw, 5, 0.05)
+        proj = tx.ext_cuda.warp_pattern_forward(pattern, disp)
+        out, gi, sums = tx.ext_cuda.photometric_loss_forward_backward_masked(proj, lcn, std, std, 9, 3, 0.5)
+        gd = tx.ext_cuda.warp_pattern_backward(pattern, disp, gi)
+        return lcn, proj, out, gi, sums, gd
+
+    eager = [t.clone() for t in run()]
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        captured = run()
+    for _ in range(2):
+        g.replay()
+    torch.cuda.synchronize()
+    for a, b in zip(eager, captured):
+        assert torch.equal(a, b)

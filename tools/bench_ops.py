@@ -57,7 +57,7 @@ def timeit(fn, iters, warmup=5, nrep=NREP):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--only", default="calib,photometric,warp,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
+    ap.add_argument("--only", default="calib,photometric,warp,pyramid,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -128,6 +128,41 @@ def main():
             _lib.call("ctd_warp_pattern_bwd_f32", pat.data_ptr(), disps[i % NS].data_ptr(), gis[i % NS].data_ptr(), d["o2"].data_ptr(), B, 1, H, W, H, W, st)
         add("pattern_similarity_loss_step", *timeit(f, args.iters), (8 + 24 + 12) * npx,
             extra={"note": "RectifiedPatternSimilarityLoss.tforward + backward to the disparity: warp, fused census_sad loss, warp gradient"})
+    if "pyramid" in only:
+        # the loss at the model's four pyramid levels (exp_synph.py:25-27,107-111) -- 4 x (warp, fused
+        # census_sad loss, warp gradient) = 12 kernels.  Every entry point is capture-safe, so the whole pyramid is ONE
+        # CUDA graph replay; the same 12 calls issued from Python on a stream are reported next to it.
+        levels = []
+        for s_ in range(4):
+            h_, w_ = H >> s_, W >> s_
+            dd = synth.make_batch(min(B, 8), h_, w_)
+            t_ = {k: torch.from_numpy(np.ascontiguousarray(np.concatenate([dd[k]] * ((B + 7) // 8))[:B])).to(dev) for k in ("ta", "std", "disp", "pat_lcn")}
+            t_["pat"] = t_["pat_lcn"][:1].contiguous()
+            for k in ("proj", "loss", "gi", "gd"):
+                t_[k] = torch.empty(B, 1, h_, w_, device=dev)
+            t_["sums"] = torch.zeros(2, device=dev)
+            levels.append((h_, w_, t_))
+        def chain(st):
+            for h_, w_, t_ in levels:
+                _lib.call("ctd_warp_pattern_fwd_f32", t_["pat"].data_ptr(), t_["disp"].data_ptr(), t_["proj"].data_ptr(), B, 1, h_, w_, h_, w_, st)
+                _lib.call("ctd_photometric_fwd_bwd_masked_f32", t_["proj"].data_ptr(), t_["ta"].data_ptr(), t_["std"].data_ptr(), t_["std"].data_ptr(),
+                          t_["loss"].data_ptr(), t_["gi"].data_ptr(), t_["sums"].data_ptr(), B, 1, h_, w_, 9, 3, 0.5, st)
+                _lib.call("ctd_warp_pattern_bwd_f32", t_["pat"].data_ptr(), t_["disp"].data_ptr(), t_["gi"].data_ptr(), t_["gd"].data_ptr(), B, 1, h_, w_, h_, w_, st)
+        px_all = sum(B * h_ * w_ for h_, w_, _ in levels)
+        add("pyramid_4_levels_graph", *timeit(lambda i, st: chain(st), args.iters, nrep=1), 44 * px_all, px=px_all,
+            extra={"note": "one CUDA graph replay = 12 kernels (4 levels x warp, fused census_sad loss, warp gradient)"})
+        cur = torch.cuda.current_stream().cuda_stream
+        for _ in range(5):
+            chain(cur)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.iters):
+            chain(cur)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        add("pyramid_4_levels_stream_launches", ms, ms, 44 * px_all, px=px_all, extra={"note": "the same 12 calls issued one by one from Python"})
     if "lcn" in only:
         def f(i, st):
             d = sets[i % NS]
