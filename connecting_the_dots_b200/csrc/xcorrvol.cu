@@ -5,6 +5,7 @@
 // of in1 at (h, w-d); rows replicate-clamped, in0 columns clamped, in1 columns clamped AFTER the
 // disparity shift.  The reference has no batch dimension; here B images are one launch.
 #include <algorithm>
+#include <type_traits>
 
 #include "ctd_common.cuh"
 #include "ctd_tma.cuh"
@@ -193,7 +194,8 @@ xcorrvol_direct(const float* __restrict__ in0, const float* __restrict__ in1, fl
 // only by the fix-up pass).  The fast path's error is about 1.5e-7 * sqrt(S2_0 S2_1) / (sd0 sd1) =
 // 1.5e-7 * 2^((L0+L1)/8); outputs with L0 + L1 >= XS_LSUM (sd0 sd1 < 2^-4.5 sqrt(S2_0 S2_1), a few per
 // thousand on LCN'd images) are recomputed by xcorr_fixup_kernel: it walks the listed windows
-// (L >= XS_LLIST), compacts the affected outputs and evaluates them in fp64 -- or, for flat windows
+// (L >= XS_LLIST), compacts the affected outputs and evaluates them in the centred form, one fp32 pass with the
+// window means of the statistics pass (xcorr_centred_one) -- or, for flat windows
 // (var < 1e-6 sum v^2), where the reference's result is its own rounding noise, with the reference's
 // centred two-pass fp32 arithmetic (ext.h:133-190).
 // ------------------------------------------------------------------------------------------
@@ -206,12 +208,12 @@ constexpr int XS_TD = CTD_XS_TD;      // disparities per thread (4: 4 warps per 
 constexpr int XS_AW = XS_W + 8;       // in0 tile: image columns x0-4 .. x0+131
 constexpr int XS_BW = XS_W + 8 + 16;  // in1 tile: image columns x0-20-d0 .. x0+131-d0 (clamped)
 constexpr int ST_W = 128, ST_H = 16;  // statistics tile
-constexpr int XS_LSUM = 36;           // L0 + L1 >= 36 <=> (sd0 sd1)^2 <= 2^-9 S2_0 S2_1: recompute in fp64
+constexpr int XS_LSUM = 36;           // L0 + L1 >= 36 <=> (sd0 sd1)^2 <= 2^-9 S2_0 S2_1: recompute centred
 constexpr int XS_LLIST = 18;          // max(L0, L1) >= 18 whenever L0 + L1 >= 36
-constexpr float XS_FLAT = 1e-6f;      // var < 1e-6 * sum v^2: flat window, reference arithmetic
+constexpr int XS_LEXACT = 76;         // var < 2^-19 sum v^2 (~2e-6): flat window, reference arithmetic
 template <int TD>
 struct XsNst {  // statistics rows in flight per warp (more warps per CTA -> shallower rings, same shared memory)
-  static constexpr int value = TD == 4 ? 4 : 2;
+  static constexpr int value = TD == 4 ? 3 : 2;
 };
 template <int NST>
 struct alignas(16) XsStatRing {
@@ -259,33 +261,28 @@ __device__ __forceinline__ float xcorr_exact_one(const float* __restrict__ p0, c
   return dot / (float)((double)sqrtf(s0 * s1) + 1e-8);
 }
 
-// the same output in fp64 (expanded sums are harmless at 53 bits): agrees with the reference to its own
-// rounding error wherever the windows are not flat; flat windows are handed to xcorr_exact_one
+// One output from the centred form with the window means and deviations the statistics pass already holds
+// (fp64 box sums, rounded once): dot = sum (a - mu0)(b - mu1) in one fp32 pass.  a - mu is exact where it matters
+// (Sterbenz), the rounding of the stored means enters only as N d0 d1, and the accumulation error is bounded by
+// ~81 eps sd0 sd1 -- about 1e-6 of the normaliser however large the window means are.  Flat windows
+// (grade >= XS_LEXACT), where the reference's result is its own rounding noise, go to xcorr_exact_one.
 template <int BS>
-__device__ __forceinline__ float xcorr_fp64_one(const float* __restrict__ p0, const float* __restrict__ p1, int H, int W,
-                                                int h, int w, int d) {
+__device__ __forceinline__ float xcorr_centred_one(const float* __restrict__ p0, const float* __restrict__ p1, int H, int W,
+                                                   int h, int w, int d, float mu0, float mu1, float sd0, float sd1) {
   constexpr int R = BS / 2;
-  double sa = 0.0, sb = 0.0, saa = 0.0, sbb = 0.0, sab = 0.0;
+  float dot[3] = {0.f, 0.f, 0.f};  // three rows in flight
 #pragma unroll
   for (int bh = 0; bh < BS; ++bh) {
     const int64_t row = (int64_t)clampi(h + bh - R, 0, H - 1) * W;
 #pragma unroll
     for (int bw = 0; bw < BS; ++bw) {
       const int w0 = w + bw - R;
-      const double a = (double)__ldg(p0 + row + clampi(w0, 0, W - 1));
-      const double b = (double)__ldg(p1 + row + clampi(w0 - d, 0, W - 1));
-      sa += a;
-      sb += b;
-      saa = fma(a, a, saa);
-      sbb = fma(b, b, sbb);
-      sab = fma(a, b, sab);
+      const float a = __ldg(p0 + row + clampi(w0, 0, W - 1));
+      const float b = __ldg(p1 + row + clampi(w0 - d, 0, W - 1));
+      dot[bh % 3] = fmaf(a - mu0, b - mu1, dot[bh % 3]);
     }
   }
-  const double inv_n = 1.0 / double(BS * BS);
-  const double dot = sab - sa * sb * inv_n;
-  const double v0 = fmax(saa - sa * sa * inv_n, 0.0), v1 = fmax(sbb - sb * sb * inv_n, 0.0);
-  if (v0 < (double)XS_FLAT * saa || v1 < (double)XS_FLAT * sbb) return xcorr_exact_one<BS>(p0, p1, H, W, h, w, d);
-  return (float)(dot / (sqrt(v0 * v1) + 1e-8));
+  return ((dot[0] + dot[1]) + dot[2]) / (sd0 * sd1 + 1e-8f);
 }
 
 // Window statistics of one image over positions i = u + uoff, u = column of the window centre (may be
@@ -389,11 +386,11 @@ __device__ __forceinline__ void xs_hsum(const float* p, float* o) {
 // TD = disparities per thread.  TD = 4: 128 threads, 246 registers (suffix sums of 16 outputs), 8 warps/SM.
 // TD = 2: 256 threads, half the suffix registers, 16 warps/SM -- the tile and the arithmetic per output are the
 // same, the resident warps double (the kernel is latency-bound), the in1 row is read as seven 64-bit loads.
-template <int BS, int TD>
+template <int BS, int TD, bool VEC>
 __global__ void __launch_bounds__(512 / TD, 2)
 xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
                  const float2* __restrict__ st0, const float2* __restrict__ st1, int H, int W, int D, int ws0, int ws1,
-                 int uoff, int ndchunks, int vec) {
+                 int uoff, int ndchunks) {
   constexpr int R = BS / 2, TH = XsCfg<BS>::TH, XH = XsCfg<BS>::XH, NBLK = XsCfg<BS>::NBLK;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float(*At)[XS_AW] = reinterpret_cast<float(*)[XS_AW]>(smem_raw);
@@ -411,7 +408,7 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   // independent loads in flight per thread
   auto fetch4 = [&](const float* img, int r, int gx) -> float4 {
     const float* row = img + (int64_t)clampi(y0 - R + r, 0, H - 1) * W;
-    if (vec && gx >= 0 && gx + 3 < W) return ldg4(row + gx);
+    if (VEC && gx >= 0 && gx + 3 < W) return ldg4(row + gx);
     return make_float4(__ldg(row + clampi(gx, 0, W - 1)), __ldg(row + clampi(gx + 1, 0, W - 1)),
                        __ldg(row + clampi(gx + 2, 0, W - 1)), __ldg(row + clampi(gx + 3, 0, W - 1)));
   };
@@ -463,37 +460,58 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   constexpr int BOFF = TD == 4 ? 4 : 2;
   const float* arow = &At[0][4 * lane];
   const float* brow = &Bt[0][4 * lane + 16 - BOFF - TD * g];
-  float* outp = out + (((int64_t)b * D + dbase) * H) * W + x;
+  // store pointer of the row being emitted (tile row r -> output row y0 + r - 2R), advanced by W per row: no
+  // 64-bit index arithmetic inside the loop
+  float* orow = out + (((int64_t)b * D + dbase) * H + (y0 - 2 * R)) * W + x;
   const int64_t dstride = (int64_t)H * W;
+  const int ndl = min(TD, D - dbase);  // disparities of this warp that exist
+  const bool xin = VEC ? x < W : true;
   // Window statistics of the output rows stream through a per-warp shared-memory ring: one lane fetches a
   // row's w-side {N*mu0, sd0} (128 positions) and u-side {mu1, sd1} (136 positions u = x0-dbase-4 ..) with two
   // cp.async.bulk copies, NST rows ahead, completion on an mbarrier -- no registers are held across the
-  // arithmetic and the L2 round trip is off the critical path.
+  // arithmetic and the L2 round trip is off the critical path.  Rows are fetched in order, so the source
+  // pointers just advance; with NST | BS the stage of a row is a compile-time constant of the unrolled loop.
   Ring& ring = rings[g];
-  const float2* wsrc = st0 + ((int64_t)b * H) * ws0 + x0;
-  const float2* usrc = st1 + ((int64_t)b * H) * ws1 + (x0 - dbase - 4 + uoff);
+  const uint32_t ring_w = smem_u32(&ring.w[0][0]), ring_u = smem_u32(&ring.u[0][0]), ring_bar = smem_u32(&ring.full[0]);
+  const char* wnext = reinterpret_cast<const char*>(st0 + ((int64_t)b * H + y0) * ws0 + x0);
+  const char* unext = reinterpret_cast<const char*>(st1 + ((int64_t)b * H + y0) * ws1 + (x0 - dbase - 4 + uoff));
+  const int64_t wstep = (int64_t)ws0 * 8, ustep = (int64_t)ws1 * 8;
   const uint32_t wbytes = (uint32_t)min(XS_W, ws0 - x0) * 8u;
   const uint32_t ubytes = (uint32_t)min(XS_W + 8, ws1 - (x0 - dbase - 4 + uoff)) * 8u;
   const int nrows = min(XH, H - y0);  // output rows of this tile
-  auto issue = [&](int e) {           // lane 0: fetch the statistics of output row y0 + e into stage e % NST
-    const int st = e % NST;
-    fence_proxy_async();
-    mbar_expect_tx(&ring.full[st], wbytes + ubytes);
-    bulk_load(&ring.w[st][0], wsrc + (int64_t)(y0 + e) * ws0, wbytes, &ring.full[st]);
-    bulk_load(&ring.u[st][0], usrc + (int64_t)(y0 + e) * ws1, ubytes, &ring.full[st]);
+  int nissued = 0;                    // lane 0: rows handed to the copy engine so far
+  auto issue = [&](int st) {          // lane 0: fetch the statistics of the next output row into stage st
+    const uint32_t bar = ring_bar + 8u * st;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(wbytes + ubytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ring_w + (uint32_t)(sizeof(float2) * XS_W) * st), "l"(wnext), "r"(wbytes), "r"(bar) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(ring_u + (uint32_t)(sizeof(float2) * (XS_W + 8)) * st), "l"(unext), "r"(ubytes), "r"(bar) : "memory");
+    wnext += wstep;
+    unext += ustep;
+    ++nissued;
   };
   if (lane == 0) {
 #pragma unroll
     for (int st = 0; st < NST; ++st) mbar_init(&ring.full[st], 1);
     fence_barrier_init();
-    for (int e = 0; e < NST && e < nrows; ++e) issue(e);
+#pragma unroll
+    for (int e = 0; e < NST; ++e)
+      if (e < nrows) issue(e);
   }
   __syncwarp();
-#pragma unroll 1
-  for (int blk = 0; blk < NBLK; ++blk) {
+  // One block of BS tile rows.  FIRST: the tile's first block only fills the vertical state (its last row
+  // completes the first window); afterwards every row emits one output row.  Returns true when the tile's
+  // last output row has been written.
+  auto do_block = [&](auto first_tag, const int blk) -> bool {
+    constexpr bool FIRST = decltype(first_tag)::value;
 #pragma unroll
     for (int j = 0; j < BS; ++j) {
       const int r = blk * BS + j;
+      const bool emit = !FIRST || j == BS - 1;  // compile-time after unrolling
+      const int e = r - 2 * R;                  // output row of the tile completed by tile row r
+      if (emit && e >= nrows) return true;      // warp-uniform
       float a[12], bv[16];
       {
         const float4* ap = reinterpret_cast<const float4*>(arow + r * XS_AW);
@@ -518,11 +536,10 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
           }
         }
       }
-      const int yo = y0 + r - 2 * R;                       // the window ending at tile row r
-      const bool emit = (blk > 0 || j == BS - 1) && yo < H;  // warp-uniform
+      // stage of this row's statistics: static when NST divides BS
+      const int st = (BS % NST == 0) ? (j + NST * BS - 2 * R) % NST : e % NST;
       float2 wst[4], ust[8];
       if (emit) {  // conflict-free 128-bit reads of this row's statistics, once per row
-        const int e = r - 2 * R, st = e % NST;
         mbar_wait(&ring.full[st], (uint32_t)(e / NST) & 1u);
         const float4* wp = reinterpret_cast<const float4*>(&ring.w[st][4 * lane]);
         const float4* up = reinterpret_cast<const float4*>(&ring.u[st][4 * lane]);
@@ -542,19 +559,18 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
         xs_hsum<BS>(p, hs);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          F[dl][k] += hs[k];
+          F[dl][k] = j == 0 ? hs[k] : F[dl][k] + hs[k];  // a block starts with its first row (no 0 + x)
           S[k] = j == BS - 1 ? F[dl][k] : suf[j < BS - 1 ? j : 0][dl][k] + F[dl][k];  // suf[j] = rows j+1.. of the previous block
           if (j > 0) suf[j - 1][dl][k] = hs[k];
         }
-        if (j == BS - 1) {  // the block is complete: rows -> suffix sums, restart F
+        if (j == BS - 1) {  // the block is complete: rows -> suffix sums
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
 #pragma unroll
             for (int i = BS - 3; i >= 0; --i) suf[i][dl][k] += suf[i + 1][dl][k];
-            F[dl][k] = 0.f;
           }
         }
-        if (emit && dbase + dl < D) {
+        if (emit) {
           // lane's four columns: {N*mu0, sd0} pairs; its eight u positions (x - dbase - 4 ..): {mu1, sd1} pairs, of
           // which disparity dbase + dl uses positions 4 + k - dl
           float v[4];
@@ -563,24 +579,28 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
             const float2 ws_ = wst[k], us_ = ust[4 + k - dl];
             v[k] = fmaf(-ws_.x, us_.x, S[k]) * rcp_approx(fmaf(ws_.y, us_.y, 1e-8f));  // untrusted outputs: see fix-up
           }
-          float* dst = outp + dl * dstride + (int64_t)yo * W;
-          if (x >= W) {
-          } else if (vec) {
-            __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+          float* dst = orow + dl * dstride;
+          if (VEC) {
+            if (xin && dl < ndl) __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
           } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              if (x + k < W) dst[k] = v[k];
+              if (x + k < W && dl < ndl) dst[k] = v[k];
           }
         }
       }
       if (emit) {  // every lane has read this stage: hand it to the row NST further down
         __syncwarp();
-        const int e = r - 2 * R;
-        if (lane == 0 && e + NST < nrows) issue(e + NST);
+        if (lane == 0 && nissued < nrows) issue(st);
       }
+      orow += W;
     }
-  }
+    return false;
+  };
+  if (do_block(std::true_type{}, 0)) return;
+#pragma unroll 1
+  for (int blk = 1; blk < NBLK; ++blk)
+    if (do_block(std::false_type{}, blk)) return;
 }
 
 // One warp per (listed window, 32 disparities): lane l looks at output d = 32*chunk + l.  side 0: window
@@ -591,8 +611,9 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
 template <int BS>
 __global__ void __launch_bounds__(256)
 xcorr_fixup_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
-                   const uint8_t* __restrict__ g0, const uint8_t* __restrict__ g1, const unsigned* __restrict__ list,
-                   const unsigned* __restrict__ count, int H, int W, int D, int ws0, int ws1, int uoff) {
+                   const float2* __restrict__ st0, const float2* __restrict__ st1, const uint8_t* __restrict__ g0,
+                   const uint8_t* __restrict__ g1, const unsigned* __restrict__ list, const unsigned* __restrict__ count, int H,
+                   int W, int D, int ws0, int ws1, int uoff) {
   __shared__ unsigned long long queue[8][64];  // (b*D + d) << 32 | (h*W + w)
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
@@ -607,7 +628,16 @@ xcorr_fixup_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
       const int w = (int)(hw % (unsigned)W), h = (int)(hw / (unsigned)W);
       const int d = (int)(bd % (unsigned)D);
       const int64_t b = bd / (unsigned)D;
-      out[(int64_t)bd * plane + hw] = xcorr_fp64_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d);
+      const int64_t i0 = (b * H + h) * ws0 + w, i1 = (b * H + h) * ws1 + (w - d + uoff);
+      float v;
+      if (g0[i0] >= XS_LEXACT || g1[i1] >= XS_LEXACT) {
+        v = xcorr_exact_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d);
+      } else {
+        const float2 s0 = __ldg(st0 + i0), s1 = __ldg(st1 + i1);  // {N mu0, sd0}, {mu1, sd1}
+        v = xcorr_centred_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d, s0.x * (1.0f / float(BS * BS)), s1.x,
+                                  s0.y, s1.y);
+      }
+      out[(int64_t)bd * plane + hw] = v;
     }
     __syncwarp();
   };
@@ -670,7 +700,8 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
   const size_t smem = sizeof(float) * TH * (XS_AW + XS_BW) + (16 / TD) * sizeof(XsStatRing<XsNst<TD>::value>);
   static const bool attr_ok =
       cudaFuncSetAttribute(xcorr_stats_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem) == cudaSuccess &&
-      cudaFuncSetAttribute(xcorr_sep_kernel<BS, TD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
+      cudaFuncSetAttribute(xcorr_sep_kernel<BS, TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
+      cudaFuncSetAttribute(xcorr_sep_kernel<BS, TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
   if (!attr_ok || cudaMemsetAsync(count, 0, sizeof(unsigned), st) != cudaSuccess) {
     cudaGetLastError();
     scratch_free(scratch, st);
@@ -682,11 +713,16 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
       in1, st1, g1, (int)H, (int)W, (int)ws1, (int)uoff, 1.0f, 0x80000000u, list, count);
   const int vec = (W % 4 == 0) && !((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) |
                                      reinterpret_cast<uintptr_t>(out)) & 15);
-  xcorr_sep_kernel<BS, TD><<<dim3((unsigned)cdiv(W, XS_W), (unsigned)cdiv(H, XH), (unsigned)(B * ndchunks)), 512 / TD, smem, st>>>(
-      in0, in1, out, st0, st1, (int)H, (int)W, (int)D, (int)ws0, (int)ws1, (int)uoff, (int)ndchunks, vec);
+  const dim3 sgrid((unsigned)cdiv(W, XS_W), (unsigned)cdiv(H, XH), (unsigned)(B * ndchunks));
+  if (vec)
+    xcorr_sep_kernel<BS, TD, true><<<sgrid, 512 / TD, smem, st>>>(in0, in1, out, st0, st1, (int)H, (int)W, (int)D, (int)ws0,
+                                                                 (int)ws1, (int)uoff, (int)ndchunks);
+  else
+    xcorr_sep_kernel<BS, TD, false><<<sgrid, 512 / TD, smem, st>>>(in0, in1, out, st0, st1, (int)H, (int)W, (int)D, (int)ws0,
+                                                                  (int)ws1, (int)uoff, (int)ndchunks);
   if (!g_xcorr_nofix)
-    xcorr_fixup_kernel<BS><<<148 * 3, 256, 0, st>>>(in0, in1, out, g0, g1, list, count, (int)H, (int)W, (int)D, (int)ws0,
-                                                 (int)ws1, (int)uoff);
+    xcorr_fixup_kernel<BS><<<148 * 3, 256, 0, st>>>(in0, in1, out, st0, st1, g0, g1, list, count, (int)H, (int)W, (int)D,
+                                                 (int)ws0, (int)ws1, (int)uoff);
   count_launch(4);
   scratch_free(scratch, st);
   return true;

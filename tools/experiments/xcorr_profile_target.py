@@ -5,7 +5,7 @@ import connecting_the_dots_b200 as ctd
 from connecting_the_dots_b200 import synth
 tx = ctd.torchext
 cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-d = synth.make_batch(2, 480, 640)
+d = synth.make_batch(int(sys.argv[1]) if len(sys.argv) > 1 else 2, 480, 640)
 a, b = cu(d["ta"]), cu(d["pat_lcn"])
 for it in range(2):
     o = tx.xcorrvol(a, b, 128, 9)
