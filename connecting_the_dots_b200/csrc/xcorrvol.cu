@@ -213,7 +213,7 @@ constexpr int XS_LLIST = 18;          // max(L0, L1) >= 18 whenever L0 + L1 >= 3
 constexpr int XS_LEXACT = 76;         // var < 2^-19 sum v^2 (~2e-6): flat window, reference arithmetic
 template <int TD>
 struct XsNst {  // statistics rows in flight per warp (more warps per CTA -> shallower rings, same shared memory)
-  static constexpr int value = TD == 4 ? 3 : 2;
+  static constexpr int value = 3;
 };
 template <int NST>
 struct alignas(16) XsStatRing {
@@ -270,17 +270,24 @@ template <int BS>
 __device__ __forceinline__ float xcorr_centred_one(const float* __restrict__ p0, const float* __restrict__ p1, int H, int W,
                                                    int h, int w, int d, float mu0, float mu1, float sd0, float sd1) {
   constexpr int R = BS / 2;
+  unsigned ca[BS], cb[BS];  // byte offsets of the clamped columns of the two windows, once per output
+#pragma unroll
+  for (int bw = 0; bw < BS; ++bw) {
+    ca[bw] = 4u * (unsigned)clampi(w + bw - R, 0, W - 1);
+    cb[bw] = 4u * (unsigned)clampi(w + bw - R - d, 0, W - 1);
+  }
+  const char* q0 = reinterpret_cast<const char*>(p0);
+  const char* q1 = reinterpret_cast<const char*>(p1);
   float dot[3] = {0.f, 0.f, 0.f};  // three rows in flight
 #pragma unroll
   for (int bh = 0; bh < BS; ++bh) {
-    const int64_t row = (int64_t)clampi(h + bh - R, 0, H - 1) * W;
+    const int64_t row = (int64_t)clampi(h + bh - R, 0, H - 1) * W * 4;
+    const char* ra = q0 + row;
+    const char* rb = q1 + row;
 #pragma unroll
-    for (int bw = 0; bw < BS; ++bw) {
-      const int w0 = w + bw - R;
-      const float a = __ldg(p0 + row + clampi(w0, 0, W - 1));
-      const float b = __ldg(p1 + row + clampi(w0 - d, 0, W - 1));
-      dot[bh % 3] = fmaf(a - mu0, b - mu1, dot[bh % 3]);
-    }
+    for (int bw = 0; bw < BS; ++bw)
+      dot[bh % 3] = fmaf(__ldg(reinterpret_cast<const float*>(ra + ca[bw])) - mu0,
+                         __ldg(reinterpret_cast<const float*>(rb + cb[bw])) - mu1, dot[bh % 3]);
   }
   return ((dot[0] + dot[1]) + dot[2]) / (sd0 * sd1 + 1e-8f);
 }
@@ -398,7 +405,8 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   constexpr int NT = 512 / TD, NST = XsNst<TD>::value;
   typedef XsStatRing<NST> Ring;
   Ring* rings = reinterpret_cast<Ring*>(smem_raw + sizeof(float) * TH * (XS_AW + XS_BW));
-  const int tid = threadIdx.x, lane = tid & 31, g = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int g = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp index, known to be warp-uniform (uniform datapath)
   const int x0 = blockIdx.x * XS_W, y0 = blockIdx.y * XH;
   const int b = blockIdx.z / ndchunks, d0 = (blockIdx.z % ndchunks) * XS_DT;
   const int64_t plane = (int64_t)H * W;
@@ -479,15 +487,17 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   const uint32_t wbytes = (uint32_t)min(XS_W, ws0 - x0) * 8u;
   const uint32_t ubytes = (uint32_t)min(XS_W + 8, ws1 - (x0 - dbase - 4 + uoff)) * 8u;
   const int nrows = min(XH, H - y0);  // output rows of this tile
-  int nissued = 0;                    // lane 0: rows handed to the copy engine so far
-  auto issue = [&](int st) {          // lane 0: fetch the statistics of the next output row into stage st
-    const uint32_t bar = ring_bar + 8u * st;
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(wbytes + ubytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(ring_w + (uint32_t)(sizeof(float2) * XS_W) * st), "l"(wnext), "r"(wbytes), "r"(bar) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(ring_u + (uint32_t)(sizeof(float2) * (XS_W + 8)) * st), "l"(unext), "r"(ubytes), "r"(bar) : "memory");
+  int nissued = 0;                    // rows handed to the copy engine so far (every lane keeps the warp-uniform state)
+  auto issue = [&](int st) {          // fetch the statistics of the next output row into stage st (lane 0 issues)
+    if (lane == 0) {
+      const uint32_t bar = ring_bar + 8u * st;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(wbytes + ubytes) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(ring_w + (uint32_t)(sizeof(float2) * XS_W) * st), "l"(wnext), "r"(wbytes), "r"(bar) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(ring_u + (uint32_t)(sizeof(float2) * (XS_W + 8)) * st), "l"(unext), "r"(ubytes), "r"(bar) : "memory");
+    }
     wnext += wstep;
     unext += ustep;
     ++nissued;
@@ -496,10 +506,11 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
 #pragma unroll
     for (int st = 0; st < NST; ++st) mbar_init(&ring.full[st], 1);
     fence_barrier_init();
-#pragma unroll
-    for (int e = 0; e < NST; ++e)
-      if (e < nrows) issue(e);
   }
+  __syncwarp();
+#pragma unroll
+  for (int e = 0; e < NST; ++e)
+    if (e < nrows) issue(e);
   __syncwarp();
   // One block of BS tile rows.  FIRST: the tile's first block only fills the vertical state (its last row
   // completes the first window); afterwards every row emits one output row.  Returns true when the tile's
@@ -591,7 +602,7 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
       }
       if (emit) {  // every lane has read this stage: hand it to the row NST further down
         __syncwarp();
-        if (lane == 0 && nissued < nrows) issue(st);
+        if (nissued < nrows) issue(st);
       }
       orow += W;
     }
