@@ -10,6 +10,7 @@ namespace ctd {
 
 int g_force_generic = 0;  // tests: route every op through its generic kernel
 int g_xcorr_direct = 0;   // tests / A-B runs: XCorrVol through the direct (centred two-pass) tile kernel
+int g_xcorr_hitcap = -1;  // tests: size of XCorrVol's fix-up hit list (0 forces the overflow path), -1 = automatic
 int g_xcorr_nofix = 0;    // experiments: skip XCorrVol's fix-up pass (fast-path error measurements)
 int g_host_chunks = 4;     // host-buffer API: image chunks per call (copies below ~2 MB lose PCIe efficiency)
 extern int g_census_pairs;
@@ -121,6 +122,10 @@ CTD_API int ctd_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "xcorr_nofix")) {
     ctd::g_xcorr_nofix = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "xcorr_hitcap")) {
+    ctd::g_xcorr_hitcap = value;
     return CTD_OK;
   }
   if (name && !strcmp(name, "host_chunks")) {

@@ -15,6 +15,7 @@ namespace ctd {
 extern int g_force_generic;
 extern int g_xcorr_direct;
 extern int g_xcorr_nofix;
+extern int g_xcorr_hitcap;
 
 // generic: any C, any block size, float or double; one thread per output, reference operation order
 // (built with -fmad=false), so it reproduces the reference's two-pass centred statistics exactly.
@@ -192,7 +193,7 @@ xcorrvol_direct(const float* __restrict__ in0, const float* __restrict__ in1, fl
 // Conditioning: the expanded form cancels when a window's spread is small against its mean.
 // xcorr_stats_kernel grades every window with L = floor(-4 log2(var / sum v^2)) (a byte per window, read
 // only by the fix-up pass).  The fast path's error is about 1.5e-7 * sqrt(S2_0 S2_1) / (sd0 sd1) =
-// 1.5e-7 * 2^((L0+L1)/8); outputs with L0 + L1 >= XS_LSUM (sd0 sd1 < 2^-4.5 sqrt(S2_0 S2_1), a few per
+// 1.5e-7 * 2^((L0+L1)/8); outputs with L0 + L1 >= XS_LSUM (sd0 sd1 < 2^-5 sqrt(S2_0 S2_1), a few per
 // thousand on LCN'd images) are recomputed by xcorr_fixup_kernel: it walks the listed windows
 // (L >= XS_LLIST), compacts the affected outputs and evaluates them in the centred form, one fp32 pass with the
 // window means of the statistics pass (xcorr_centred_one) -- or, for flat windows
@@ -208,8 +209,8 @@ constexpr int XS_TD = CTD_XS_TD;      // disparities per thread (4: 4 warps per 
 constexpr int XS_AW = XS_W + 8;       // in0 tile: image columns x0-4 .. x0+131
 constexpr int XS_BW = XS_W + 8 + 16;  // in1 tile: image columns x0-20-d0 .. x0+131-d0 (clamped)
 constexpr int ST_W = 128, ST_H = 16;  // statistics tile
-constexpr int XS_LSUM = 36;           // L0 + L1 >= 36 <=> (sd0 sd1)^2 <= 2^-9 S2_0 S2_1: recompute centred
-constexpr int XS_LLIST = 18;          // max(L0, L1) >= 18 whenever L0 + L1 >= 36
+constexpr int XS_LSUM = 40;           // L0 + L1 >= 40 <=> (sd0 sd1)^2 <= 2^-10 S2_0 S2_1 (fast-path error ~5e-6): recompute centred
+constexpr int XS_LLIST = 20;          // max(L0, L1) >= 20 whenever L0 + L1 >= 40
 constexpr int XS_LEXACT = 76;         // var < 2^-19 sum v^2 (~2e-6): flat window, reference arithmetic
 template <int TD>
 struct XsNst {  // statistics rows in flight per warp (more warps per CTA -> shallower rings, same shared memory)
@@ -307,9 +308,19 @@ xcorr_stats_kernel(const float* __restrict__ img, float2* __restrict__ st_out, u
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * ST_W, y0 = blockIdx.y * ST_H;
   const float* src = img + (int64_t)blockIdx.z * H * W;
-  for (int i = tid; i < TH * TW; i += 256) {
-    const int r = i / TW, j = i % TW;
-    T[r][j] = __ldg(src + (int64_t)clampi(y0 - R + r, 0, H - 1) * W + clampi(i0 - uoff - R + j, 0, W - 1));
+  {  // every load of the tile in flight before the first shared-memory store (one round trip, not thirteen)
+    constexpr int NLD = (TH * TW + 255) / 256;
+    float v[NLD];
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = tid + 256 * k, r = i / TW, j = i % TW;
+      if (i < TH * TW) v[k] = __ldg(src + (int64_t)clampi(y0 - R + r, 0, H - 1) * W + clampi(i0 - uoff - R + j, 0, W - 1));
+    }
+#pragma unroll
+    for (int k = 0; k < NLD; ++k) {
+      const int i = tid + 256 * k;
+      if (i < TH * TW) T[i / TW][i % TW] = v[k];
+    }
   }
   __syncthreads();
   for (int it = tid; it < TH * (ST_W / 4); it += 256) {
@@ -614,6 +625,122 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
     if (do_block(std::false_type{}, blk)) return;
 }
 
+// Recompute one untrusted output: centred form with the statistics pass's means, or the reference arithmetic
+// where a window is flat.
+template <int BS>
+__device__ __forceinline__ void xcorr_fix_one(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
+                                              const float2* __restrict__ st0, const float2* __restrict__ st1,
+                                              const uint8_t* __restrict__ g0, const uint8_t* __restrict__ g1,
+                                              unsigned long long e, int H, int W, int D, int ws0, int ws1, int uoff) {
+  const int64_t plane = (int64_t)H * W;
+  const unsigned hw = (unsigned)(e & 0xffffffffu), bd = (unsigned)(e >> 32);  // h*W + w, b*D + d
+  const int w = (int)(hw % (unsigned)W), h = (int)(hw / (unsigned)W);
+  const int d = (int)(bd % (unsigned)D);
+  const int64_t b = bd / (unsigned)D;
+  const int64_t i0 = (b * H + h) * ws0 + w, i1 = (b * H + h) * ws1 + (w - d + uoff);
+  float v;
+  if (g0[i0] >= XS_LEXACT || g1[i1] >= XS_LEXACT) {
+    v = xcorr_exact_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d);
+  } else {
+    const float2 s0 = __ldg(st0 + i0), s1 = __ldg(st1 + i1);  // {N mu0, sd0}, {mu1, sd1}
+    v = xcorr_centred_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d, s0.x * (1.0f / float(BS * BS)), s1.x, s0.y,
+                              s1.y);
+  }
+  out[(int64_t)bd * plane + hw] = v;
+}
+
+// Fix-up, step 1: which outputs are untrusted.  A listed window (side 0: window of in0 at (h, w) -> outputs
+// (d, h, w); side 1: window of in1 at (h, u) -> outputs (d, h, u + d) inside the image) is checked against the
+// grade of its partner window at every disparity; an output is owned by the side with the larger grade (side 0
+// on ties) so it is listed once.  A warp takes SW_BATCH listed windows at a time: their list entries and grades are
+// fetched by as many lanes in parallel, then the windows are visited one by one, lane l looking at disparities
+// 32c + l, four chunks per step with the partner-grade loads issued together -- the only serial latency per window
+// is one load; hits collect in a per-warp shared-memory queue that is flushed to `hits` with one atomic.  nhits
+// keeps counting past `cap`, which hands the whole job to xcorr_fixup_kernel (below).
+constexpr int SW_BATCH = 8;   // listed windows a warp takes at a time
+constexpr int SW_QUEUE = 256;  // per-warp hit queue (flushed with one atomic when half full)
+__global__ void __launch_bounds__(256)
+xcorr_sweep_kernel(const uint8_t* __restrict__ g0, const uint8_t* __restrict__ g1, const unsigned* __restrict__ list,
+                   const unsigned* __restrict__ count, unsigned long long* __restrict__ hits, unsigned* __restrict__ nhits,
+                   unsigned cap, int H, int W, int D, int ws0, int ws1, int uoff) {
+  __shared__ unsigned long long queue[8][SW_QUEUE];
+  const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
+  const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
+  const unsigned n = *count;
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned nq = 0;  // warp-uniform queue length
+  auto flush = [&]() {
+    unsigned slot = 0;
+    if (lane == 0) slot = atomicAdd(nhits, nq);
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    for (unsigned k = lane; k < nq; k += 32)
+      if (slot + k < cap) hits[slot + k] = queue[wl][k];
+    nq = 0;
+    __syncwarp();
+  };
+  for (unsigned base = SW_BATCH * (blockIdx.x * (blockDim.x >> 5) + wl); base < n; base += SW_BATCH * nwarps) {
+    // lane j < SW_BATCH: the facts of window base + j
+    unsigned my_side = 0, my_row = 0, my_L = 0;
+    int my_i = 0;
+    if (lane < SW_BATCH && base + lane < n) {
+      const unsigned e = list[base + lane];
+      my_side = e >> 31;
+      const unsigned pos = e & 0x7fffffffu, ws = my_side ? (unsigned)ws1 : (unsigned)ws0;
+      my_row = pos / ws;  // b*H + h
+      my_i = (int)(pos - my_row * ws);
+      my_L = my_side ? g1[pos] : g0[pos];
+    }
+    const int nwin = (int)min((unsigned)SW_BATCH, n - base);
+    for (int j = 0; j < nwin; ++j) {
+      const unsigned side = __shfl_sync(0xffffffffu, my_side, j), row = __shfl_sync(0xffffffffu, my_row, j);
+      const unsigned Ls = __shfl_sync(0xffffffffu, my_L, j);
+      const int i = __shfl_sync(0xffffffffu, my_i, j);
+      const uint8_t* other = side ? g0 + (size_t)row * ws0 : g1 + (size_t)row * ws1 + uoff;
+      const unsigned bD = (row / (unsigned)H) * (unsigned)D, hW = (row % (unsigned)H) * (unsigned)W;
+      for (int d0 = 0; d0 < D; d0 += 128) {
+        unsigned Lo[4];
+        int wv[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {  // the four partner grades of this lane, loads in flight together
+          const int d = d0 + 32 * c + lane;
+          wv[c] = side ? i - uoff + d : i;
+          const bool valid = d < D && wv[c] >= 0 && wv[c] < W;
+          Lo[c] = valid ? (unsigned)(side ? other[wv[c]] : other[wv[c] - d]) : 0xffffu;  // 0xffff: never a hit
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const bool hit = Lo[c] != 0xffffu && Ls + Lo[c] >= (unsigned)XS_LSUM && (side ? Ls > Lo[c] : Ls >= Lo[c]);
+          const unsigned m = __ballot_sync(0xffffffffu, hit);
+          if (hit)
+            queue[wl][nq + __popc(m & lt)] =
+                ((unsigned long long)(bD + (unsigned)(d0 + 32 * c + lane)) << 32) | (hW + (unsigned)wv[c]);
+          nq += __popc(m);
+        }
+        __syncwarp();
+        if (nq >= SW_QUEUE / 2) flush();  // at most 128 entries are added per step
+      }
+    }
+  }
+  if (nq > 0) flush();
+}
+
+// Fix-up, step 2: one thread per untrusted output (neighbouring hits are neighbouring disparities of one window, so
+// the gathers of a warp stay within a few cache lines).
+template <int BS>
+__global__ void __launch_bounds__(256)
+xcorr_eval_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
+                  const float2* __restrict__ st0, const float2* __restrict__ st1, const uint8_t* __restrict__ g0,
+                  const uint8_t* __restrict__ g1, const unsigned long long* __restrict__ hits, const unsigned* __restrict__ nhits,
+                  unsigned cap, int H, int W, int D, int ws0, int ws1, int uoff) {
+  const unsigned n = *nhits;
+  if (n > cap) return;  // the list overflowed: xcorr_fixup_kernel does the whole job
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    xcorr_fix_one<BS>(in0, in1, out, st0, st1, g0, g1, hits[i], H, W, D, ws0, ws1, uoff);
+}
+
+// Fallback when more outputs are untrusted than the hit list holds (pathological inputs: every window flat):
+// the same sweep, but affected outputs are queued per warp and evaluated in place, 32 at a time, so the expensive
+// path runs with full warps however sparse the hits are.  Exits at once when the list did not overflow.
 // One warp per (listed window, 32 disparities): lane l looks at output d = 32*chunk + l.  side 0: window
 // of in0 at (h, w) -> outputs (d, h, w); side 1: window of in1 at (h, u) -> outputs (d, h, u + d) inside the
 // image.  An output is owned by the side with the larger grade (side 0 on ties) so it is done once.
@@ -623,9 +750,10 @@ template <int BS>
 __global__ void __launch_bounds__(256)
 xcorr_fixup_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ out,
                    const float2* __restrict__ st0, const float2* __restrict__ st1, const uint8_t* __restrict__ g0,
-                   const uint8_t* __restrict__ g1, const unsigned* __restrict__ list, const unsigned* __restrict__ count, int H,
-                   int W, int D, int ws0, int ws1, int uoff) {
+                   const uint8_t* __restrict__ g1, const unsigned* __restrict__ list, const unsigned* __restrict__ count,
+                   const unsigned* __restrict__ nhits, unsigned cap, int H, int W, int D, int ws0, int ws1, int uoff) {
   __shared__ unsigned long long queue[8][64];  // (b*D + d) << 32 | (h*W + w)
+  if (*nhits <= cap) return;  // the hit list held everything: xcorr_eval_kernel has done the job
   const int lane = threadIdx.x & 31, wl = threadIdx.x >> 5;
   const unsigned nwarps = gridDim.x * (blockDim.x >> 5);
   const unsigned dchunks = (unsigned)(D + 31) / 32u;
@@ -633,23 +761,7 @@ xcorr_fixup_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
   const int64_t plane = (int64_t)H * W;
   int nq = 0;  // warp-uniform queue length
   auto drain = [&](int m) {  // evaluate the first m (<= 32) queued outputs, one per lane
-    if (lane < m) {
-      const unsigned long long e = queue[wl][lane];
-      const unsigned hw = (unsigned)(e & 0xffffffffu), bd = (unsigned)(e >> 32);  // h*W + w, b*D + d
-      const int w = (int)(hw % (unsigned)W), h = (int)(hw / (unsigned)W);
-      const int d = (int)(bd % (unsigned)D);
-      const int64_t b = bd / (unsigned)D;
-      const int64_t i0 = (b * H + h) * ws0 + w, i1 = (b * H + h) * ws1 + (w - d + uoff);
-      float v;
-      if (g0[i0] >= XS_LEXACT || g1[i1] >= XS_LEXACT) {
-        v = xcorr_exact_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d);
-      } else {
-        const float2 s0 = __ldg(st0 + i0), s1 = __ldg(st1 + i1);  // {N mu0, sd0}, {mu1, sd1}
-        v = xcorr_centred_one<BS>(in0 + b * plane, in1 + b * plane, H, W, h, w, d, s0.x * (1.0f / float(BS * BS)), s1.x,
-                                  s0.y, s1.y);
-      }
-      out[(int64_t)bd * plane + hw] = v;
-    }
+    if (lane < m) xcorr_fix_one<BS>(in0, in1, out, st0, st1, g0, g1, queue[wl][lane], H, W, D, ws0, ws1, uoff);
     __syncwarp();
   };
   // listed windows are spread over the warps; a warp sweeps the disparities of its window 32 at a time
@@ -697,13 +809,17 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
   const int64_t uoff = ndchunks * XS_DT, ws0 = cdiv(W, 4) * 4, ws1 = uoff + ws0;
   const int64_t n0 = B * H * ws0, n1 = B * H * ws1;
   if (B * ndchunks > 65535 || cdiv(H, XH) > 65535 || cdiv(H, ST_H) > 65535 || n1 >= ((int64_t)1 << 31)) return false;
-  const size_t words = (size_t)(3 * n0 + 3 * n1 + 4) + (size_t)(n0 + n1 + 3) / 4;
+  // hit list of the fix-up: room for 1/32 of the outputs (a few per thousand are expected), at most 4 M entries;
+  // g_xcorr_hitcap >= 0 overrides (tests force the overflow path with 0)
+  const int64_t cap = (g_xcorr_hitcap >= 0 ? g_xcorr_hitcap : std::min<int64_t>(B * D * H * W / 32 + 1024, (int64_t)1 << 22)) / 2 * 2;  // even: the statistics planes behind it stay 16-byte aligned
+  const size_t words = (size_t)(2 * cap) + (size_t)(3 * n0 + 3 * n1 + 4) + (size_t)(n0 + n1 + 3) / 4;
   float* scratch = static_cast<float*>(scratch_alloc(words * sizeof(float), st));
   if (!scratch) return false;
-  float2* st0 = reinterpret_cast<float2*>(scratch);
+  unsigned long long* hits = reinterpret_cast<unsigned long long*>(scratch);  // 8-byte aligned: first
+  float2* st0 = reinterpret_cast<float2*>(hits + cap);
   float2* st1 = st0 + n0;
   unsigned* list = reinterpret_cast<unsigned*>(st1 + n1);
-  unsigned* count = list + n0 + n1;
+  unsigned* count = list + n0 + n1;  // count[0]: listed windows, count[1]: untrusted outputs
   uint8_t* g0 = reinterpret_cast<uint8_t*>(count + 4);
   uint8_t* g1 = g0 + n0;
   const size_t st_smem = sizeof(double) * 2 * (ST_H + 2 * R) * ST_W + sizeof(float) * (ST_H + 2 * R) * (ST_W + 2 * R);
@@ -713,7 +829,7 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
       cudaFuncSetAttribute(xcorr_stats_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem) == cudaSuccess &&
       cudaFuncSetAttribute(xcorr_sep_kernel<BS, TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
       cudaFuncSetAttribute(xcorr_sep_kernel<BS, TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;
-  if (!attr_ok || cudaMemsetAsync(count, 0, sizeof(unsigned), st) != cudaSuccess) {
+  if (!attr_ok || cudaMemsetAsync(count, 0, 2 * sizeof(unsigned), st) != cudaSuccess) {
     cudaGetLastError();
     scratch_free(scratch, st);
     return false;
@@ -731,10 +847,15 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
   else
     xcorr_sep_kernel<BS, TD, false><<<sgrid, 512 / TD, smem, st>>>(in0, in1, out, st0, st1, (int)H, (int)W, (int)D, (int)ws0,
                                                                   (int)ws1, (int)uoff, (int)ndchunks);
-  if (!g_xcorr_nofix)
-    xcorr_fixup_kernel<BS><<<148 * 3, 256, 0, st>>>(in0, in1, out, st0, st1, g0, g1, list, count, (int)H, (int)W, (int)D,
-                                                 (int)ws0, (int)ws1, (int)uoff);
-  count_launch(4);
+  if (!g_xcorr_nofix) {
+    xcorr_sweep_kernel<<<148 * 8, 256, 0, st>>>(g0, g1, list, count, hits, count + 1, (unsigned)cap, (int)H, (int)W, (int)D,
+                                               (int)ws0, (int)ws1, (int)uoff);
+    xcorr_eval_kernel<BS><<<148 * 8, 256, 0, st>>>(in0, in1, out, st0, st1, g0, g1, hits, count + 1, (unsigned)cap, (int)H,
+                                                  (int)W, (int)D, (int)ws0, (int)ws1, (int)uoff);
+    xcorr_fixup_kernel<BS><<<148 * 3, 256, 0, st>>>(in0, in1, out, st0, st1, g0, g1, list, count, count + 1, (unsigned)cap,
+                                                   (int)H, (int)W, (int)D, (int)ws0, (int)ws1, (int)uoff);
+  }
+  count_launch(g_xcorr_nofix ? 3 : 6);
   scratch_free(scratch, st);
   return true;
 }

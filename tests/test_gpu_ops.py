@@ -339,6 +339,26 @@ def test_xcorrvol_ill_conditioned_windows(tx):
     assert_close(got[0], oracle.xcorrvol(z[0], np.roll(z, 2, axis=3)[0], D, 5), what="zero band")
 
 
+def test_xcorrvol_fixup_overflow_path(tx):
+    """The fix-up lists untrusted outputs in a bounded hit list; with the list forced to size 0 the in-place
+    fallback kernel must produce exactly the same volume."""
+    from connecting_the_dots_b200 import _lib
+    rng = np.random.RandomState(11)
+    H, W, D = 40, 132, 21
+    a = (0.5 + 0.02 * rng.randn(2, 1, H, W)).astype(np.float32)
+    b = (0.5 + 0.02 * rng.randn(2, 1, H, W)).astype(np.float32)
+    a[1, 0, 5:25, 30:70] = 0.75
+    listed = tx.xcorrvol(cu(a), cu(b), D, 9)
+    _lib.set_option("xcorr_hitcap", 0)
+    try:
+        inplace = tx.xcorrvol(cu(a), cu(b), D, 9)
+    finally:
+        _lib.set_option("xcorr_hitcap", -1)
+    assert torch.equal(listed, inplace)
+    for n in range(2):
+        assert_close(listed[n].cpu().numpy(), oracle.xcorrvol(a[n], b[n], D, 9), what="raw intensities image %d" % n)
+
+
 def test_xcorrvol_separable_matches_direct(tx):
     """A/B: the separable kernel against the direct centred kernel of the same library on LCN'd data."""
     from connecting_the_dots_b200 import _lib, synth
