@@ -32,6 +32,22 @@ constexpr int L_RG = 8;        // rows per shared-memory round
 extern int g_force_generic;
 constexpr int L_THREADS = 256;
 
+// a / n correctly rounded for a constant n whose reciprocal inv_n = RN(1/n) is given (Markstein: one
+// residual step on the rounded product is exact when 1/n is correctly rounded and n's significand is not all
+// ones; checked exhaustively for n = 121 by tools/experiments/div121_exhaustive.cu: bit-identical to IEEE division
+// for every finite float except -0, which comes out as +0 -- harmless, avg only enters as avg * avg and x - avg).
+// Three FMA-pipe instructions instead of the IEEE division's reciprocal, refinement and range checks.
+__device__ __forceinline__ float div_const_rn(float a, float n, float inv_n) {
+  const float q = a * inv_n;
+  const float r = fmaf(-q, n, a);
+  return fmaf(r, inv_n, q);
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 __device__ __forceinline__ int reflect(int i, int n) {  // torch ReflectionPad2d: no edge repeat
   if (i < 0) i = -i;
   if (i > n - 1) i = 2 * (n - 1) - i;
@@ -171,7 +187,7 @@ lcn_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ lc
   extern __shared__ unsigned char smem_raw[];
   LcnSmem& S = *reinterpret_cast<LcnSmem*>(align128_shared(smem_raw));
   constexpr int K = 2 * R + 1;
-  const float n = float(K * K);
+  const float n = float(K * K), inv_n = 1.0f / float(K * K);
   const int tid = threadIdx.x;
   if (tid == 0) {
     mbar_init(&S.full[0], 1);
@@ -244,10 +260,13 @@ lcn_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ lc
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         const float box = (float)h1, box2 = (float)h2;
-        const float avg = box / n;
-        const float var = box2 / n - avg * avg + 1e-6f;
-        const float sd = sqrtf(var) + eps;
-        ol[m] = (xv[m] - avg) / sd;
+        // avg, E[x^2] and var feed a cancellation, so they carry the reference's roundings bit for bit: box / n
+        // is the correctly rounded quotient (div_const_rn), var keeps the reference's operation order.  What
+        // follows the cancellation is not amplified: approximate square root and reciprocal (~2 ulp).
+        const float avg = div_const_rn(box, n, inv_n);
+        const float var = div_const_rn(box2, n, inv_n) - avg * avg + 1e-6f;
+        const float sd = sqrt_approx(var) + eps;
+        ol[m] = (xv[m] - avg) * rcp_approx(sd);
         os[m] = sd;
         if (m < 3) {
           h1 += a1[lcol36(m + K)] - a1[lcol36(m)];

@@ -373,6 +373,9 @@ constexpr int CT_NH = CT_H / 16;
 #define CTD_CB_NPX 2
 #endif
 constexpr int CB_NPX = CTD_CB_NPX;  // pixels per thread and pass in the census backward
+#ifndef CTD_CB_MINB
+#define CTD_CB_MINB 3  // resident CTAs per SM the census backward is compiled for (4 = 64 registers: measured slower / spills)
+#endif
 #ifndef CTD_CB_H
 #define CTD_CB_H 16
 #endif
@@ -664,7 +667,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
 }
 
 template <int TYPE, bool FUSE, int NPX>
-__global__ void __launch_bounds__(256, NPX == 4 ? 2 : 3)
+__global__ void __launch_bounds__(256, NPX == 4 ? 2 : CTD_CB_MINB)
 photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
                   float* __restrict__ gi, float* __restrict__ out, int C, int H, int W, float eps, int vec,
                   const float* __restrict__ mask, double* __restrict__ partials, unsigned* __restrict__ ticket,
