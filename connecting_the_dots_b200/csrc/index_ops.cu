@@ -11,6 +11,8 @@
 
 namespace ctd {
 
+extern int g_force_generic;
+
 // ------------------------------------------------------------------------------------------
 // ProjNN
 // ------------------------------------------------------------------------------------------
@@ -166,6 +168,65 @@ crosscheck_kernel(const int64_t* __restrict__ in0, const int64_t* __restrict__ i
   }
 }
 
+// Fixed patch size (1, 2, 3, 5, 7, 9), images below 2^31 / 3 pixels: the PS x PS scan is unrolled, the in-image
+// test of every candidate is done up front and all its loads are issued before the first comparison (PS^2 gathers
+// in flight instead of one), indices are 32-bit inside the image.  Same arithmetic and scan order as above: an
+// absent candidate gets distance +inf, which never passes the strict `<` against 1e9 or anything below it.
+template <typename T, int PS>
+__global__ void __launch_bounds__(PN_THREADS)
+proj_nn_fixed_kernel(const T* __restrict__ xyz0, const T* __restrict__ xyz1, const T* __restrict__ K,
+                     int64_t* __restrict__ out, int64_t total, int H, int W) {
+  __shared__ T pts[PN_THREADS * 3];
+  const int tid = threadIdx.x;
+  const int64_t i0 = (int64_t)blockIdx.x * PN_THREADS;
+  const int nvalid = (int)min((int64_t)PN_THREADS, total - i0);
+  for (int j = tid; j < nvalid * 3; j += PN_THREADS) pts[j] = __ldg(xyz0 + i0 * 3 + j);
+  T k[9];
+#pragma unroll
+  for (int j = 0; j < 9; ++j) k[j] = __ldg(K + j);
+  __syncthreads();
+  if (tid >= nvalid) return;
+  const int64_t i = i0 + tid;
+  const unsigned hw = (unsigned)H * (unsigned)W;
+  const int64_t b = i / hw;
+  const T* img1 = xyz1 + b * (int64_t)hw * 3;
+  const T x = pts[tid * 3 + 0], y = pts[tid * 3 + 1], z = pts[tid * 3 + 2];
+  const T den = k[6] * x + k[7] * y + k[8] * z;
+  const T u = (k[0] * x + k[1] * y + k[2] * z) / den;
+  const T v = (k[3] * x + k[4] * y + k[5] * z) / den;
+  const int u0 = x86_double_to_int((double)u + 0.5);
+  const int v0 = x86_double_to_int((double)v + 0.5);
+  constexpr int half = PS / 2;
+  // INT_MIN (x86's answer to NaN / out of range) must stay far outside the image after the offsets are added
+  const int ub = u0 < -(1 << 30) ? -(1 << 30) : u0 - half, vb = v0 < -(1 << 30) ? -(1 << 30) : v0 - half;
+  T best_d = (T)1e9;
+  int best = -1;
+#pragma unroll
+  for (int pv = 0; pv < PS; ++pv) {
+    const int v1 = vb + pv;
+    const bool vok = v1 >= 0 && v1 < H;
+    T qx[PS], qy[PS], qz[PS];
+#pragma unroll
+    for (int pu = 0; pu < PS; ++pu) {
+      const int u1 = ub + pu;
+      const bool ok = vok && u1 >= 0 && u1 < W;
+      const T* q = img1 + (unsigned)(ok ? v1 * W + u1 : 0) * 3u;
+      qx[pu] = ok ? __ldg(q) : (T)INFINITY;
+      qy[pu] = ok ? __ldg(q + 1) : (T)0;
+      qz[pu] = ok ? __ldg(q + 2) : (T)0;
+    }
+#pragma unroll
+    for (int pu = 0; pu < PS; ++pu) {
+      const T dd = (x - qx[pu]) * (x - qx[pu]) + (y - qy[pu]) * (y - qy[pu]) + (z - qz[pu]) * (z - qz[pu]);
+      if (dd < best_d) {
+        best_d = dd;
+        best = (vb + pv) * W + (ub + pu);
+      }
+    }
+  }
+  out[i] = best < 0 ? (int64_t)-1 : b * (int64_t)hw + best;
+}
+
 template <typename T>
 static int proj_nn_impl(const T* xyz0, const T* xyz1, const T* K, int64_t* out, int64_t B, int64_t H, int64_t W,
                         int ps, cudaStream_t st) {
@@ -176,8 +237,24 @@ static int proj_nn_impl(const T* xyz0, const T* xyz1, const T* K, int64_t* out, 
   if (total == 0) return CTD_OK;
   CTD_REQUIRE(xyz0 && xyz1 && K && out, "proj_nn: null pointer");
   CTD_REQUIRE(cdiv(total, PN_THREADS) <= INT32_MAX, "proj_nn: too many pixels");
-  proj_nn_kernel<T><<<(unsigned)cdiv(total, PN_THREADS), PN_THREADS, 0, st>>>(xyz0, xyz1, K, out, total, (int)H,
-                                                                            (int)W, ps);
+  const unsigned grid = (unsigned)cdiv(total, PN_THREADS);
+  const bool fixed = !g_force_generic && H * W < ((int64_t)1 << 31) / 3;
+#define CTD_PN_CASE(PS)                                                                                             \
+  case PS:                                                                                                          \
+    proj_nn_fixed_kernel<T, PS><<<grid, PN_THREADS, 0, st>>>(xyz0, xyz1, K, out, total, (int)H, (int)W);           \
+    count_launch();                                                                                                 \
+    return check_launch("proj_nn(fixed)");
+  if (fixed) switch (ps) {
+      CTD_PN_CASE(1)
+      CTD_PN_CASE(2)
+      CTD_PN_CASE(3)
+      CTD_PN_CASE(5)
+      CTD_PN_CASE(7)
+      CTD_PN_CASE(9)
+      default: break;
+    }
+#undef CTD_PN_CASE
+  proj_nn_kernel<T><<<grid, PN_THREADS, 0, st>>>(xyz0, xyz1, K, out, total, (int)H, (int)W, ps);
   count_launch();
   return check_launch("proj_nn");
 }
