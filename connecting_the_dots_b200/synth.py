@@ -110,3 +110,34 @@ def make_clouds(n_frames, H=H0, W=W0, seed=0):
 def transform(xyz, pose):
     R, t = pose
     return (xyz @ R.T + t).astype(np.float32)
+
+
+def make_depth_pairs(B, H=H0, W=W0, seed=0):
+    """Inputs of the geometric loss (model/exp_synphge.py:185-200) for B frame pairs: depth0, depth1 [B,1,H,W]
+    (depth = baseline * focal / disparity of two nearby smooth surfaces, as DispToDepth produces them), camera
+    poses R0, t0, R1, t1 of a small rigid motion between the frames, and the intrinsics K, Ki scaled to (H, W)."""
+    rng = np.random.RandomState(7000 + seed)
+    K = K_REF.astype(np.float64).copy()
+    K[0] *= W / W0
+    K[1] *= H / H0
+    Ki = np.linalg.inv(K)
+
+    def rot(a):
+        Rx = np.array([[1, 0, 0], [0, np.cos(a[0]), -np.sin(a[0])], [0, np.sin(a[0]), np.cos(a[0])]])
+        Ry = np.array([[np.cos(a[1]), 0, np.sin(a[1])], [0, 1, 0], [-np.sin(a[1]), 0, np.cos(a[1])]])
+        Rz = np.array([[np.cos(a[2]), -np.sin(a[2]), 0], [np.sin(a[2]), np.cos(a[2]), 0], [0, 0, 1]])
+        return Rx @ Ry @ Rz
+
+    d0, d1, R0, t0, R1, t1 = [], [], [], [], [], []
+    for n in range(B):
+        disp = smooth_disparity(np.random.RandomState(3000 + seed + n % 8), H, W)
+        d0.append((BASELINE * FOCAL * (W / W0) / disp).astype(np.float32))
+        d1.append((BASELINE * FOCAL * (W / W0) / (disp + 0.3 + 0.1 * np.sin(np.arange(W) / 37.0))).astype(np.float32))
+        R0.append(rot(rng.uniform(-0.01, 0.01, 3)))
+        R1.append(rot(rng.uniform(-0.01, 0.01, 3)))
+        t0.append(rng.uniform(-0.01, 0.01, 3))
+        t1.append(rng.uniform(-0.01, 0.01, 3))
+    f = lambda a: np.ascontiguousarray(np.stack(a), dtype=np.float32)
+    return {"depth0": f(d0)[:, None], "depth1": f(d1)[:, None], "R0": f(R0), "t0": f(t0), "R1": f(R1), "t1": f(t1),
+            "K": K.astype(np.float32), "Ki": Ki.astype(np.float32)}
+

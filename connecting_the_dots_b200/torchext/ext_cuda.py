@@ -219,6 +219,39 @@ def warp_pattern_backward(pattern, disp, grad_out):
     return gd
 
 
+def depth_similarity(depth0, depth1, ray, K, R0, t0, R1, t1, clamp=-1.0):
+    """model/networks.py:500-503 (ProjectionDepthSimilarityLoss.tforward): both directions of the projected depth
+    difference, loss sums and gradients in two kernels.  depth0/1 [B,1,H,W]; ray [H*W,3] or [1,H*W,3]; K [3,3] or
+    [1,3,3]; R0/R1 [B,3,3]; t0/t1 [B,3].  Returns (sums [2,2] = per direction {sum diff, pixel count},
+    grad_depth0, grad_depth1) with the gradients of l0 + l1 (each a mean over B*H*W)."""
+    for t, name in ((depth0, "depth0"), (depth1, "depth1"), (ray, "ray"), (K, "K"), (R0, "R0"), (t0, "t0"), (R1, "R1"), (t1, "t1")):
+        _check_input_cuda(t, name)
+        _check(t.dtype == torch.float32, "depth_similarity is float32 only")
+        _same(depth0, t, "depth0", name)
+    _check(depth0.dim() == 4 and depth0.size(1) == 1, "depth0 has to be B x 1 x H x W")
+    _check(depth1.shape == depth0.shape, "depth0 and depth1 have to have the same shape")
+    B, _, H, W = depth0.shape
+    _check(ray.numel() == H * W * 3, "ray has to be H*W x 3")
+    _check(K.numel() == 9, "K has to be 3 x 3")
+    _check(R0.numel() == B * 9 and R1.numel() == B * 9, "R0, R1 have to be B x 3 x 3")
+    _check(t0.numel() == B * 3 and t1.numel() == B * 3, "t0, t1 have to be B x 3")
+    sums = torch.empty(2, 2, dtype=torch.float32, device=depth0.device)
+    g0 = torch.empty_like(depth0)
+    g1 = torch.zeros_like(depth1)
+    scale = 1.0 / max(B * H * W, 1)
+    with torch.cuda.device(depth0.device):
+        st = _stream(depth0)
+        # direction 0 -> 1: g0 gets every pixel's own gradient (store), g1 the bilinear scatter (atomics on zeros)
+        _lib.call("ctd_depth_similarity_f32", depth0.data_ptr(), depth1.data_ptr(), ray.data_ptr(), K.data_ptr(), R0.data_ptr(),
+                  t0.data_ptr(), R1.data_ptr(), t1.data_ptr(), g0.data_ptr(), g1.data_ptr(), sums[0].data_ptr(), B, H, W,
+                  float(clamp), scale, 0, st)
+        # direction 1 -> 0: roles swapped, own gradients are added to g1, the scatter lands on g0
+        _lib.call("ctd_depth_similarity_f32", depth1.data_ptr(), depth0.data_ptr(), ray.data_ptr(), K.data_ptr(), R1.data_ptr(),
+                  t1.data_ptr(), R0.data_ptr(), t0.data_ptr(), g1.data_ptr(), g0.data_ptr(), sums[1].data_ptr(), B, H, W,
+                  float(clamp), scale, 1, st)
+    return sums, g0, g1
+
+
 def lcn_forward(x, radius, epsilon):
     """model/networks.py:523-533 as one kernel.  x [N,1,H,W] -> (lcn, std), both [N,1,H,W]."""
     _check_input_cuda(x, "x")

@@ -193,6 +193,45 @@ def pattern_similarity_loss(disp, pattern, im, std=None, loss_type="census_sad",
     return val, pattern_proj
 
 
+class ProjectionDepthSimilarityFunction(torch.autograd.Function):
+    """The geometric loss of the stage-2 trainer, ProjectionDepthSimilarityLoss.tforward (model/networks.py:474-503,
+    called per frame pair at model/exp_synphge.py:185-200): unproject, two rigid transforms, projection, bilinear
+    sampling of the other frame's depth and the (clamped) absolute difference, both directions.  In the reference
+    that is 4 bmm, 2 grid_sample and ~20 elementwise kernels plus their autograd twins; here two launches produce
+    the loss and both depth gradients (the upstream gradient of a scalar loss is a scalar, applied in backward).
+    Poses, K and the ray table are not differentiated (they are data in the reference)."""
+
+    @staticmethod
+    def forward(ctx, depth0, depth1, R0, t0, R1, t1, K, ray, clamp):
+        if not depth0.is_cuda:
+            raise RuntimeError("torchext.projection_depth_similarity_loss: connecting_the_dots_b200 has no CPU implementation")
+        c = lambda t: t.detach().contiguous()
+        sums, g0, g1 = ext_cuda.depth_similarity(c(depth0), c(depth1), c(ray), c(K), c(R0), c(t0), c(R1), c(t1), clamp)
+        ctx.save_for_backward(g0, g1)
+        return sums[0, 0] / sums[0, 1] + sums[1, 0] / sums[1, 1]
+
+    @staticmethod
+    def backward(ctx, g):
+        g0, g1 = ctx.saved_tensors
+        return g0 * g, g1 * g, None, None, None, None, None, None, None
+
+
+def projection_depth_similarity_loss(depth0, depth1, R0, t0, R1, t1, K, ray, clamp=-1):
+    """l0 + l1 of ProjectionDepthSimilarityLoss.tforward(depth0, depth1, R0, t0, R1, t1) (model/networks.py:500-503).
+    K [3,3] and ray [H*W,3] are the module's constants (networks.py:421-434: ray = uv1 @ Ki^T in float32)."""
+    return ProjectionDepthSimilarityFunction.apply(depth0, depth1, R0, t0, R1, t1, K, ray, clamp)
+
+
+def projection_rays(Ki, im_height, im_width):
+    """The ray table of ProjectionBaseLoss.__init__ (model/networks.py:427-434): pixel centres (u, v, 1) times
+    Ki^T, computed in float64 by numpy and stored as float32 [H*W,3]."""
+    import numpy as np
+    u, v = np.meshgrid(range(im_width), range(im_height))
+    uv = np.stack((u, v, np.ones_like(u)), axis=2).reshape(-1, 3)
+    ray = uv @ np.asarray(Ki, dtype=np.float64).T if not torch.is_tensor(Ki) else uv @ Ki.cpu().numpy().T
+    return torch.from_numpy(ray.reshape(-1, 3).astype(np.float32))
+
+
 class LCNFunction(torch.autograd.Function):
     """Fused local contrast normalisation (model/networks.py:507-533); forward only -- in the
     reference the gradient flows to an input image nobody reads (exp_synph.py:80-91)."""

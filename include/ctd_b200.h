@@ -92,6 +92,18 @@ int ctd_warp_pattern_fwd_f32(const float* pattern, const float* disp, float* out
 int ctd_warp_pattern_bwd_f32(const float* pattern, const float* disp, const float* grad_out, float* grad_disp,
                              int64_t B, int64_t Bp, int64_t Hp, int64_t Wp, int64_t H, int64_t W, ctd_stream_t stream);
 
+/* ---- geometric loss of the stage-2 trainer, one direction: model/networks.py:474-498
+ * (ProjectionDepthSimilarityLoss.fwd over ProjectionBaseLoss.unproject/transform/project, networks.py:436-472).
+ * depthA, depthB [B,1,H,W]; ray [H*W,3] (the module's uv @ Ki^T table); K [3,3]; RA, RB [B,3,3]; tA, tB [B,3];
+ * all DEVICE pointers.  sums2[0] = sum |d - grid_sample(depthB)| (clamped to [0, clamp] when clamp > 0),
+ * sums2[1] = B*H*W, deterministic.  Gradients of sums2[0] * scale: grad_depthA [B,1,H,W] is written
+ * (direct_accumulate = 0) or added to (1); grad_depthB receives the bilinear scatter by atomicAdd and must be
+ * initialised by the caller.  Either gradient pointer may be NULL. */
+int ctd_depth_similarity_f32(const float* depthA, const float* depthB, const float* ray, const float* K,
+                             const float* RA, const float* tA, const float* RB, const float* tB,
+                             float* grad_depthA, float* grad_depthB, float* sums2, int64_t B, int64_t H, int64_t W,
+                             float clamp, float scale, int direct_accumulate, ctd_stream_t stream);
+
 /* ---- XCorrVolFunctor: ext.h:120-191, ext_cuda.cpp:73-86 (xcorrvol_cuda).  The reference has no
  * batch dimension; here in0,in1 are [B,C,H,W] and out is [B,D,H,W] (B=1 is the reference call). */
 int ctd_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,

@@ -687,3 +687,90 @@ def test_loss_path_is_cuda_graph_capturable(tx):
     torch.cuda.synchronize()
     for a, b in zip(eager, captured):
         assert torch.equal(a, b)
+
+
+# ---------------------------------------------------------------- geometric loss
+def _ref_depth_similarity(depth0, depth1, R0, t0, R1, t1, K, ray, clamp):
+    """model/networks.py:436-503 restated with torch ops (same calls in the same order), any device."""
+    B, _, H, W = depth0.shape
+
+    def fwd(dA, dB, RA, tA, RB, tB):
+        xyz = dA.reshape(B, -1, 1) * ray.reshape(1, -1, 3)              # unproject, networks.py:448
+        xyz = torch.bmm(xyz - tA.reshape(B, 1, 3), RA)                   # transform, networks.py:436-442
+        xyz = torch.bmm(xyz, RB.transpose(1, 2)) + tB.reshape(B, 1, 3)   # project, networks.py:456-457
+        uv = torch.bmm(xyz, K.reshape(1, 3, 3).transpose(1, 2).expand(B, -1, -1))
+        d = uv[:, :, 2:3]
+        uv = uv[:, :, :2] / (torch.nn.functional.relu(d) + 1e-12)
+        g = torch.stack((2 * (uv[..., 0] / (W - 1) - 0.5), 2 * (uv[..., 1] / (H - 1) - 0.5)), -1).view(-1, H, W, 2)
+        s = torch.nn.functional.grid_sample(dB, g, padding_mode="border", align_corners=False)
+        diff = torch.abs(d.view(-1) - s.view(-1))
+        if clamp > 0:
+            diff = torch.clamp(diff, 0, clamp)
+        return diff.mean()
+
+    return fwd(depth0, depth1, R0, t0, R1, t1) + fwd(depth1, depth0, R1, t1, R0, t0)
+
+
+def _grad_close(got, ref, what, tol=1e-5, outliers=2e-3):
+    """Gradients of |d - s| jump by 2/N where d - s changes sign and by a finite-difference step where the sample
+    crosses a pixel boundary, so a rounding-level difference in the projection (bmm summation order) flips a few
+    pixels: all but a fraction `outliers` of the pixels must agree to tol * max|ref|, and the flips must be bounded."""
+    got, ref = np.asarray(got, np.float64), np.asarray(ref, np.float64)
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref)
+    bad = err > tol * scale
+    assert bad.mean() <= outliers, f"{what}: {bad.mean():.2e} of the pixels differ (max err {err.max():.3e}, scale {scale:.3e})"
+    assert err.max() <= 4.5 * scale, f"{what}: outlier of {err.max():.3e} against scale {scale:.3e}"
+
+
+@pytest.mark.parametrize("name,clamp", (("noclamp", -1), ("clamp", 0.1), ("tight", 0.004)))
+def test_depth_similarity_golden(tx, golden, name, clamp):
+    """Against values and autograd gradients of the reference's own ProjectionDepthSimilarityLoss on CPU torch
+    (tests/golden/make_golden_geometric.py)."""
+    g = golden("geometric")
+    d0, d1 = cu(g["depth0"]).requires_grad_(True), cu(g["depth1"]).requires_grad_(True)
+    val = tx.projection_depth_similarity_loss(d0, d1, cu(g["R0"]), cu(g["t0"]), cu(g["R1"]), cu(g["t1"]), cu(g["K"]), cu(g["ray"]), clamp)
+    val.backward()
+    assert abs(float(val) - float(g[name + "_val"])) <= 1e-5 * abs(float(g[name + "_val"]))
+    _grad_close(d0.grad.cpu().numpy(), g[name + "_g0"], name + " grad depth0", outliers=5e-3)
+    _grad_close(d1.grad.cpu().numpy(), g[name + "_g1"], name + " grad depth1", outliers=5e-3)
+
+
+def test_depth_similarity_vs_torch_full_size(tx):
+    """Batch 4 at 480x640 against the torch restatement of networks.py:436-503 on the same GPU, value and both
+    gradients, plus the upstream-gradient scaling and the ray table helper."""
+    from connecting_the_dots_b200 import synth
+    d = synth.make_depth_pairs(4, 480, 640, seed=3)
+    ray = tx.projection_rays(d["Ki"], 480, 640).to(DEV)
+    args = [cu(d[k]) for k in ("R0", "t0", "R1", "t1", "K")]
+    for clamp in (-1, 0.1):
+        a0, a1 = cu(d["depth0"]).requires_grad_(True), cu(d["depth1"]).requires_grad_(True)
+        b0, b1 = cu(d["depth0"]).requires_grad_(True), cu(d["depth1"]).requires_grad_(True)
+        val = tx.projection_depth_similarity_loss(a0, a1, *args, ray, clamp)
+        ref = _ref_depth_similarity(b0, b1, *args, ray, clamp)
+        (3.0 * val).backward()
+        (3.0 * ref).backward()
+        assert abs(float(val) - float(ref)) <= 1e-5 * abs(float(ref)), (float(val), float(ref))
+        _grad_close(a0.grad.cpu().numpy(), b0.grad.cpu().numpy(), "grad depth0 clamp %g" % clamp)
+        _grad_close(a1.grad.cpu().numpy(), b1.grad.cpu().numpy(), "grad depth1 clamp %g" % clamp)
+
+
+def test_depth_similarity_identity_and_errors(tx):
+    """Identical frames and poses: every pixel projects onto itself, and what is left is the reference's own
+    sampling convention (grid normalised with W-1, sampled with align_corners=False: position x*W/(W-1) - 0.5) --
+    small against the depth and equal to the torch restatement.  Shape / device / dtype violations raise like the
+    other ops."""
+    from connecting_the_dots_b200 import synth
+    d = synth.make_depth_pairs(2, 48, 64, seed=5)
+    ray = tx.projection_rays(d["Ki"], 48, 64).to(DEV)
+    dep = cu(d["depth0"])
+    val = tx.projection_depth_similarity_loss(dep, dep.clone(), cu(d["R0"]), cu(d["t0"]), cu(d["R0"]), cu(d["t0"]), cu(d["K"]), ray, 0.1)
+    ref = _ref_depth_similarity(dep, dep.clone(), cu(d["R0"]), cu(d["t0"]), cu(d["R0"]), cu(d["t0"]), cu(d["K"]), ray, 0.1)
+    assert abs(float(val) - float(ref)) <= 1e-5 * float(ref)
+    assert float(val) <= 0.2 * float(dep.mean())
+    with pytest.raises(RuntimeError):
+        tx.projection_depth_similarity_loss(dep.cpu(), dep.cpu(), cu(d["R0"]), cu(d["t0"]), cu(d["R0"]), cu(d["t0"]), cu(d["K"]), ray, 0.1)
+    with pytest.raises(RuntimeError):
+        tx.projection_depth_similarity_loss(dep, dep[:, :, :-1].contiguous(), cu(d["R0"]), cu(d["t0"]), cu(d["R0"]), cu(d["t0"]), cu(d["K"]), ray, 0.1)
+    with pytest.raises((RuntimeError, NotImplementedError)):
+        tx.projection_depth_similarity_loss(dep.double(), dep.double(), cu(d["R0"]), cu(d["t0"]), cu(d["R0"]), cu(d["t0"]), cu(d["K"]), ray, 0.1)

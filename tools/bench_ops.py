@@ -57,7 +57,7 @@ def timeit(fn, iters, warmup=5, nrep=NREP):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--only", default="calib,photometric,warp,pyramid,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
+    ap.add_argument("--only", default="calib,photometric,warp,pyramid,geometric,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -163,6 +163,56 @@ def main():
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.iters
         add("pyramid_4_levels_stream_launches", ms, ms, 44 * px_all, px=px_all, extra={"note": "the same 12 calls issued one by one from Python"})
+    if "geometric" in only:
+        # ProjectionDepthSimilarityLoss.tforward (both directions, loss + both depth gradients) for B
+        # frame pairs: two kernels, against the reference's own torch formulation (4 bmm, 2 grid_sample, ~20 elementwise
+        # kernels and their autograd twins) on the same GPU
+        gd = synth.make_depth_pairs(B, H, W, seed=0)
+        cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+        ray = tx.projection_rays(gd["Ki"], H, W).to(dev)
+        g = {k: cu(v) for k, v in gd.items()}
+        deps = [(cu(np.roll(gd["depth0"], 5 * s, axis=3)), cu(np.roll(gd["depth1"], 5 * s, axis=3))) for s in range(NS)]
+        g0s = [torch.empty(B, 1, H, W, device=dev) for _ in range(NS)]
+        g1s = [torch.empty(B, 1, H, W, device=dev) for _ in range(NS)]
+        sums = torch.zeros(2, 2, device=dev)
+        scale = 1.0 / npx
+        def f(i, st):
+            d0, d1 = deps[i % NS]
+            a0, a1 = g0s[i % NS], g1s[i % NS]
+            a1.zero_()
+            _lib.call("ctd_depth_similarity_f32", d0.data_ptr(), d1.data_ptr(), ray.data_ptr(), g["K"].data_ptr(), g["R0"].data_ptr(),
+                      g["t0"].data_ptr(), g["R1"].data_ptr(), g["t1"].data_ptr(), a0.data_ptr(), a1.data_ptr(), sums[0].data_ptr(),
+                      B, H, W, 0.1, scale, 0, st)
+            _lib.call("ctd_depth_similarity_f32", d1.data_ptr(), d0.data_ptr(), ray.data_ptr(), g["K"].data_ptr(), g["R1"].data_ptr(),
+                      g["t1"].data_ptr(), g["R0"].data_ptr(), g["t0"].data_ptr(), a1.data_ptr(), a0.data_ptr(), sums[1].data_ptr(),
+                      B, H, W, 0.1, scale, 1, st)
+        # per direction: depthA + grad depthA (8 B) and the gather / scatter on depthB, grad depthB (8 B); + the memset
+        add("depth_similarity_both_directions", *timeit(f, args.iters), (2 * 16 + 4) * npx,
+            extra={"note": "ProjectionDepthSimilarityLoss.tforward, value + gradients w.r.t. both depth maps, clamp 0.1; Mpix/s counts one frame of each pair"})
+        import time
+        def torch_ref():
+            d0, d1 = deps[0][0].clone().requires_grad_(True), deps[0][1].clone().requires_grad_(True)
+            def fwd(dA, dB, RA, tA, RB, tB):
+                xyz = dA.reshape(B, -1, 1) * ray.reshape(1, -1, 3)
+                xyz = torch.bmm(xyz - tA.reshape(B, 1, 3), RA)
+                xyz = torch.bmm(xyz, RB.transpose(1, 2)) + tB.reshape(B, 1, 3)
+                uv = torch.bmm(xyz, g["K"].reshape(1, 3, 3).transpose(1, 2).expand(B, -1, -1))
+                d = uv[:, :, 2:3]
+                uv = uv[:, :, :2] / (torch.nn.functional.relu(d) + 1e-12)
+                gr = torch.stack((2 * (uv[..., 0] / (W - 1) - 0.5), 2 * (uv[..., 1] / (H - 1) - 0.5)), -1).view(-1, H, W, 2)
+                s_ = torch.nn.functional.grid_sample(dB, gr, padding_mode="border", align_corners=False)
+                return torch.clamp(torch.abs(d.view(-1) - s_.view(-1)), 0, 0.1).mean()
+            (fwd(d0, d1, g["R0"], g["t0"], g["R1"], g["t1"]) + fwd(d1, d0, g["R1"], g["t1"], g["R0"], g["t0"])).backward()
+        for _ in range(3):
+            torch_ref()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            torch_ref()
+        e1.record()
+        torch.cuda.synchronize()
+        res["ops"]["depth_similarity_both_directions"]["torch_eager_ms"] = e0.elapsed_time(e1) / 10
     if "lcn" in only:
         def f(i, st):
             d = sets[i % NS]
