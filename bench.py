@@ -50,6 +50,25 @@ BYTES_PER_PX = {"lcn_fwd": 12, "sad_fwd": 12, "sad_bwd": 16, "census_sad_fwd": 1
                 "masked_sums": 8}
 
 
+
+# The contract is ONE JSON line on stdout.  Libraries write to file descriptor 1 behind Python's back (NCCL prints
+# its version banner there at the first collective), so fd 1 is pointed at stderr for the whole run and the line
+# goes out through a private duplicate of the original stdout.
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit_line(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    print(json.dumps(line), file=out, flush=True)
+
 def measured_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -197,7 +216,7 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "Mpix/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit_line(line)
 
 
 def cpu_baseline_leg(n_images=4):
@@ -469,7 +488,7 @@ def run_b200_arm(args, rank, world, local_rank):
                                "note": "same chain, forward and backward of both losses as separate calls (torch autograd path)"}}
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_leg()
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -485,6 +504,7 @@ def main():
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling (BASELINE configs[4]): split this many images over the ranks instead of 8 per GPU")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
