@@ -252,6 +252,27 @@ def depth_similarity(depth0, depth1, ray, K, R0, t0, R1, t1, clamp=-1.0):
     return sums, g0, g1
 
 
+def disparity_loss(disp, edge=None):
+    """model/networks.py:395-411 (DisparityLoss.tforward) in one kernel.  disp [B,1,H,W]; edge [B,1,H,W] or None.
+    Returns (sums [2] = {sum of the per-pixel loss, pixel count}, grad_disp, grad_edge or None) with the gradients
+    of the mean."""
+    _check_input_cuda(disp, "disp")
+    _check(disp.dim() == 4 and disp.size(1) == 1, "disp has to be B x 1 x H x W")
+    _check(disp.dtype == torch.float32, "disparity_loss is float32 only")
+    if edge is not None:
+        _check_input_cuda(edge, "edge")
+        _check(edge.shape == disp.shape and edge.dtype == torch.float32, "edge has to match disp")
+        _same(disp, edge, "disp", "edge")
+    B, _, H, W = disp.shape
+    sums = torch.empty(2, dtype=torch.float32, device=disp.device)
+    gd = torch.empty_like(disp)
+    ge = torch.empty_like(disp) if edge is not None else None
+    with torch.cuda.device(disp.device):
+        _lib.call("ctd_disparity_loss_f32", disp.data_ptr(), edge.data_ptr() if edge is not None else 0, gd.data_ptr(),
+                  ge.data_ptr() if ge is not None else 0, sums.data_ptr(), B, H, W, 1.0 / max(B * H * W, 1), _stream(disp))
+    return sums, gd, ge
+
+
 def lcn_forward(x, radius, epsilon):
     """model/networks.py:523-533 as one kernel.  x [N,1,H,W] -> (lcn, std), both [N,1,H,W]."""
     _check_input_cuda(x, "x")

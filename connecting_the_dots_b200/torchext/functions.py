@@ -232,6 +232,32 @@ def projection_rays(Ki, im_height, im_width):
     return torch.from_numpy(ray.reshape(-1, 3).astype(np.float32))
 
 
+class DisparityLossFunction(torch.autograd.Function):
+    """DisparityLoss.tforward (model/networks.py:395-411, called at model/exp_synph.py:116): 5x5 Sobel gradient
+    magnitude of the disparity under a two-Laplacian mixture weighted by the edge probability (or, without an edge
+    map, its clamped mean).  One kernel computes the loss and the gradients w.r.t. disp and edge; autograd's backward
+    is a scalar multiply."""
+
+    @staticmethod
+    def forward(ctx, disp, edge):
+        if not disp.is_cuda:
+            raise RuntimeError("torchext.disparity_loss: connecting_the_dots_b200 has no CPU implementation")
+        sums, gd, ge = ext_cuda.disparity_loss(disp.detach().contiguous(), None if edge is None else edge.detach().contiguous())
+        ctx.has_edge = edge is not None
+        ctx.save_for_backward(gd, ge if ge is not None else gd)
+        return sums[0] / sums[1]
+
+    @staticmethod
+    def backward(ctx, g):
+        gd, ge = ctx.saved_tensors
+        return gd * g, (ge * g if ctx.has_edge else None)
+
+
+def disparity_loss(disp, edge=None):
+    """DisparityLoss()(disp, edge) of the reference (model/networks.py:380-412)."""
+    return DisparityLossFunction.apply(disp, edge)
+
+
 class LCNFunction(torch.autograd.Function):
     """Fused local contrast normalisation (model/networks.py:507-533); forward only -- in the
     reference the gradient flows to an input image nobody reads (exp_synph.py:80-91)."""

@@ -104,6 +104,14 @@ int ctd_depth_similarity_f32(const float* depthA, const float* depthB, const flo
                              float* grad_depthA, float* grad_depthB, float* sums2, int64_t B, int64_t H, int64_t W,
                              float clamp, float scale, int direct_accumulate, ctd_stream_t stream);
 
+/* ---- disparity (smoothness / edge) loss of the stage-1 trainer: model/networks.py:380-412 (DisparityLoss.tforward)
+ * over the 5x5 Sobel filter with replicate padding (networks.py:537-565).  disp, edge, grad_disp, grad_edge
+ * [B,1,H,W], DEVICE pointers; edge may be NULL (the reference's edge=None branch: mean of the clamped gradient
+ * magnitude).  sums2[0] = sum of the per-pixel loss, sums2[1] = B*H*W, deterministic; the gradients are those of
+ * sums2[0] * scale, fully overwritten, no atomics.  grad_disp / grad_edge may be NULL. */
+int ctd_disparity_loss_f32(const float* disp, const float* edge, float* grad_disp, float* grad_edge, float* sums2,
+                           int64_t B, int64_t H, int64_t W, float scale, ctd_stream_t stream);
+
 /* ---- XCorrVolFunctor: ext.h:120-191, ext_cuda.cpp:73-86 (xcorrvol_cuda).  The reference has no
  * batch dimension; here in0,in1 are [B,C,H,W] and out is [B,D,H,W] (B=1 is the reference call). */
 int ctd_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,

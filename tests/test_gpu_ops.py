@@ -774,3 +774,62 @@ def test_depth_similarity_identity_and_errors(tx):
         tx.projection_depth_similarity_loss(dep, dep[:, :, :-1].contiguous(), cu(d["R0"]), cu(d["t0"]), cu(d["R0"]), cu(d["t0"]), cu(d["K"]), ray, 0.1)
     with pytest.raises((RuntimeError, NotImplementedError)):
         tx.projection_depth_similarity_loss(dep.double(), dep.double(), cu(d["R0"]), cu(d["t0"]), cu(d["R0"]), cu(d["t0"]), cu(d["K"]), ray, 0.1)
+
+
+# ---------------------------------------------------------------- disparity loss
+def _ref_disparity_loss(disp, edge):
+    """model/networks.py:395-411 over SobelFilter (networks.py:537-565) restated with torch ops, any device."""
+    kx = torch.tensor([[-5, -4, 0, 4, 5], [-8, -10, 0, 10, 8], [-10, -20, 0, 20, 10], [-8, -10, 0, 10, 8], [-5, -4, 0, 4, 5]],
+                      dtype=torch.float64, device=disp.device) / 240.0
+    x = torch.nn.functional.pad(disp, (2, 2, 2, 2), "replicate")
+    gx = torch.nn.functional.conv2d(x, kx.float()[None, None])
+    gy = torch.nn.functional.conv2d(x, kx.t().contiguous().float()[None, None])
+    grad = torch.sqrt(gx ** 2 + gy ** 2 + 1e-8)
+    if edge is None:
+        return torch.mean(torch.clamp(grad, 0, 1.0))
+    b0, b1 = 0.0503428816795, 1.07274045944
+    pdf = (1 - edge) / b0 * torch.exp(-torch.abs(grad) / b0) + edge / b1 * torch.exp(-torch.abs(grad) / b1)
+    return torch.mean(-torch.log(pdf.clamp(min=1e-4)))
+
+
+@pytest.mark.parametrize("name", ("edge", "noedge"))
+def test_disparity_loss_golden(tx, golden, name):
+    """Against the reference's own DisparityLoss / SobelFilter on CPU torch (tests/golden/make_golden_geometric.py)."""
+    g = golden("disparity_loss")
+    d = cu(g["disp"]).requires_grad_(True)
+    e = cu(g["edge"]).requires_grad_(True) if name == "edge" else None
+    val = tx.disparity_loss(d, e)
+    val.backward()
+    ref = float(g[name + "_val"])
+    assert abs(float(val.detach()) - ref) <= 1e-5 * abs(ref), (float(val.detach()), ref)
+    assert_close(d.grad.cpu().numpy(), g[name + "_gdisp"], tol=2e-5, what=name + " grad disp")
+    if e is not None:
+        assert_close(e.grad.cpu().numpy(), g[name + "_gedge"], tol=2e-5, what=name + " grad edge")
+
+
+def test_disparity_loss_vs_torch_full_size(tx):
+    """Batch 8 at 480x640 (a full-resolution disparity map and a sigmoid edge map, exp_synph.py:115-116) against the
+    torch restatement on the same GPU; odd sizes that do not fill the 32x32 tiles; upstream-gradient scaling."""
+    from connecting_the_dots_b200 import synth
+    torch.backends.cudnn.allow_tf32 = False  # the reference's two convolutions in fp32, not TF32 (cuDNN's default)
+    for (B, H, W) in ((8, 480, 640), (3, 61, 83)):
+        base = np.stack([synth.smooth_disparity(np.random.RandomState(60 + n), H, W) for n in range(B)])[:, None].astype(np.float32)
+        base = base / 8.0 if H < 100 else base
+        rng = np.random.RandomState(B)
+        edge = (1.0 / (1.0 + np.exp(-rng.randn(B, 1, H, W) * 2))).astype(np.float32)
+        for use_edge in (True, False):
+            a, b = cu(base).requires_grad_(True), cu(base).requires_grad_(True)
+            ea = cu(edge).requires_grad_(True) if use_edge else None
+            eb = cu(edge).requires_grad_(True) if use_edge else None
+            val = tx.disparity_loss(a, ea)
+            ref = _ref_disparity_loss(b, eb)
+            (2.5 * val).backward()
+            (2.5 * ref).backward()
+            assert abs(float(val.detach()) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+            assert_close(a.grad.cpu().numpy(), b.grad.cpu().numpy(), tol=2e-5, what="grad disp %dx%d edge=%s" % (H, W, use_edge))
+            if use_edge:
+                assert_close(ea.grad.cpu().numpy(), eb.grad.cpu().numpy(), tol=2e-5, what="grad edge %dx%d" % (H, W))
+    with pytest.raises(RuntimeError):
+        tx.disparity_loss(cu(base).cpu(), None)
+    with pytest.raises(RuntimeError):
+        tx.disparity_loss(cu(base), cu(edge)[:, :, :-1].contiguous())

@@ -57,7 +57,7 @@ def timeit(fn, iters, warmup=5, nrep=NREP):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--only", default="calib,photometric,warp,pyramid,geometric,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
+    ap.add_argument("--only", default="calib,photometric,warp,pyramid,geometric,disparity,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -213,6 +213,39 @@ def main():
         e1.record()
         torch.cuda.synchronize()
         res["ops"]["depth_similarity_both_directions"]["torch_eager_ms"] = e0.elapsed_time(e1) / 10
+    if "disparity" in only:
+        # DisparityLoss.tforward (5x5 Sobel, two-Laplacian mixture weighted by the edge map) with the
+        # gradients w.r.t. disp and edge, one kernel, against the reference's torch formulation on the same GPU
+        disps = [torch.from_numpy(np.ascontiguousarray(np.roll(base["disp"], 5 * s, axis=3))).to(dev) for s in range(NS)]
+        edges = [torch.sigmoid(torch.randn(B, 1, H, W, device=dev, generator=torch.Generator(device=dev).manual_seed(s))) for s in range(NS)]
+        gds = [torch.empty(B, 1, H, W, device=dev) for _ in range(NS)]
+        ges = [torch.empty(B, 1, H, W, device=dev) for _ in range(NS)]
+        sums = torch.zeros(2, device=dev)
+        def f(i, st):
+            _lib.call("ctd_disparity_loss_f32", disps[i % NS].data_ptr(), edges[i % NS].data_ptr(), gds[i % NS].data_ptr(), ges[i % NS].data_ptr(),
+                      sums.data_ptr(), B, H, W, 1.0 / npx, st)
+        add("disparity_loss_fwd_bwd", *timeit(f, args.iters), 16 * npx,
+            extra={"note": "DisparityLoss.tforward with edge map: loss + gradients w.r.t. disp and edge"})
+        kx = torch.tensor([[-5, -4, 0, 4, 5], [-8, -10, 0, 10, 8], [-10, -20, 0, 20, 10], [-8, -10, 0, 10, 8], [-5, -4, 0, 4, 5]],
+                          dtype=torch.float32, device=dev) / 240.0
+        def torch_ref():
+            d, e = disps[0].clone().requires_grad_(True), edges[0].clone().requires_grad_(True)
+            x = torch.nn.functional.pad(d, (2, 2, 2, 2), "replicate")
+            gx = torch.nn.functional.conv2d(x, kx[None, None])
+            gy = torch.nn.functional.conv2d(x, kx.t().contiguous()[None, None])
+            grad = torch.sqrt(gx ** 2 + gy ** 2 + 1e-8)
+            pdf = (1 - e) / 0.0503428816795 * torch.exp(-torch.abs(grad) / 0.0503428816795) + e / 1.07274045944 * torch.exp(-torch.abs(grad) / 1.07274045944)
+            torch.mean(-torch.log(pdf.clamp(min=1e-4))).backward()
+        for _ in range(3):
+            torch_ref()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            torch_ref()
+        e1.record()
+        torch.cuda.synchronize()
+        res["ops"]["disparity_loss_fwd_bwd"]["torch_eager_ms"] = e0.elapsed_time(e1) / 10
     if "lcn" in only:
         def f(i, st):
             d = sets[i % NS]

@@ -11,7 +11,7 @@ mkdir -p gpurun_out
 python bench.py > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err || exit 1
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref_$tag.json 2>> gpurun_out/bench_$tag.err
 python tools/bench_ops.py --batch 8 > gpurun_out/ops_${tag}_b8.json 2> gpurun_out/ops_${tag}_b8.err
-python tools/bench_ops.py --batch 64 --only calib,photometric,warp,geometric,lcn,xcorrvol,reduce > gpurun_out/ops_${tag}_b64.json 2> gpurun_out/ops_${tag}_b64.err
+python tools/bench_ops.py --batch 64 --only calib,photometric,warp,geometric,disparity,lcn,xcorrvol,reduce > gpurun_out/ops_${tag}_b64.json 2> gpurun_out/ops_${tag}_b64.err
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_$tag.csv \
   python bench.py --steps 2 --warmup 1 > gpurun_out/ncu_bench_$tag.log 2>&1
 ncu --set full --import-source on --clock-control none -c 16 -f -o gpurun_out/prof_$tag python tools/profile_target.py > gpurun_out/ncu_prof_$tag.log 2>&1
