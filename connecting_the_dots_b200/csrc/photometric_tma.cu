@@ -7,8 +7,9 @@
 // memory ring, completion signalled on an mbarrier.  The next tile's loads are in flight while the
 // current tile is filtered, so load latency, arithmetic and stores overlap inside every SM instead of
 // every CTA serialising load -> sync -> compute -> store.  TMA zero-fills out-of-image elements: that is
-// exactly the backward's zero padding; the forward's replicate clamp is an index remap when reading the
-// staged tile (rows always, columns only in tiles that touch the left/right border).
+// exactly the backward's zero padding; the forward's replicate clamp is an index remap of the staged rows, and
+// in tiles that touch the left/right border the (at most 4 + 4) box columns outside the image are overwritten
+// with the border column once per tile (patch_clamped_columns).
 #include <algorithm>
 
 #include "ctd_common.cuh"
@@ -78,6 +79,33 @@ __device__ __forceinline__ void vsum2(const float4* v, float4& o0, float4& o1) {
   o1 = add4(mid, v[9]);
 }
 
+// Tiles touching the left / right image border: TMA zero-fills the box columns outside the image; the forward's
+// replicate clamp wants the first / last image column there.  Patching those (at most 4 + 4) columns of the staged
+// es / ta boxes once per tile lets every thread take the 128-bit path below (an index remap per tap costs a border
+// tile three times the shared-memory instructions, and two of five tile columns of a 640-wide image are border
+// tiles).  Block-uniform; ends with a barrier.
+template <typename SM>
+__device__ __forceinline__ void patch_clamped_columns(SM& S, int s, int x0, int W, int tid) {
+  const int lo = R9 - x0;          // box column of image column 0 (4 in the first tile column)
+  const int hi = W - 1 - (x0 - R9);  // box column of image column W - 1
+  for (int i = tid; i < TB_H * 2 * R9; i += 256) {
+    const int r = i / (2 * R9), k = i % (2 * R9);
+    if (k < R9) {
+      if (k < lo) {
+        S.es[s][r][k] = S.es[s][r][lo];
+        S.ta[s][r][k] = S.ta[s][r][lo];
+      }
+    } else {
+      const int cc = hi + 1 + (k - R9);
+      if (cc < TB_W) {
+        S.es[s][r][cc] = S.es[s][r][hi];
+        S.ta[s][r][cc] = S.ta[s][r][hi];
+      }
+    }
+  }
+  __syncthreads();
+}
+
 template <int TYPE>
 __global__ void __launch_bounds__(256, 3)
 photo_fwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_constant__ CUtensorMap map_ta,
@@ -110,28 +138,17 @@ photo_fwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_cons
     const TileCoord c = tile_coord(t, tiles_x, tiles_y);
     mbar_wait(&S.full[s], (it >> 1) & 1);
     // phase A: horizontal 9-sums of phi(es - ta), replicate clamp by index remap
-    const bool xborder = c.x0 == 0 || c.x0 + TT_W + R9 > W;
+    if (c.x0 == 0 || c.x0 + TT_W + R9 > W) patch_clamped_columns(S, s, c.x0, W, tid);  // block-uniform
     for (int i = tid; i < TB_H * (TT_W / 4); i += 256) {
       const int r = i / (TT_W / 4), q = i % (TT_W / 4);
       const int rr = clampi(c.y0 - R9 + r, 0, H - 1) - (c.y0 - R9);
-      const float* er = &S.es[s][rr][0];
-      const float* tr = &S.ta[s][rr][0];
       float e[12], v[12];
-      if (!xborder) {
-        ld12(e, er + 4 * q);
-        ld12(v, tr + 4 * q);
+      ld12(e, &S.es[s][rr][4 * q]);
+      ld12(v, &S.ta[s][rr][4 * q]);
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          const float d = e[j] - v[j];
-          v[j] = TYPE == 0 ? d * d : fabsf(d);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          const int cc = clampi(c.x0 - R9 + 4 * q + j, 0, W - 1) - (c.x0 - R9);
-          const float d = er[cc] - tr[cc];
-          v[j] = TYPE == 0 ? d * d : fabsf(d);
-        }
+      for (int j = 0; j < 12; ++j) {
+        const float d = e[j] - v[j];
+        v[j] = TYPE == 0 ? d * d : fabsf(d);
       }
       *reinterpret_cast<float4*>(&S.hs[r][4 * q]) = hsum9x4(v);
     }
@@ -289,30 +306,19 @@ photo_fwd_bwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_
     }
     const TileCoord c = tile_coord(t, tiles_x, tiles_y);
     mbar_wait(&S.full[s], (it >> 1) & 1);
-    const bool xborder = c.x0 == 0 || c.x0 + TT_W + R9 > W;
+    if (c.x0 == 0 || c.x0 + TT_W + R9 > W) patch_clamped_columns(S, s, c.x0, W, tid);  // block-uniform
     const int xr = W - 1 - c.x0;  // tile-local column of the last image column
     for (int i = tid; i < TB_H * (TT_W / 4); i += 256) {
       const int r = i / (TT_W / 4), q = i % (TT_W / 4);
-      // forward: replicate clamp by index remap (rows always, columns only in tiles touching the left/right border)
+      // forward: replicate clamp -- rows by index remap, columns patched into the staged boxes above
       const int rr = clampi(c.y0 - R9 + r, 0, H - 1) - (c.y0 - R9);
-      const float* er = &S.es[s][rr][0];
-      const float* tr = &S.ta[s][rr][0];
       float e[12], v[12];
-      if (!xborder) {
-        ld12(e, er + 4 * q);
-        ld12(v, tr + 4 * q);
+      ld12(e, &S.es[s][rr][4 * q]);
+      ld12(v, &S.ta[s][rr][4 * q]);
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          const float d = e[j] - v[j];
-          v[j] = TYPE == 0 ? d * d : fabsf(d);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          const int cc = clampi(c.x0 - R9 + 4 * q + j, 0, W - 1) - (c.x0 - R9);
-          const float d = er[cc] - tr[cc];
-          v[j] = TYPE == 0 ? d * d : fabsf(d);
-        }
+      for (int j = 0; j < 12; ++j) {
+        const float d = e[j] - v[j];
+        v[j] = TYPE == 0 ? d * d : fabsf(d);
       }
       *reinterpret_cast<float4*>(&S.hf[r][4 * q]) = hsum9x4(v);
       // backward: zero-padded grad_out, first / last image column collects the clamp multiplicity
