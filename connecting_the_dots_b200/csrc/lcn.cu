@@ -13,6 +13,7 @@
 // each thread produces 4 adjacent pixels with a sliding fp64 window, then the per-pixel epilogue and
 // 128-bit stores of lcn and std.
 #include <algorithm>
+#include <type_traits>
 
 #include "ctd_common.cuh"
 #include "ctd_tma.cuh"
@@ -219,25 +220,31 @@ lcn_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ lc
     int x0, y0, img;
     coords(t, x0, y0, img);
     mbar_wait(&S.full[s], (it >> 1) & 1);
-    // vertical pass: thread c owns needed column c (image column x0 - R + c), 0 <= c < 128 + 2R
+    // vertical pass: thread c owns needed column c (image column x0 - R + c), 0 <= c < 128 + 2R.  Tiles whose box
+    // rows all lie inside the image (all but the first and last tile row) skip the per-row reflection remap.
     if (tid < LTM_W + 2 * R) {
       const int cc = reflect(x0 - R + tid, W) - (x0 - LTM_XOFF);
-      double p1[K + 1], p2[K + 1];  // ring of prefix sums: slot j % (K+1) holds prefix through box row j-1
-      p1[0] = 0.0;
-      p2[0] = 0.0;
+      auto vertical = [&](auto interior_tag) {
+        constexpr bool INTERIOR = decltype(interior_tag)::value;
+        double p1[K + 1], p2[K + 1];  // ring of prefix sums: slot j % (K+1) holds prefix through box row j-1
+        p1[0] = 0.0;
+        p2[0] = 0.0;
 #pragma unroll
-      for (int j = 0; j < LTM_H + 2 * R; ++j) {  // box rows y0 - R + j
-        const int rr = reflect(y0 - R + j, H) - (y0 - LTM_R);
-        const float v = S.x[s][rr][cc];
-        const int cur = (j + 1) % (K + 1), prev = j % (K + 1);
-        p1[cur] = p1[prev] + (double)v;
-        p2[cur] = p2[prev] + (double)(v * v);
-        if (j >= 2 * R) {  // rows j-2R .. j form the window of output row j - 2R
-          const int old = (j + 1 + 1) % (K + 1);  // slot holding the prefix through row j - 2R - 1
-          S.v1[j - 2 * R][lcol36(tid)] = p1[cur] - p1[old];
-          S.v2[j - 2 * R][lcol36(tid)] = p2[cur] - p2[old];
+        for (int j = 0; j < LTM_H + 2 * R; ++j) {  // box rows y0 - R + j
+          const int rr = INTERIOR ? j + (LTM_R - R) : reflect(y0 - R + j, H) - (y0 - LTM_R);
+          const float v = S.x[s][rr][cc];
+          const int cur = (j + 1) % (K + 1), prev = j % (K + 1);
+          p1[cur] = p1[prev] + (double)v;
+          p2[cur] = p2[prev] + (double)(v * v);
+          if (j >= 2 * R) {  // rows j-2R .. j form the window of output row j - 2R
+            const int old = (j + 1 + 1) % (K + 1);  // slot holding the prefix through row j - 2R - 1
+            S.v1[j - 2 * R][lcol36(tid)] = p1[cur] - p1[old];
+            S.v2[j - 2 * R][lcol36(tid)] = p2[cur] - p2[old];
+          }
         }
-      }
+      };
+      if (y0 >= R && y0 + LTM_H + R <= H) vertical(std::true_type{});
+      else vertical(std::false_type{});
     }
     __syncthreads();
     // horizontal pass + epilogue: 16 rows x 32 quads, two items per thread
