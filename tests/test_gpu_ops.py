@@ -690,25 +690,7 @@ def test_loss_path_is_cuda_graph_capturable(tx):
 
 
 # ---------------------------------------------------------------- geometric loss
-def _ref_depth_similarity(depth0, depth1, R0, t0, R1, t1, K, ray, clamp):
-    """model/networks.py:436-503 restated with torch ops (same calls in the same order), any device."""
-    B, _, H, W = depth0.shape
-
-    def fwd(dA, dB, RA, tA, RB, tB):
-        xyz = dA.reshape(B, -1, 1) * ray.reshape(1, -1, 3)              # unproject, networks.py:448
-        xyz = torch.bmm(xyz - tA.reshape(B, 1, 3), RA)                   # transform, networks.py:436-442
-        xyz = torch.bmm(xyz, RB.transpose(1, 2)) + tB.reshape(B, 1, 3)   # project, networks.py:456-457
-        uv = torch.bmm(xyz, K.reshape(1, 3, 3).transpose(1, 2).expand(B, -1, -1))
-        d = uv[:, :, 2:3]
-        uv = uv[:, :, :2] / (torch.nn.functional.relu(d) + 1e-12)
-        g = torch.stack((2 * (uv[..., 0] / (W - 1) - 0.5), 2 * (uv[..., 1] / (H - 1) - 0.5)), -1).view(-1, H, W, 2)
-        s = torch.nn.functional.grid_sample(dB, g, padding_mode="border", align_corners=False)
-        diff = torch.abs(d.view(-1) - s.view(-1))
-        if clamp > 0:
-            diff = torch.clamp(diff, 0, clamp)
-        return diff.mean()
-
-    return fwd(depth0, depth1, R0, t0, R1, t1) + fwd(depth1, depth0, R1, t1, R0, t0)
+from losses_torch import depth_similarity as _ref_depth_similarity, disparity_loss as _ref_disparity_loss  # noqa: E402
 
 
 def _grad_close(got, ref, what, tol=1e-5, outliers=2e-3):
@@ -777,21 +759,6 @@ def test_depth_similarity_identity_and_errors(tx):
 
 
 # ---------------------------------------------------------------- disparity loss
-def _ref_disparity_loss(disp, edge):
-    """model/networks.py:395-411 over SobelFilter (networks.py:537-565) restated with torch ops, any device."""
-    kx = torch.tensor([[-5, -4, 0, 4, 5], [-8, -10, 0, 10, 8], [-10, -20, 0, 20, 10], [-8, -10, 0, 10, 8], [-5, -4, 0, 4, 5]],
-                      dtype=torch.float64, device=disp.device) / 240.0
-    x = torch.nn.functional.pad(disp, (2, 2, 2, 2), "replicate")
-    gx = torch.nn.functional.conv2d(x, kx.float()[None, None])
-    gy = torch.nn.functional.conv2d(x, kx.t().contiguous().float()[None, None])
-    grad = torch.sqrt(gx ** 2 + gy ** 2 + 1e-8)
-    if edge is None:
-        return torch.mean(torch.clamp(grad, 0, 1.0))
-    b0, b1 = 0.0503428816795, 1.07274045944
-    pdf = (1 - edge) / b0 * torch.exp(-torch.abs(grad) / b0) + edge / b1 * torch.exp(-torch.abs(grad) / b1)
-    return torch.mean(-torch.log(pdf.clamp(min=1e-4)))
-
-
 @pytest.mark.parametrize("name", ("edge", "noedge"))
 def test_disparity_loss_golden(tx, golden, name):
     """Against the reference's own DisparityLoss / SobelFilter on CPU torch (tests/golden/make_golden_geometric.py)."""

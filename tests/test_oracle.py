@@ -9,6 +9,7 @@ import pytest
 import torch
 
 import oracle
+from conftest import assert_close
 
 TYPES = ("mse", "sad", "census_mse", "census_sad")
 
@@ -157,3 +158,37 @@ def test_photometric_matches_reference_torch_restatement():
         w = w.reshape(2, -1, 10, 12).sum(1, keepdim=True).numpy() / bs ** 2
         got = oracle.photometric_loss_forward(es, ta, bs, name, eps)
         assert np.abs(got - w).max() <= 2e-6 * max(1.0, np.abs(w).max()), name
+
+
+# ---------------------------------------------------------------- next-row losses
+@pytest.mark.parametrize("name,clamp", (("noclamp", -1), ("clamp", 0.1), ("tight", 0.004)))
+def test_depth_similarity_restatement_golden(golden, name, clamp):
+    """oracle/losses_torch.depth_similarity against the reference's own ProjectionDepthSimilarityLoss (golden)."""
+    import torch
+    import losses_torch
+    g = golden("geometric")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    d0, d1 = t(g["depth0"]).requires_grad_(True), t(g["depth1"]).requires_grad_(True)
+    val = losses_torch.depth_similarity(d0, d1, t(g["R0"]), t(g["t0"]), t(g["R1"]), t(g["t1"]), t(g["K"]), t(g["ray"]), clamp)
+    val.backward()
+    assert abs(float(val.detach()) - float(g[name + "_val"])) <= 1e-6 * abs(float(g[name + "_val"]))
+    assert_close(d0.grad.numpy(), g[name + "_g0"], tol=1e-6, what=name + " grad depth0")
+    assert_close(d1.grad.numpy(), g[name + "_g1"], tol=1e-6, what=name + " grad depth1")
+
+
+@pytest.mark.parametrize("name", ("edge", "noedge"))
+def test_disparity_loss_restatement_golden(golden, name):
+    """oracle/losses_torch.disparity_loss against the reference's own DisparityLoss / SobelFilter (golden)."""
+    import torch
+    import losses_torch
+    g = golden("disparity_loss")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a))
+    d = t(g["disp"]).requires_grad_(True)
+    e = t(g["edge"]).requires_grad_(True) if name == "edge" else None
+    val = losses_torch.disparity_loss(d, e)
+    val.backward()
+    assert abs(float(val.detach()) - float(g[name + "_val"])) <= 1e-6 * abs(float(g[name + "_val"]))
+    assert_close(d.grad.numpy(), g[name + "_gdisp"], tol=1e-6, what=name + " grad disp")
+    if e is not None:
+        assert_close(e.grad.numpy(), g[name + "_gedge"], tol=1e-6, what=name + " grad edge")
+
