@@ -401,6 +401,20 @@ __device__ __forceinline__ void xs_hsum(const float* p, float* o) {
   }
 }
 
+// The same four window sums straight from the factors (block 9): products and additions fused into FMA chains --
+// 19 instructions instead of 12 multiplies + 15 additions, every o[k] still a sum of exactly its own window's
+// products (nothing is subtracted), each product rounded at most once less than before.  b points at the factor of a[0].
+__device__ __forceinline__ void xs_hsum9_fma(const float* a, const float* b, float* o) {
+  const float m0 = fmaf(a[5], b[5], fmaf(a[4], b[4], a[3] * b[3]));
+  const float m1 = fmaf(a[8], b[8], fmaf(a[7], b[7], a[6] * b[6]));
+  const float mid = m0 + m1;
+  const float l12 = fmaf(a[1], b[1], a[2] * b[2]), r910 = fmaf(a[9], b[9], a[10] * b[10]);
+  o[0] = mid + fmaf(a[0], b[0], l12);
+  o[1] = mid + fmaf(a[9], b[9], l12);
+  o[2] = mid + fmaf(a[2], b[2], r910);
+  o[3] = mid + fmaf(a[11], b[11], r910);
+}
+
 // TD = disparities per thread.  TD = 4: 128 threads, 246 registers (suffix sums of 16 outputs), 8 warps/SM.
 // TD = 2: 256 threads, half the suffix registers, 16 warps/SM -- the tile and the arithmetic per output are the
 // same, the resident warps double (the kernel is latency-bound), the in1 row is read as seven 64-bit loads.
@@ -523,6 +537,71 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
   for (int e = 0; e < NST; ++e)
     if (e < nrows) issue(e);
   __syncwarp();
+  // the pieces of a row step shared by the two vertical-sum schemes below
+  auto load_ab = [&](int r, float (&a)[12], float (&bv)[16]) {
+    const float4* ap = reinterpret_cast<const float4*>(arow + r * XS_AW);
+    const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
+    a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    a[8] = a2.x; a[9] = a2.y; a[10] = a2.z; a[11] = a2.w;
+    if (TD == 4) {
+      const float4* bp = reinterpret_cast<const float4*>(brow + r * XS_BW);
+      const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+      bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
+      bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+      bv[8] = b2.x; bv[9] = b2.y; bv[10] = b2.z; bv[11] = b2.w;
+      bv[12] = b3.x; bv[13] = b3.y; bv[14] = b3.z; bv[15] = b3.w;
+    } else {
+      const float2* bp = reinterpret_cast<const float2*>(brow + r * XS_BW);
+#pragma unroll
+      for (int q = 0; q < 7; ++q) {
+        const float2 v2 = bp[q];
+        bv[2 * q] = v2.x;
+        bv[2 * q + 1] = v2.y;
+      }
+    }
+  };
+  auto hsum_row = [&](const float (&a)[12], const float (&bv)[16], int dl, float (&hs)[4]) {
+    if (BS == 9) {
+      xs_hsum9_fma(a, &bv[BOFF - dl], hs);
+    } else {
+      float p[12];
+#pragma unroll
+      for (int t = 4 - R; t <= 7 + R; ++t) p[t] = a[t] * bv[BOFF - dl + t];
+      xs_hsum<BS>(p, hs);
+    }
+  };
+  // conflict-free 128-bit reads of output row e's statistics (stage st), once per row
+  auto load_stats = [&](int st, int e, float2 (&wst)[4], float2 (&ust)[8]) {
+    mbar_wait(&ring.full[st], (uint32_t)(e / NST) & 1u);
+    const float4* wp = reinterpret_cast<const float4*>(&ring.w[st][4 * lane]);
+    const float4* up = reinterpret_cast<const float4*>(&ring.u[st][4 * lane]);
+    const float4 w01 = wp[0], w23 = wp[1], u01 = up[0], u23 = up[1], u45 = up[2], u67 = up[3];
+    wst[0] = make_float2(w01.x, w01.y); wst[1] = make_float2(w01.z, w01.w);
+    wst[2] = make_float2(w23.x, w23.y); wst[3] = make_float2(w23.z, w23.w);
+    ust[0] = make_float2(u01.x, u01.y); ust[1] = make_float2(u01.z, u01.w);
+    ust[2] = make_float2(u23.x, u23.y); ust[3] = make_float2(u23.z, u23.w);
+    ust[4] = make_float2(u45.x, u45.y); ust[5] = make_float2(u45.z, u45.w);
+    ust[6] = make_float2(u67.x, u67.y); ust[7] = make_float2(u67.z, u67.w);
+  };
+  // lane's four columns: {N*mu0, sd0} pairs; its eight u positions (x - dbase - 4 ..): {mu1, sd1} pairs, of which
+  // disparity dbase + dl uses positions 4 + k - dl
+  auto emit_out = [&](int dl, const float (&S)[4], const float2 (&wst)[4], const float2 (&ust)[8]) {
+    float v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 ws_ = wst[k], us_ = ust[4 + k - dl];
+      v[k] = fmaf(-ws_.x, us_.x, S[k]) * rcp_approx(fmaf(ws_.y, us_.y, 1e-8f));  // untrusted outputs: see fix-up
+    }
+    float* dst = orow + dl * dstride;
+    if (VEC) {
+      if (xin && dl < ndl) __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (x + k < W && dl < ndl) dst[k] = v[k];
+    }
+  };
   // One block of BS tile rows.  FIRST: the tile's first block only fills the vertical state (its last row
   // completes the first window); afterwards every row emits one output row.  Returns true when the tile's
   // last output row has been written.
@@ -535,50 +614,15 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
       const int e = r - 2 * R;                  // output row of the tile completed by tile row r
       if (emit && e >= nrows) return true;      // warp-uniform
       float a[12], bv[16];
-      {
-        const float4* ap = reinterpret_cast<const float4*>(arow + r * XS_AW);
-        const float4 a0 = ap[0], a1 = ap[1], a2 = ap[2];
-        a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w;
-        a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
-        a[8] = a2.x; a[9] = a2.y; a[10] = a2.z; a[11] = a2.w;
-        if (TD == 4) {
-          const float4* bp = reinterpret_cast<const float4*>(brow + r * XS_BW);
-          const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-          bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w;
-          bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
-          bv[8] = b2.x; bv[9] = b2.y; bv[10] = b2.z; bv[11] = b2.w;
-          bv[12] = b3.x; bv[13] = b3.y; bv[14] = b3.z; bv[15] = b3.w;
-        } else {
-          const float2* bp = reinterpret_cast<const float2*>(brow + r * XS_BW);
-#pragma unroll
-          for (int q = 0; q < 7; ++q) {
-            const float2 v2 = bp[q];
-            bv[2 * q] = v2.x;
-            bv[2 * q + 1] = v2.y;
-          }
-        }
-      }
+      load_ab(r, a, bv);
       // stage of this row's statistics: static when NST divides BS
       const int st = (BS % NST == 0) ? (j + NST * BS - 2 * R) % NST : e % NST;
       float2 wst[4], ust[8];
-      if (emit) {  // conflict-free 128-bit reads of this row's statistics, once per row
-        mbar_wait(&ring.full[st], (uint32_t)(e / NST) & 1u);
-        const float4* wp = reinterpret_cast<const float4*>(&ring.w[st][4 * lane]);
-        const float4* up = reinterpret_cast<const float4*>(&ring.u[st][4 * lane]);
-        const float4 w01 = wp[0], w23 = wp[1], u01 = up[0], u23 = up[1], u45 = up[2], u67 = up[3];
-        wst[0] = make_float2(w01.x, w01.y); wst[1] = make_float2(w01.z, w01.w);
-        wst[2] = make_float2(w23.x, w23.y); wst[3] = make_float2(w23.z, w23.w);
-        ust[0] = make_float2(u01.x, u01.y); ust[1] = make_float2(u01.z, u01.w);
-        ust[2] = make_float2(u23.x, u23.y); ust[3] = make_float2(u23.z, u23.w);
-        ust[4] = make_float2(u45.x, u45.y); ust[5] = make_float2(u45.z, u45.w);
-        ust[6] = make_float2(u67.x, u67.y); ust[7] = make_float2(u67.z, u67.w);
-      }
+      if (emit) load_stats(st, e, wst, ust);
 #pragma unroll
       for (int dl = 0; dl < TD; ++dl) {
-        float p[12], hs[4], S[4];
-#pragma unroll
-        for (int t = 4 - R; t <= 7 + R; ++t) p[t] = a[t] * bv[BOFF - dl + t];
-        xs_hsum<BS>(p, hs);
+        float hs[4], S[4];
+        hsum_row(a, bv, dl, hs);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           F[dl][k] = j == 0 ? hs[k] : F[dl][k] + hs[k];  // a block starts with its first row (no 0 + x)
@@ -592,24 +636,7 @@ xcorr_sep_kernel(const float* __restrict__ in0, const float* __restrict__ in1, f
             for (int i = BS - 3; i >= 0; --i) suf[i][dl][k] += suf[i + 1][dl][k];
           }
         }
-        if (emit) {
-          // lane's four columns: {N*mu0, sd0} pairs; its eight u positions (x - dbase - 4 ..): {mu1, sd1} pairs, of
-          // which disparity dbase + dl uses positions 4 + k - dl
-          float v[4];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 ws_ = wst[k], us_ = ust[4 + k - dl];
-            v[k] = fmaf(-ws_.x, us_.x, S[k]) * rcp_approx(fmaf(ws_.y, us_.y, 1e-8f));  // untrusted outputs: see fix-up
-          }
-          float* dst = orow + dl * dstride;
-          if (VEC) {
-            if (xin && dl < ndl) __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
-          } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              if (x + k < W && dl < ndl) dst[k] = v[k];
-          }
-        }
+        if (emit) emit_out(dl, S, wst, ust);
       }
       if (emit) {  // every lane has read this stage: hand it to the row NST further down
         __syncwarp();
