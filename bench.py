@@ -452,7 +452,12 @@ def run_b200_arm(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps * 1e3
-    h2d = (1 + 3 + 3) * npx * 4
+    # bytes per step as the library counted them for the last batch: the two photometric calls read the same es / ta /
+    # grad_out host buffers, which a batch uploads once (ctd_host_begin_batch, include/ctd_b200.h)
+    copied, saved = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    L.ctd_host_batch_stats(ctypes.byref(copied), ctypes.byref(saved))
+    h2d = int(copied.value)
+    assert h2d + int(saved.value) == (1 + 3 + 3) * npx * 4, "host API byte accounting"
     d2h = (2 + 2 + 2) * npx * 4
 
     if rank != 0:
@@ -490,7 +495,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": npx_global / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "api": "ctd_host_begin_batch; ctd_host_lcn_f32 + 2x ctd_host_photometric_fwd_bwd_f32; ctd_host_end_batch -- pinned host buffers"},
+                    "api": "ctd_host_begin_batch; ctd_host_lcn_f32 + 2x ctd_host_photometric_fwd_bwd_f32; ctd_host_end_batch -- pinned host buffers; the batch uploads es / ta / grad_out, which both loss calls read, once"},
             "roofline": roofline, "ops": ops,
             "separate_calls": {"ms_per_step": sep_ms_per_step, "value": npx_global / (sep_ms_per_step * 1e-3) / 1e6, "steps": sep_steps,
                                "note": "same chain, forward and backward of both losses as separate calls (torch autograd path)"}}

@@ -48,6 +48,7 @@ _RESTYPES = {
     "ctd_launch_count": (ctypes.c_uint64, []),
     "ctd_masked_sums_workspace_bytes": (ctypes.c_int64, []),
     "ctd_host_release": (None, []),
+    "ctd_host_batch_stats": (None, [_ptr, _ptr]),
 }
 EXPORTS = sorted(list(SIGNATURES) + list(_RESTYPES))
 

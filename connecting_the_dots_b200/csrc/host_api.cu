@@ -27,6 +27,35 @@ struct Workspace {
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_run[MAX_CHUNKS] = {};
   bool deferred = false;  // inside ctd_host_begin_batch / ctd_host_end_batch
   size_t used = 0;        // bytes of the workspace owned by calls still in flight (deferred mode: no reuse)
+  // Uploads of the open batch: an input (same host address, same size) that several calls of a batch read -- the
+  // image pair of the sad and the census loss, the gradient weights -- crosses the bus once.  Later calls find the
+  // device copy of the earlier one; their kernels are enqueued on the same compute stream after the kernel that
+  // waited for that upload, so no extra dependency is needed.  Host inputs must not change while a batch is open.
+  struct Upload {
+    const void* host;
+    size_t bytes;
+    char* dev;
+  };
+  std::vector<Upload> uploads;
+  uint64_t h2d_bytes = 0, h2d_saved = 0;  // statistics since ctd_host_begin_batch (ctd_host_batch_stats)
+
+  // device address holding `bytes` bytes of `host`: the earlier upload of this batch, or `dst` after enqueuing the copy
+  int upload(cudaStream_t st, char* dst, const void* host, size_t bytes, char** dev) {
+    *dev = dst;
+    if (bytes == 0) return CTD_OK;
+    if (deferred) {
+      for (const Upload& u : uploads)
+        if (u.host == host && u.bytes == bytes) {
+          *dev = u.dev;
+          h2d_saved += bytes;
+          return CTD_OK;
+        }
+      uploads.push_back({host, bytes, dst});
+    }
+    h2d_bytes += bytes;
+    CTD_CUDA(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, st));
+    return CTD_OK;
+  }
 
   // workspace of one call: `bytes` fresh bytes behind everything still in flight
   int carve(size_t bytes, char** out) {
@@ -68,6 +97,7 @@ struct Workspace {
         base = nullptr;
         cap = 0;
         used = 0;
+        uploads.clear();  // the device copies of this batch's earlier uploads went with the old workspace
       }
       const size_t want = bytes + bytes / 8 + (1 << 20);
       if (cudaMalloc(&base, want) != cudaSuccess) {
@@ -127,9 +157,12 @@ static inline int chunk_count(int64_t B, bool deferred) {
 
 using namespace ctd;
 
-#define H2D(dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, g_ws.stream))
+#define H2D(dst, src, bytes)                                                                   \
+  do {                                                                                         \
+    g_ws.h2d_bytes += (bytes);                                                                 \
+    CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, g_ws.stream));     \
+  } while (0)
 #define D2H(dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, g_ws.stream))
-#define H2D_ON(st, dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, (st)))
 #define D2H_ON(st, dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (st)))
 #define RUN(call)                    \
   do {                               \
@@ -153,22 +186,20 @@ static int photometric_host(const float* es, const float* ta, const float* go, f
   for (int c = 0; c < nch; ++c) {
     const int64_t i0 = chunk_lo(B, nch, c), nb = chunk_lo(B, nch, c + 1) - i0;
     const size_t oi = (size_t)i0 * in_img, oo = (size_t)i0 * out_img;
-    if (in_img) {
-      H2D_ON(g_ws.s_in, b + o_es + oi, (const char*)es + oi, nb * in_img);
-      H2D_ON(g_ws.s_in, b + o_ta + oi, (const char*)ta + oi, nb * in_img);
-    }
-    if (gi && out_img) H2D_ON(g_ws.s_in, b + o_go + oo, (const char*)go + oo, nb * out_img);
+    char *d_es = nullptr, *d_ta = nullptr, *d_go = nullptr;
+    RUN(g_ws.upload(g_ws.s_in, b + o_es + oi, (const char*)es + oi, nb * in_img, &d_es));
+    RUN(g_ws.upload(g_ws.s_in, b + o_ta + oi, (const char*)ta + oi, nb * in_img, &d_ta));
+    RUN(g_ws.upload(g_ws.s_in, b + o_go + oo, (const char*)go + oo, gi ? nb * out_img : 0, &d_go));
     CTD_CUDA(cudaEventRecord(g_ws.ev_in[c], g_ws.s_in));
     CTD_CUDA(cudaStreamWaitEvent(g_ws.stream, g_ws.ev_in[c], 0));
     if (out && gi)
-      RUN(ctd_photometric_fwd_bwd_f32((float*)(b + o_es + oi), (float*)(b + o_ta + oi), (float*)(b + o_go + oo),
-                                      (float*)(b + o_out + oo), (float*)(b + o_gi + oi), nb, C, H, W, bs, type, eps, g_ws.stream));
+      RUN(ctd_photometric_fwd_bwd_f32((float*)d_es, (float*)d_ta, (float*)d_go, (float*)(b + o_out + oo), (float*)(b + o_gi + oi),
+                                      nb, C, H, W, bs, type, eps, g_ws.stream));
     else if (out)
-      RUN(ctd_photometric_fwd_f32((float*)(b + o_es + oi), (float*)(b + o_ta + oi), (float*)(b + o_out + oo), nb, C, H, W, bs,
-                                  type, eps, g_ws.stream));
+      RUN(ctd_photometric_fwd_f32((float*)d_es, (float*)d_ta, (float*)(b + o_out + oo), nb, C, H, W, bs, type, eps, g_ws.stream));
     else if (gi)
-      RUN(ctd_photometric_bwd_f32((float*)(b + o_es + oi), (float*)(b + o_ta + oi), (float*)(b + o_go + oo),
-                                  (float*)(b + o_gi + oi), nb, C, H, W, bs, type, eps, g_ws.stream));
+      RUN(ctd_photometric_bwd_f32((float*)d_es, (float*)d_ta, (float*)d_go, (float*)(b + o_gi + oi), nb, C, H, W, bs, type, eps,
+                                  g_ws.stream));
     CTD_CUDA(cudaEventRecord(g_ws.ev_run[c], g_ws.stream));
     CTD_CUDA(cudaStreamWaitEvent(g_ws.s_out, g_ws.ev_run[c], 0));
     if (out && out_img) D2H_ON(g_ws.s_out, (char*)out + oo, b + o_out + oo, nb * out_img);
@@ -210,13 +241,12 @@ CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out
   for (int c = 0; c < nch; ++c) {
     const int64_t i0 = chunk_lo(B, nch, c), nb = chunk_lo(B, nch, c + 1) - i0;
     const size_t oi = (size_t)i0 * in_img, ov = (size_t)i0 * out_img;
-    if (in_img) {
-      H2D_ON(g_ws.s_in, b + o0 + oi, (const char*)in0 + oi, nb * in_img);
-      H2D_ON(g_ws.s_in, b + o1 + oi, (const char*)in1 + oi, nb * in_img);
-    }
+    char *d0 = nullptr, *d1 = nullptr;
+    RUN(g_ws.upload(g_ws.s_in, b + o0 + oi, (const char*)in0 + oi, nb * in_img, &d0));
+    RUN(g_ws.upload(g_ws.s_in, b + o1 + oi, (const char*)in1 + oi, nb * in_img, &d1));
     CTD_CUDA(cudaEventRecord(g_ws.ev_in[c], g_ws.s_in));
     CTD_CUDA(cudaStreamWaitEvent(g_ws.stream, g_ws.ev_in[c], 0));
-    RUN(ctd_xcorrvol_f32((float*)(b + o0 + oi), (float*)(b + o1 + oi), (float*)(b + oo + ov), nb, C, H, W, D, bs, g_ws.stream));
+    RUN(ctd_xcorrvol_f32((float*)d0, (float*)d1, (float*)(b + oo + ov), nb, C, H, W, D, bs, g_ws.stream));
     CTD_CUDA(cudaEventRecord(g_ws.ev_run[c], g_ws.stream));
     CTD_CUDA(cudaStreamWaitEvent(g_ws.s_out, g_ws.ev_run[c], 0));
     if (out_img) D2H_ON(g_ws.s_out, (char*)out + ov, b + oo + ov, nb * out_img);
@@ -299,10 +329,11 @@ CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, i
   for (int c = 0; c < nch; ++c) {
     const int64_t i0 = chunk_lo(N, nch, c), nb = chunk_lo(N, nch, c + 1) - i0;
     const size_t o = (size_t)i0 * img;
-    H2D_ON(g_ws.s_in, b + ox + o, (const char*)x + o, nb * img);
+    char* d_x = nullptr;
+    RUN(g_ws.upload(g_ws.s_in, b + ox + o, (const char*)x + o, nb * img, &d_x));
     CTD_CUDA(cudaEventRecord(g_ws.ev_in[c], g_ws.s_in));
     CTD_CUDA(cudaStreamWaitEvent(g_ws.stream, g_ws.ev_in[c], 0));
-    RUN(ctd_lcn_f32((float*)(b + ox + o), (float*)(b + ol + o), (float*)(b + os + o), nb, H, W, r, eps, g_ws.stream));
+    RUN(ctd_lcn_f32((float*)d_x, (float*)(b + ol + o), (float*)(b + os + o), nb, H, W, r, eps, g_ws.stream));
     CTD_CUDA(cudaEventRecord(g_ws.ev_run[c], g_ws.stream));
     CTD_CUDA(cudaStreamWaitEvent(g_ws.s_out, g_ws.ev_run[c], 0));
     D2H_ON(g_ws.s_out, (char*)lcn + o, b + ol + o, nb * img);
@@ -315,6 +346,8 @@ CTD_API int ctd_host_begin_batch(void) {
   CTD_REQUIRE(!g_ws.deferred, "ctd_host_begin_batch: a batch is already open on this thread");
   g_ws.deferred = true;
   g_ws.used = 0;
+  g_ws.uploads.clear();
+  g_ws.h2d_bytes = g_ws.h2d_saved = 0;
   return CTD_OK;
 }
 
@@ -322,12 +355,18 @@ CTD_API int ctd_host_end_batch(void) {
   CTD_REQUIRE(g_ws.deferred, "ctd_host_end_batch: no batch is open on this thread");
   g_ws.deferred = false;
   g_ws.used = 0;
+  g_ws.uploads.clear();
   if (g_ws.stream) {
     CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
     CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
     CTD_CUDA(cudaStreamSynchronize(g_ws.s_in));
   }
   return CTD_OK;
+}
+
+CTD_API void ctd_host_batch_stats(uint64_t* h2d_bytes, uint64_t* h2d_bytes_saved) {
+  if (h2d_bytes) *h2d_bytes = g_ws.h2d_bytes;
+  if (h2d_bytes_saved) *h2d_bytes_saved = g_ws.h2d_saved;
 }
 
 CTD_API void ctd_host_release(void) {

@@ -171,9 +171,13 @@ int ctd_host_lcn_f32(const float* x, float* lcn, float* std, int64_t N, int64_t 
                      int radius, float epsilon);
 /* Deferred mode for the calling thread: between begin and end the ctd_host_* calls only enqueue their copies and
  * kernels (they return at once), so consecutive calls overlap on the bus; every result is in host memory when
- * ctd_host_end_batch() returns.  Input buffers must stay untouched, output buffers unread, until then. */
+ * ctd_host_end_batch() returns.  Input buffers must stay untouched, output buffers unread, until then.
+ * An input that several photometric calls of one batch read (same host address and size: the image pair of two
+ * loss types, the gradient weights) is uploaded once. */
 int ctd_host_begin_batch(void);
 int ctd_host_end_batch(void);
+/* host-to-device bytes the calling thread's current (or last) batch copied, and bytes it did not have to copy again */
+void ctd_host_batch_stats(uint64_t* h2d_bytes, uint64_t* h2d_bytes_saved);
 /* release the calling thread's staging workspace */
 void ctd_host_release(void);
 

@@ -601,6 +601,11 @@ def test_host_api_deferred_batch_matches_synchronous_calls(tx):
         _lib.call("ctd_host_proj_nn_f32", P(xyz), P(xyz), P(K), P(idx), B, H, W, 3)
         if deferred:
             _lib.call("ctd_host_end_batch")
+            # the second photometric call reads the same es / ta / grad_out: they crossed the bus once
+            copied, saved = ctypes.c_uint64(0), ctypes.c_uint64(0)
+            _lib.lib().ctd_host_batch_stats(ctypes.byref(copied), ctypes.byref(saved))
+            plane = B * H * W * 4
+            assert saved.value == 3 * plane and copied.value >= 4 * plane
         res.append((lcn, std, o1, g1, o3, g3, idx))
     for a, b in zip(*res):
         assert np.array_equal(a, b)
