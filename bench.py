@@ -318,6 +318,21 @@ def run_b200_arm(args, rank, world, local_rank):
         i += 1
         mark(i)
 
+    # The two losses both wait for LCN's std but not for each other: as graph branches the memory-bound sad kernel
+    # runs beside the issue-bound census kernel instead of in front of it.
+    side = torch.cuda.Stream(dev)
+
+    def launch_forked(d, cs):
+        p = {n: t.data_ptr() for n, t in d.items()}
+        _lib.call("ctd_lcn_f32", p["im"], p["lcn"], p["std"], B, H, W, LCN_R, LCN_EPS, cs.cuda_stream)
+        side.wait_stream(cs)
+        first, second = (side, cs) if args.fork == 1 else (cs, side)
+        _lib.call("ctd_photometric_fwd_bwd_masked_f32", p["es"], p["ta"], p["go"], p["std"], p["out_sad"], p["gi_sad"], p["sums"],
+                  B, 1, H, W, BS, 1, EPS, first.cuda_stream)
+        _lib.call("ctd_photometric_fwd_bwd_masked_f32", p["es"], p["ta"], p["go"], p["std"], p["out_cs"], p["gi_cs"], p["sums"] + 8,
+                  B, 1, H, W, BS, 3, EPS, second.cuda_stream)
+        cs.wait_stream(side)
+
     # One CUDA graph per buffer set: the step's kernels plus event-record nodes between the ops, so neither
     # `value` nor the per-op durations contain host launch latency (the kernels are 10-200 us long).
     set_events = [[torch.cuda.Event(enable_timing=True, external=True) for _ in range(len(OPS) + 1)] for _ in range(NSETS)]
@@ -340,7 +355,10 @@ def run_b200_arm(args, rank, world, local_rank):
                 g = torch.cuda.CUDAGraph()  # the same step without the event-record nodes
                 with torch.cuda.graph(g):
                     cs = torch.cuda.current_stream(dev)
-                    launch_chain(sets[si], cs.cuda_stream, lambda i: None)
+                    if args.fork:
+                        launch_forked(sets[si], cs)
+                    else:
+                        launch_chain(sets[si], cs.cuda_stream, lambda i: None)
                 plain_graphs.append(g)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -490,7 +508,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD if not strong else WORKLOAD.replace("configs[1]", "configs[4] (batch %d split over the ranks)" % args.global_batch).replace("batch 8 per GPU", "batch %d on rank 0" % B),
                        "batch_per_gpu": B, "global_batch": args.global_batch if strong else B * world, "height": H, "width": W,
                        "l2_policy": "inputs and outputs rotate over %d buffer sets, %.0f MB touched > 126 MB L2" % (NSETS, footprint_mb),
-                       "launch": "one CUDA graph replay per step; the last replay of each buffer set in the timed region also carries the event-record nodes the per-op durations are read from" if use_graph else "stream launches",
+                       "launch": ("one CUDA graph replay per step" + (", the sad and the census loss as parallel branches behind LCN (both need its std, not each other)" if args.fork else "") + "; the last replay of each buffer set in the timed region is the plain chain with the event-record nodes the per-op durations are read from") if use_graph else "stream launches",
                        "parallelism": "batch-sharded x%d, one packed 4-float NCCL all-reduce per step" % world},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": npx_global / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
@@ -514,6 +532,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time plain stream launches instead of CUDA graph replays")
+    ap.add_argument("--fork", type=int, default=1,
+                    help="the two losses as parallel graph branches behind LCN (1: sad on the side stream, 2: census; 0: one chain)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="strong scaling (BASELINE configs[4]): split this many images over the ranks instead of 8 per GPU")
     args = ap.parse_args()
