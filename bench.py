@@ -382,14 +382,25 @@ def run_b200_arm(args, rank, world, local_rank):
     # An event-record node between two kernels costs a few microseconds of serialisation, so only the LAST replay of
     # each buffer set inside the timed region (the one whose timestamps are read) carries them; every other step
     # replays the same kernels without event nodes.
+    # The all-reduce of a step's four loss scalars runs on its own stream: it waits for the step's kernels, and the
+    # next step (another buffer set) does not wait for it -- only the next use of the SAME buffer set does.  The timed
+    # region ends with a synchronisation of both streams, so every reduction is inside it.
+    comm_stream = torch.cuda.Stream(dev) if world > 1 else None
+    comm_done = [None] * NSETS
+
     def step(k, timed_events=True):
         si = k % NSETS
+        if world > 1 and comm_done[si] is not None:
+            stream.wait_event(comm_done[si])  # the previous reduction of this set's sums has finished
         if use_graph:
             (graphs if timed_events else plain_graphs)[si].replay()
         else:
             launch_chain(sets[si], st, lambda i: set_events[si][i].record(stream))
         if world > 1:
-            dist.all_reduce(sets[si]["sums"])  # 4 floats: the only inter-GPU traffic of the path
+            comm_stream.wait_stream(stream)
+            with torch.cuda.stream(comm_stream):
+                dist.all_reduce(sets[si]["sums"])  # 4 floats: the only inter-GPU traffic of the path
+                comm_done[si] = comm_stream.record_event()
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -410,6 +421,8 @@ def run_b200_arm(args, rank, world, local_rank):
     e0.record(stream)
     for k in range(args.steps):
         step(k, timed_events=k >= args.steps - NSETS)
+    if world > 1:
+        stream.wait_stream(comm_stream)  # the timed region contains every reduction
     e1.record(stream)
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
@@ -509,7 +522,7 @@ def run_b200_arm(args, rank, world, local_rank):
                        "batch_per_gpu": B, "global_batch": args.global_batch if strong else B * world, "height": H, "width": W,
                        "l2_policy": "inputs and outputs rotate over %d buffer sets, %.0f MB touched > 126 MB L2" % (NSETS, footprint_mb),
                        "launch": ("one CUDA graph replay per step" + (", the sad and the census loss as parallel branches behind LCN (both need its std, not each other)" if args.fork else "") + "; the last replay of each buffer set in the timed region is the plain chain with the event-record nodes the per-op durations are read from") if use_graph else "stream launches",
-                       "parallelism": "batch-sharded x%d, one packed 4-float NCCL all-reduce per step" % world},
+                       "parallelism": "batch-sharded x%d, one packed 4-float NCCL all-reduce per step on a side stream (overlaps the next step)" % world},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": npx_global / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
