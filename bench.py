@@ -388,19 +388,38 @@ def run_b200_arm(args, rank, world, local_rank):
     comm_stream = torch.cuda.Stream(dev) if world > 1 else None
     comm_done = [None] * NSETS
 
+    # Steps are independent batches (they rotate over NSETS buffer sets), so consecutive steps are replayed on
+    # alternating streams: the next step's LCN and sad kernels fill the SM slots the census kernel of the previous step
+    # frees in its last wave.  A buffer set is always used by the same stream (NSETS is even), so its steps stay ordered.
+    # The evented replays at the end of the timed region run alone on the main stream (everything before them is
+    # waited for), so the per-op durations are those of an undisturbed chain.
+    lanes = [stream] + [torch.cuda.Stream(dev) for _ in range(max(args.pipeline, 1) - 1)] if use_graph else [stream]
+    assert NSETS % len(lanes) == 0
+
     def step(k, timed_events=True):
         si = k % NSETS
+        lane = stream if timed_events else lanes[k % len(lanes)]
+        if timed_events:
+            for other in lanes[1:]:
+                stream.wait_stream(other)
         if world > 1 and comm_done[si] is not None:
-            stream.wait_event(comm_done[si])  # the previous reduction of this set's sums has finished
+            lane.wait_event(comm_done[si])  # the previous reduction of this set's sums has finished
         if use_graph:
-            (graphs if timed_events else plain_graphs)[si].replay()
+            with torch.cuda.stream(lane):
+                (graphs if timed_events else plain_graphs)[si].replay()
         else:
             launch_chain(sets[si], st, lambda i: set_events[si][i].record(stream))
         if world > 1:
-            comm_stream.wait_stream(stream)
+            comm_stream.wait_stream(lane)
             with torch.cuda.stream(comm_stream):
                 dist.all_reduce(sets[si]["sums"])  # 4 floats: the only inter-GPU traffic of the path
                 comm_done[si] = comm_stream.record_event()
+
+    def join_lanes():
+        for other in lanes[1:]:
+            stream.wait_stream(other)
+        if world > 1:
+            stream.wait_stream(comm_stream)  # the timed region contains every reduction
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -419,10 +438,11 @@ def run_b200_arm(args, rank, world, local_rank):
         time.sleep(0.3)
     sync_all()
     e0.record(stream)
+    for other in lanes[1:]:
+        other.wait_stream(stream)  # no lane starts before the timed region does
     for k in range(args.steps):
         step(k, timed_events=k >= args.steps - NSETS)
-    if world > 1:
-        stream.wait_stream(comm_stream)  # the timed region contains every reduction
+    join_lanes()
     e1.record(stream)
     sync_all()
     clocks = sampler.stop() if rank == 0 else None
@@ -521,7 +541,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "config": {"workload": WORKLOAD if not strong else WORKLOAD.replace("configs[1]", "configs[4] (batch %d split over the ranks)" % args.global_batch).replace("batch 8 per GPU", "batch %d on rank 0" % B),
                        "batch_per_gpu": B, "global_batch": args.global_batch if strong else B * world, "height": H, "width": W,
                        "l2_policy": "inputs and outputs rotate over %d buffer sets, %.0f MB touched > 126 MB L2" % (NSETS, footprint_mb),
-                       "launch": ("one CUDA graph replay per step" + (", the sad and the census loss as parallel branches behind LCN (both need its std, not each other)" if args.fork else "") + "; the last replay of each buffer set in the timed region is the plain chain with the event-record nodes the per-op durations are read from") if use_graph else "stream launches",
+                       "launch": ("one CUDA graph replay per step" + (", consecutive steps on %d alternating streams" % len(lanes) if len(lanes) > 1 else "") + (", the sad and the census loss as parallel branches behind LCN (both need its std, not each other)" if args.fork else "") + "; the last replay of each buffer set in the timed region is the plain chain with the event-record nodes the per-op durations are read from") if use_graph else "stream launches",
                        "parallelism": "batch-sharded x%d, one packed 4-float NCCL all-reduce per step on a side stream (overlaps the next step)" % world},
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": npx_global / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
@@ -545,6 +565,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time plain stream launches instead of CUDA graph replays")
+    ap.add_argument("--pipeline", type=int, default=2, help="steps in flight (replayed on alternating streams); 1 = one stream")
     ap.add_argument("--fork", type=int, default=1,
                     help="the two losses as parallel graph branches behind LCN (1: sad on the side stream, 2: census; 0: one chain)")
     ap.add_argument("--global-batch", type=int, default=0,

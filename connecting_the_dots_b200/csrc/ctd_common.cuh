@@ -22,7 +22,7 @@ void scratch_free(void* p, cudaStream_t st);
 
 // Ticket + block-partial workspace for kernels that end with finish_masked_sums (see ctd_core.cu); false when the
 // grid has more than MS_MAXBLK blocks (callers then take scratch memory and zero the ticket themselves).
-constexpr int MS_SLOTS = 16, MS_MAXBLK = 4096;
+constexpr int MS_SLOTS = 64, MS_MAXBLK = 4096;  // 64 slots: kernels of a few CUDA graphs replayed on concurrent streams never share one
 bool masked_sums_slot(size_t nblocks, unsigned** ticket, double** partials);
 
 // Check the launch that was just issued (no synchronisation, like a normal async API).
