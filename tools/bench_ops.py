@@ -12,6 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))  # losses_torch: comparison legs only (torch formulation of the reference)
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -189,20 +190,10 @@ def main():
         # per direction: depthA + grad depthA (8 B) and the gather / scatter on depthB, grad depthB (8 B); + the memset
         add("depth_similarity_both_directions", *timeit(f, args.iters), (2 * 16 + 4) * npx,
             extra={"note": "ProjectionDepthSimilarityLoss.tforward, value + gradients w.r.t. both depth maps, clamp 0.1; Mpix/s counts one frame of each pair"})
-        import time
+        import losses_torch  # oracle/: the reference's torch formulation, used here only as the comparison leg
         def torch_ref():
             d0, d1 = deps[0][0].clone().requires_grad_(True), deps[0][1].clone().requires_grad_(True)
-            def fwd(dA, dB, RA, tA, RB, tB):
-                xyz = dA.reshape(B, -1, 1) * ray.reshape(1, -1, 3)
-                xyz = torch.bmm(xyz - tA.reshape(B, 1, 3), RA)
-                xyz = torch.bmm(xyz, RB.transpose(1, 2)) + tB.reshape(B, 1, 3)
-                uv = torch.bmm(xyz, g["K"].reshape(1, 3, 3).transpose(1, 2).expand(B, -1, -1))
-                d = uv[:, :, 2:3]
-                uv = uv[:, :, :2] / (torch.nn.functional.relu(d) + 1e-12)
-                gr = torch.stack((2 * (uv[..., 0] / (W - 1) - 0.5), 2 * (uv[..., 1] / (H - 1) - 0.5)), -1).view(-1, H, W, 2)
-                s_ = torch.nn.functional.grid_sample(dB, gr, padding_mode="border", align_corners=False)
-                return torch.clamp(torch.abs(d.view(-1) - s_.view(-1)), 0, 0.1).mean()
-            (fwd(d0, d1, g["R0"], g["t0"], g["R1"], g["t1"]) + fwd(d1, d0, g["R1"], g["t1"], g["R0"], g["t0"])).backward()
+            losses_torch.depth_similarity(d0, d1, g["R0"], g["t0"], g["R1"], g["t1"], g["K"], ray, 0.1).backward()
         for _ in range(3):
             torch_ref()
         torch.cuda.synchronize()
@@ -226,16 +217,11 @@ def main():
                       sums.data_ptr(), B, H, W, 1.0 / npx, st)
         add("disparity_loss_fwd_bwd", *timeit(f, args.iters), 16 * npx,
             extra={"note": "DisparityLoss.tforward with edge map: loss + gradients w.r.t. disp and edge"})
-        kx = torch.tensor([[-5, -4, 0, 4, 5], [-8, -10, 0, 10, 8], [-10, -20, 0, 20, 10], [-8, -10, 0, 10, 8], [-5, -4, 0, 4, 5]],
-                          dtype=torch.float32, device=dev) / 240.0
+        import losses_torch  # oracle/: comparison leg only
+        torch.backends.cudnn.allow_tf32 = False  # the reference's convolutions in fp32 (what the kernel is checked against)
         def torch_ref():
             d, e = disps[0].clone().requires_grad_(True), edges[0].clone().requires_grad_(True)
-            x = torch.nn.functional.pad(d, (2, 2, 2, 2), "replicate")
-            gx = torch.nn.functional.conv2d(x, kx[None, None])
-            gy = torch.nn.functional.conv2d(x, kx.t().contiguous()[None, None])
-            grad = torch.sqrt(gx ** 2 + gy ** 2 + 1e-8)
-            pdf = (1 - e) / 0.0503428816795 * torch.exp(-torch.abs(grad) / 0.0503428816795) + e / 1.07274045944 * torch.exp(-torch.abs(grad) / 1.07274045944)
-            torch.mean(-torch.log(pdf.clamp(min=1e-4))).backward()
+            losses_torch.disparity_loss(d, e).backward()
         for _ in range(3):
             torch_ref()
         torch.cuda.synchronize()
