@@ -61,7 +61,7 @@ depth_similarity_kernel(const float* __restrict__ depthA, const float* __restric
                         float* __restrict__ gB, int H, int W, float inv_w, float inv_h, float clampv,
                         float scale, int direct_accumulate, double* __restrict__ partials, unsigned* __restrict__ ticket,
                         float* __restrict__ sums2) {
-  __shared__ float cst[36];  // K, RA, RB, tA, tB of this image
+  __shared__ float cst[48];  // K, RA, RB, tA, tB of this image; [36..44]: M = RA RB^T K^T (d uvw / d depth = ray M)
   const int tid = threadIdx.x;
   const int64_t b = blockIdx.y;
   if (tid < 9) cst[tid] = __ldg(K + tid);
@@ -70,11 +70,23 @@ depth_similarity_kernel(const float* __restrict__ depthA, const float* __restric
   else if (tid < 30) cst[tid] = __ldg(tA + b * 3 + (tid - 27));
   else if (tid < 33) cst[tid] = __ldg(tB + b * 3 + (tid - 30));
   __syncthreads();
+  if (tid < 9) {  // M[i][j] = sum_a sum_c RA[i][a] RB[c][a] K[j][c]: the derivative chain of a pixel is three FMAs per component
+    const int i = tid / 3, j = tid % 3;
+    float m = 0.f;
+    for (int c = 0; c < 3; ++c) {
+      float rr = 0.f;  // (RA RB^T)[i][c]
+      for (int a = 0; a < 3; ++a) rr = fmaf(cst[9 + 3 * i + a], cst[18 + 3 * c + a], rr);
+      m = fmaf(rr, cst[3 * j + c], m);
+    }
+    cst[36 + tid] = m;
+  }
+  __syncthreads();
   const float* k = cst;
   const float* ra = cst + 9;
   const float* rb = cst + 18;
   const float* ta = cst + 27;
   const float* tb = cst + 30;
+  const float* M = cst + 36;
   const unsigned hw = (unsigned)H * (unsigned)W;
   const float* dA_img = depthA + b * (int64_t)hw;
   const float* dB_img = depthB + b * (int64_t)hw;
@@ -112,27 +124,23 @@ depth_similarity_kernel(const float* __restrict__ depthA, const float* __restric
     int xa[GEO_PX], ya[GEO_PX];
 #pragma unroll
     for (int m = 0; m < GEO_PX; ++m) {
-      // forward chain (value) and the same chain on the ray alone (derivative w.r.t. depthA; translations drop out)
+      // forward chain (value); its derivative w.r.t. depthA is the same chain on the ray alone (translations drop out),
+    // folded into one 3x3 product per image
       const float x0 = dA[m] * r[m][0] - ta[0], x1 = dA[m] * r[m][1] - ta[1], x2 = dA[m] * r[m][2] - ta[2];
-      float y[3], ay[3], z[3], az[3], U[3];
+      float y[3], z[3], U[3];
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {  // xyz @ RA: column j of RA
-        y[j] = dot3(x0, x1, x2, ra[j], ra[3 + j], ra[6 + j]);
-        ay[j] = dot3(r[m][0], r[m][1], r[m][2], ra[j], ra[3 + j], ra[6 + j]);
-      }
+      for (int j = 0; j < 3; ++j) y[j] = dot3(x0, x1, x2, ra[j], ra[3 + j], ra[6 + j]);  // xyz @ RA: column j of RA
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {  // xyz @ RB^T + tB: row j of RB
+      for (int j = 0; j < 3; ++j)  // xyz @ RB^T + tB: row j of RB
         z[j] = dot3(y[0], y[1], y[2], rb[3 * j], rb[3 * j + 1], rb[3 * j + 2]) + tb[j];
-        az[j] = dot3(ay[0], ay[1], ay[2], rb[3 * j], rb[3 * j + 1], rb[3 * j + 2]);
-      }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {  // xyz @ K^T: row j of K
+      for (int j = 0; j < 3; ++j) {  // xyz @ K^T: row j of K; and d uvw / d depth = ray @ M
         U[j] = dot3(z[0], z[1], z[2], k[3 * j], k[3 * j + 1], k[3 * j + 2]);
-        A[m][j] = dot3(az[0], az[1], az[2], k[3 * j], k[3 * j + 1], k[3 * j + 2]);
+        A[m][j] = dot3(r[m][0], r[m][1], r[m][2], M[j], M[3 + j], M[6 + j]);
       }
       w[m] = U[2];
       const float den = fmaxf(w[m], 0.f) + 1e-12f;
-      rden[m] = 1.f / den;
+      rden[m] = rcp_approx(den);  // gradient path only (the sample position uses the IEEE quotients below)
       u[m] = U[0] / den;
       v[m] = U[1] / den;
       const float gx = 2.f * (u[m] * inv_w - 0.5f), gy = 2.f * (v[m] * inv_h - 0.5f);
