@@ -805,3 +805,73 @@ def test_disparity_loss_vs_torch_full_size(tx):
         tx.disparity_loss(cu(base).cpu(), None)
     with pytest.raises(RuntimeError):
         tx.disparity_loss(cu(base), cu(edge)[:, :, :-1].contiguous())
+
+
+# ---------------------------------------------------------------- no writes outside the outputs
+def _guarded(shape, dtype=torch.float32, pad=4096, fill=-777.0):
+    """A tensor view in the middle of a larger allocation whose margins are filled with a sentinel."""
+    n = int(np.prod(shape))
+    raw = torch.full((n + 2 * pad,), fill, dtype=dtype, device=DEV)
+    return raw, raw[pad:pad + n].view(*shape)
+
+
+def _margins_intact(raw, n, pad=4096, fill=-777.0):
+    return bool((raw[:pad] == fill).all()) and bool((raw[pad + n:] == fill).all())
+
+
+def test_kernels_write_only_their_outputs(tx):
+    """Odd sizes (partial tiles, scalar-store paths) with the outputs placed inside sentinel-filled allocations:
+    the margins must come back untouched (compute-sanitizer is not available on the GPU pool)."""
+    from connecting_the_dots_b200 import _lib, synth
+    rng = np.random.RandomState(3)
+    st = torch.cuda.current_stream().cuda_stream
+    # XCorrVol, separable kernel + sweep / eval fix-up, width not a multiple of 4 and a ragged last disparity chunk
+    B, H, W, D = 2, 23, 37, 19
+    a = cu((0.5 + 0.02 * rng.randn(B, 1, H, W)).astype(np.float32))
+    b = cu((0.5 + 0.02 * rng.randn(B, 1, H, W)).astype(np.float32))
+    raw, out = _guarded((B, D, H, W))
+    _lib.call("ctd_xcorrvol_f32", a.data_ptr(), b.data_ptr(), out.data_ptr(), B, 1, H, W, D, 9, st)
+    torch.cuda.synchronize()
+    assert _margins_intact(raw, out.numel())
+    assert_close(out[0].cpu().numpy(), oracle.xcorrvol(a[0].cpu().numpy(), b[0].cpu().numpy(), D, 9), what="guarded xcorrvol")
+    # mse / sad TMA kernels with a partial last tile column (W = 132) and a partial last tile row
+    B, H, W = 2, 40, 132
+    es, ta, go = (cu(rng.randn(B, 1, H, W).astype(np.float32)) for _ in range(3))
+    for ty in (0, 1):
+        raw_o, o = _guarded((B, 1, H, W))
+        raw_g, g = _guarded((B, 1, H, W))
+        _lib.call("ctd_photometric_fwd_bwd_f32", es.data_ptr(), ta.data_ptr(), go.data_ptr(), o.data_ptr(), g.data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
+        torch.cuda.synchronize()
+        assert _margins_intact(raw_o, o.numel()) and _margins_intact(raw_g, g.numel())
+        assert_close(o.cpu().numpy(), oracle.photometric_loss_forward(es.cpu().numpy(), ta.cpu().numpy(), 9, ty, 0.5), what="guarded fwd %d" % ty)
+        assert_close(g.cpu().numpy(), oracle.photometric_loss_backward(es.cpu().numpy(), ta.cpu().numpy(), go.cpu().numpy(), 9, ty, 0.5),
+                     what="guarded bwd %d" % ty)
+    # geometric loss: pixel count not a multiple of the 1024-pixel step
+    d = synth.make_depth_pairs(3, 19, 23, seed=9)
+    ray = tx.projection_rays(d["Ki"], 19, 23).to(DEV)
+    raw0, g0 = _guarded((3, 1, 19, 23))
+    raw1, g1 = _guarded((3, 1, 19, 23))
+    g1.zero_()
+    sums = torch.zeros(2, device=DEV)
+    args = [cu(d[k]) for k in ("depth0", "depth1")]
+    _lib.call("ctd_depth_similarity_f32", args[0].data_ptr(), args[1].data_ptr(), ray.data_ptr(), cu(d["K"]).data_ptr(), cu(d["R0"]).data_ptr(),
+              cu(d["t0"]).data_ptr(), cu(d["R1"]).data_ptr(), cu(d["t1"]).data_ptr(), g0.data_ptr(), g1.data_ptr(), sums.data_ptr(), 3, 19, 23,
+              0.1, 1.0 / (3 * 19 * 23), 0, st)
+    torch.cuda.synchronize()
+    assert _margins_intact(raw0, g0.numel()) and _margins_intact(raw1, g1.numel())
+    assert float(sums[1]) == 3 * 19 * 23
+    # disparity loss: image smaller than / not a multiple of the 32x32 tile
+    for (B, H, W) in ((2, 33, 35), (1, 7, 5)):
+        disp = cu((rng.rand(B, 1, H, W) * 3).astype(np.float32))
+        edge = cu(rng.rand(B, 1, H, W).astype(np.float32))
+        raw_d, gd = _guarded((B, 1, H, W))
+        raw_e, ge = _guarded((B, 1, H, W))
+        _lib.call("ctd_disparity_loss_f32", disp.data_ptr(), edge.data_ptr(), gd.data_ptr(), ge.data_ptr(), sums.data_ptr(), B, H, W,
+                  1.0 / (B * H * W), st)
+        torch.cuda.synchronize()
+        assert _margins_intact(raw_d, gd.numel()) and _margins_intact(raw_e, ge.numel())
+        d_ref, e_ref = disp.clone().requires_grad_(True), edge.clone().requires_grad_(True)
+        ref = _ref_disparity_loss(d_ref, e_ref)
+        ref.backward()
+        assert abs(float(sums[0] / sums[1]) - float(ref.detach())) <= 1e-5 * abs(float(ref.detach()))
+        assert_close(gd.cpu().numpy(), d_ref.grad.cpu().numpy(), tol=2e-5, what="guarded grad disp %dx%d" % (H, W))
