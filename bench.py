@@ -393,7 +393,7 @@ def run_b200_arm(args, rank, world, local_rank):
     # frees in its last wave.  A buffer set is always used by the same stream (NSETS is even), so its steps stay ordered.
     # The evented replays at the end of the timed region run alone on the main stream (everything before them is
     # waited for), so the per-op durations are those of an undisturbed chain.
-    lanes = [stream] + [torch.cuda.Stream(dev) for _ in range(max(args.pipeline, 1) - 1)] if use_graph else [stream]
+    lanes = [stream] + [torch.cuda.Stream(dev) for _ in range(min(max(args.pipeline, 1), NSETS) - 1)] if use_graph else [stream]
     assert NSETS % len(lanes) == 0
 
     def step(k, timed_events=True):
@@ -565,7 +565,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time plain stream launches instead of CUDA graph replays")
-    ap.add_argument("--pipeline", type=int, default=2, help="steps in flight (replayed on alternating streams); 1 = one stream")
+    ap.add_argument("--pipeline", type=int, default=4, help="steps in flight (replayed on that many alternating streams, at most one per buffer set); 1 = one stream")
     ap.add_argument("--fork", type=int, default=1,
                     help="the two losses as parallel graph branches behind LCN (1: sad on the side stream, 2: census; 0: one chain)")
     ap.add_argument("--global-batch", type=int, default=0,
