@@ -437,11 +437,14 @@ def run_b200_arm(args, rank, world, local_rank):
         sampler.start()
         time.sleep(0.3)
     sync_all()
+    # evented (sequential, single-stream) replays at the end of the timed region: one per buffer set when there are
+    # enough steps, fewer in a short run so that they stay about a tenth of it
+    n_evented = min(NSETS, max(1, args.steps // 10), args.steps)
     e0.record(stream)
     for other in lanes[1:]:
         other.wait_stream(stream)  # no lane starts before the timed region does
     for k in range(args.steps):
-        step(k, timed_events=k >= args.steps - NSETS)
+        step(k, timed_events=k >= args.steps - n_evented)
     join_lanes()
     e1.record(stream)
     sync_all()
@@ -452,8 +455,8 @@ def run_b200_arm(args, rank, world, local_rank):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     # per-op durations: the event nodes of each set keep the timestamps of its LAST replay inside the timed
-    # region; NSETS samples per op, all taken from timed steps
-    used = [si for si in range(NSETS) if si < args.steps]
+    # region; up to NSETS samples per op (one per evented step), all taken from timed steps
+    used = sorted({k % NSETS for k in range(args.steps - n_evented, args.steps)})
     op_ms = {n: float(np.mean([set_events[si][i].elapsed_time(set_events[si][i + 1]) for si in used])) for i, n in enumerate(OPS)}
     launches = (_lib.launch_count() - launches0) if not use_graph else kernels_per_graph * args.steps
     # the same chain with census_sad forward and backward as separate calls (the autograd path), a few steps
