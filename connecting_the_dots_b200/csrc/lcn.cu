@@ -197,28 +197,21 @@ lcn_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ lc
   }
   __syncthreads();
   int t = blockIdx.x;
-  auto coords = [&](int tt, int& x0, int& y0, int& img) {
-    x0 = (tt % tiles_x) * LTM_W;
-    y0 = ((tt / tiles_x) % tiles_y) * LTM_H;
-    img = tt / (tiles_x * tiles_y);
-  };
+  TileWalk walk;
+  walk.init(t, gridDim.x, tiles_x, tiles_y);
   if (tid == 0 && t < ntiles) {
-    int x0, y0, img;
-    coords(t, x0, y0, img);
     mbar_expect_tx(&S.full[0], LTM_BOX_BYTES);
-    tma_load_3d(&S.x[0][0][0], &map_x, &S.full[0], x0 - LTM_XOFF, y0 - LTM_R, img);
+    tma_load_3d(&S.x[0][0][0], &map_x, &S.full[0], walk.tx * LTM_W - LTM_XOFF, walk.ty * LTM_H - LTM_R, walk.n);
   }
-  for (int it = 0; t < ntiles; ++it, t += gridDim.x) {
+  for (int it = 0; t < ntiles; ++it, t += gridDim.x, walk = walk.next()) {
     const int s = it & 1;
     if (tid == 0 && t + (int)gridDim.x < ntiles) {
-      int x0, y0, img;
-      coords(t + gridDim.x, x0, y0, img);
+      const TileWalk nx = walk.next();
       fence_proxy_async();
       mbar_expect_tx(&S.full[s ^ 1], LTM_BOX_BYTES);
-      tma_load_3d(&S.x[s ^ 1][0][0], &map_x, &S.full[s ^ 1], x0 - LTM_XOFF, y0 - LTM_R, img);
+      tma_load_3d(&S.x[s ^ 1][0][0], &map_x, &S.full[s ^ 1], nx.tx * LTM_W - LTM_XOFF, nx.ty * LTM_H - LTM_R, nx.n);
     }
-    int x0, y0, img;
-    coords(t, x0, y0, img);
+    const int x0 = walk.tx * LTM_W, y0 = walk.ty * LTM_H, img = walk.n;
     mbar_wait(&S.full[s], (it >> 1) & 1);
     // vertical pass: thread c owns needed column c (image column x0 - R + c), 0 <= c < 128 + 2R.  Tiles whose box
     // rows all lie inside the image (all but the first and last tile row) skip the per-row reflection remap.

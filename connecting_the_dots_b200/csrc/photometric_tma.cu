@@ -64,6 +64,13 @@ __device__ __forceinline__ float sgnf(float d) { return d < 0.f ? -1.f : (d > 0.
 struct TileCoord {
   int x0, y0, n;
 };
+__device__ __forceinline__ TileCoord tile_coord(const TileWalk& w) {
+  TileCoord c;
+  c.x0 = w.tx * TT_W;
+  c.y0 = w.ty * TT_H;
+  c.n = w.n;
+  return c;
+}
 __device__ __forceinline__ TileCoord tile_coord(int t, int tiles_x, int tiles_y) {
   TileCoord c;
   c.x0 = (t % tiles_x) * TT_W;
@@ -120,22 +127,24 @@ photo_fwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_cons
   }
   __syncthreads();
   int t = blockIdx.x;
+  TileWalk walk;
+  walk.init(t, gridDim.x, tiles_x, tiles_y);
   if (tid == 0 && t < ntiles) {
-    const TileCoord c = tile_coord(t, tiles_x, tiles_y);
+    const TileCoord c = tile_coord(walk);
     mbar_expect_tx(&S.full[0], 2 * TBOX_BYTES);
     tma_load_3d(&S.es[0][0][0], &map_es, &S.full[0], c.x0 - R9, c.y0 - R9, c.n);
     tma_load_3d(&S.ta[0][0][0], &map_ta, &S.full[0], c.x0 - R9, c.y0 - R9, c.n);
   }
-  for (int it = 0; t < ntiles; ++it, t += gridDim.x) {
+  for (int it = 0; t < ntiles; ++it, t += gridDim.x, walk = walk.next()) {
     const int s = it & 1;
     if (tid == 0 && t + (int)gridDim.x < ntiles) {  // prefetch the next tile into the other stage
-      const TileCoord c = tile_coord(t + gridDim.x, tiles_x, tiles_y);
+      const TileCoord c = tile_coord(walk.next());
       fence_proxy_async();
       mbar_expect_tx(&S.full[s ^ 1], 2 * TBOX_BYTES);
       tma_load_3d(&S.es[s ^ 1][0][0], &map_es, &S.full[s ^ 1], c.x0 - R9, c.y0 - R9, c.n);
       tma_load_3d(&S.ta[s ^ 1][0][0], &map_ta, &S.full[s ^ 1], c.x0 - R9, c.y0 - R9, c.n);
     }
-    const TileCoord c = tile_coord(t, tiles_x, tiles_y);
+    const TileCoord c = tile_coord(walk);
     mbar_wait(&S.full[s], (it >> 1) & 1);
     // phase A: horizontal 9-sums of phi(es - ta), replicate clamp by index remap
     if (c.x0 == 0 || c.x0 + TT_W + R9 > W) patch_clamped_columns(S, s, c.x0, W, tid);  // block-uniform
@@ -187,20 +196,22 @@ photo_bwd_box9_tma(const __grid_constant__ CUtensorMap map_go, const float* __re
   }
   __syncthreads();
   int t = blockIdx.x;
+  TileWalk walk;
+  walk.init(t, gridDim.x, tiles_x, tiles_y);
   if (tid == 0 && t < ntiles) {
-    const TileCoord c = tile_coord(t, tiles_x, tiles_y);
+    const TileCoord c = tile_coord(walk);
     mbar_expect_tx(&S.full[0], TBOX_BYTES);
     tma_load_3d(&S.go[0][0][0], &map_go, &S.full[0], c.x0 - R9, c.y0 - R9, c.n);
   }
-  for (int it = 0; t < ntiles; ++it, t += gridDim.x) {
+  for (int it = 0; t < ntiles; ++it, t += gridDim.x, walk = walk.next()) {
     const int s = it & 1;
     if (tid == 0 && t + (int)gridDim.x < ntiles) {
-      const TileCoord c = tile_coord(t + gridDim.x, tiles_x, tiles_y);
+      const TileCoord c = tile_coord(walk.next());
       fence_proxy_async();
       mbar_expect_tx(&S.full[s ^ 1], TBOX_BYTES);
       tma_load_3d(&S.go[s ^ 1][0][0], &map_go, &S.full[s ^ 1], c.x0 - R9, c.y0 - R9, c.n);
     }
-    const TileCoord c = tile_coord(t, tiles_x, tiles_y);
+    const TileCoord c = tile_coord(walk);
     // this thread's es/ta pixels do not depend on the staged tile: fetch them while the TMA lands
     const int q = tid % 32, rs = tid / 32;
     const int gx = c.x0 + 4 * q, gy = c.y0 + 2 * rs;
@@ -288,23 +299,25 @@ photo_fwd_bwd_box9_tma(const __grid_constant__ CUtensorMap map_es, const __grid_
     fence_barrier_init();
   }
   __syncthreads();
-  auto fetch = [&](int tt, int stage) {
-    const TileCoord c = tile_coord(tt, tiles_x, tiles_y);
+  auto fetch = [&](const TileWalk& wk, int stage) {
+    const TileCoord c = tile_coord(wk);
     mbar_expect_tx(&S.full[stage], 3 * TBOX_BYTES);
     tma_load_3d(&S.es[stage][0][0], &map_es, &S.full[stage], c.x0 - R9, c.y0 - R9, c.n);
     tma_load_3d(&S.ta[stage][0][0], &map_ta, &S.full[stage], c.x0 - R9, c.y0 - R9, c.n);
     tma_load_3d(&S.go[stage][0][0], &map_go, &S.full[stage], c.x0 - R9, c.y0 - R9, c.n);
   };
   int t = blockIdx.x;
-  if (tid == 0 && t < ntiles) fetch(t, 0);
+  TileWalk walk;
+  walk.init(t, gridDim.x, tiles_x, tiles_y);
+  if (tid == 0 && t < ntiles) fetch(walk, 0);
   double mnum = 0.0, mden = 0.0;  // optional masked-mean terms, accumulated over this CTA's tiles
-  for (int it = 0; t < ntiles; ++it, t += gridDim.x) {
+  for (int it = 0; t < ntiles; ++it, t += gridDim.x, walk = walk.next()) {
     const int s = it & 1;
     if (tid == 0 && t + (int)gridDim.x < ntiles) {  // prefetch the next tile into the other stage
       fence_proxy_async();
-      fetch(t + gridDim.x, s ^ 1);
+      fetch(walk.next(), s ^ 1);
     }
-    const TileCoord c = tile_coord(t, tiles_x, tiles_y);
+    const TileCoord c = tile_coord(walk);
     mbar_wait(&S.full[s], (it >> 1) & 1);
     if (c.x0 == 0 || c.x0 + TT_W + R9 > W) patch_clamped_columns(S, s, c.x0, W, tid);  // block-uniform
     const int xr = W - 1 - c.x0;  // tile-local column of the last image column
