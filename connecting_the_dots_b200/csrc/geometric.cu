@@ -43,18 +43,25 @@ __device__ __forceinline__ float geo_source_index(float g, int size, float* mult
   return i;
 }
 
-constexpr int GEO_T = 256, GEO_PX = 4;  // threads per block, consecutive pixels per thread
+// measured (one direction, batch 8): 2 pixels x 4 blocks/SM 36.9 us, 4 x 2 46.1 us, 2 x 3 51.8 us, 4 x 3 68.9 us (spills)
+#ifndef CTD_GEO_PX
+#define CTD_GEO_PX 2
+#endif
+#ifndef CTD_GEO_CTAS
+#define CTD_GEO_CTAS 4
+#endif
+constexpr int GEO_T = 256, GEO_PX = CTD_GEO_PX, GEO_CTAS = CTD_GEO_CTAS;  // threads per block, pixels per thread, resident blocks per SM
 
 // direct_accumulate: 0 = gA[p] is overwritten with this pixel's gradient, 1 = it is added to what is there (the
 // second direction of tforward, networks.py:500-503: gA then already holds the scatter of the first direction).
 // grid = (blocks per image, B): a block stays inside one image (the poses sit in shared memory) and walks it in
-// steps of gridDim.x * 1024 pixels (the grid is two blocks per SM: a block's set-up and its part in the final sum are
-// paid once per ~8 steps).  A thread owns four pixels 256 apart, so the lanes of a warp touch neighbouring pixels in
+// steps of gridDim.x * 256 * GEO_PX pixels (the grid is GEO_CTAS blocks per SM: a block's set-up and its part in the final sum are
+// paid once per several steps).  A thread owns GEO_PX pixels 256 apart, so the lanes of a warp touch neighbouring pixels in
 // every load, store and atomic (a warp's scatter lands in one or two cache lines per instruction; four consecutive
-// pixels per thread were measured 2x slower in the atomics).  Depth and rays are requested one step ahead; the four
-// projections are computed, then all sixteen bilinear taps are fetched together, so a step waits for one round trip
+// pixels per thread were measured 2x slower in the atomics).  Depth and rays are requested one step ahead; the
+// projections are computed, then all the step's bilinear taps are fetched together, so a step waits for one round trip
 // (the taps) however many pixels are in flight.
-__global__ void __launch_bounds__(GEO_T, 2)
+__global__ void __launch_bounds__(GEO_T, GEO_CTAS)
 depth_similarity_kernel(const float* __restrict__ depthA, const float* __restrict__ depthB, const float* __restrict__ ray,
                         const float* __restrict__ K, const float* __restrict__ RA, const float* __restrict__ tA,
                         const float* __restrict__ RB, const float* __restrict__ tB, float* __restrict__ gA,
@@ -93,7 +100,7 @@ depth_similarity_kernel(const float* __restrict__ depthA, const float* __restric
   float* gA_img = gA ? gA + b * (int64_t)hw : nullptr;
   float* gB_img = gB ? gB + b * (int64_t)hw : nullptr;
   double acc = 0.0, cnt = 0.0;
-  // inputs of a step: depth and rays of the thread's four pixels; the next step's are requested before this step's
+  // inputs of a step: depth and rays of the thread's pixels; the next step's are requested before this step's
   // arithmetic so their round trip overlaps it
   auto fetch = [&](unsigned p0, float (&d)[GEO_PX], float (&q)[GEO_PX][3]) {
 #pragma unroll
@@ -232,7 +239,7 @@ CTD_API int ctd_depth_similarity_f32(const float* depthA, const float* depthB, c
   // blocks per image: enough to fill the GPU, at most MS_MAXBLK blocks in all (the deterministic sum's workspace)
   // two resident blocks per SM in all (a block's set-up and its share of the final reduction are amortised over
   // many steps), at least one block per image
-  const int64_t per_img = std::max<int64_t>(1, std::min<int64_t>(cdiv(H * W, GEO_T * GEO_PX), cdiv(148 * 2, std::max<int64_t>(B, 1))));
+  const int64_t per_img = std::max<int64_t>(1, std::min<int64_t>(cdiv(H * W, GEO_T * GEO_PX), cdiv(148 * GEO_CTAS, std::max<int64_t>(B, 1))));
   CTD_REQUIRE(per_img * B <= MS_MAXBLK, "depth_similarity: batch too large for the reduction workspace");
   const dim3 grid((unsigned)per_img, (unsigned)B);
   unsigned* ticket = nullptr;
