@@ -56,7 +56,13 @@ __device__ __forceinline__ SamplePos sample_pos(float disp, int u, int v, float 
 
 // grid: (columns / 128, rows / WP_ROWS, images): no integer division in the index math, WP_ROWS independent pixels
 // per thread so the dependent gather chains overlap
-constexpr int WP_T = 128, WP_ROWS = 4;
+#ifndef CTD_WP_T
+#define CTD_WP_T 128
+#endif
+#ifndef CTD_WP_ROWS
+#define CTD_WP_ROWS 2  // measured at batch 8 (fwd / bwd us): 2 rows 11.5 / 16.0, 4 rows 11.7 / 17.6, 8 rows 12.9 / 21.7; 256 threads x 4: 12.1 / 19.0
+#endif
+constexpr int WP_T = CTD_WP_T, WP_ROWS = CTD_WP_ROWS;
 
 __global__ void __launch_bounds__(WP_T)
 warp_fwd_kernel(const float* __restrict__ pattern, const float* __restrict__ disp, float* __restrict__ out, int Bp, int Hp,
@@ -135,7 +141,7 @@ CTD_API int ctd_warp_pattern_fwd_f32(const float* pattern, const float* disp, fl
                                         int64_t Wp, int64_t H, int64_t W, ctd_stream_t stream) {
   if (int rc = warp_check(pattern, disp, out, B, Bp, Hp, Wp, H, W)) return rc;
   if (B * H * W == 0) return CTD_OK;
-  CTD_REQUIRE(H <= 65535 * 4 && Hp * Wp < ((int64_t)1 << 31), "warp_pattern: image too large");
+  CTD_REQUIRE(H <= 65535 * (int64_t)WP_ROWS && Hp * Wp < ((int64_t)1 << 31), "warp_pattern: image too large");
   for (int64_t b0 = 0; b0 < B; b0 += 65535) {
     const int64_t nb = std::min<int64_t>(65535, B - b0);
     const dim3 grid((unsigned)cdiv(W, WP_T), (unsigned)cdiv(H, WP_ROWS), (unsigned)nb);
@@ -151,7 +157,7 @@ CTD_API int ctd_warp_pattern_bwd_f32(const float* pattern, const float* disp, co
   if (int rc = warp_check(pattern, disp, grad_disp, B, Bp, Hp, Wp, H, W)) return rc;
   if (B * H * W == 0) return CTD_OK;
   CTD_REQUIRE(grad_out, "warp_pattern_bwd: null grad_out");
-  CTD_REQUIRE(H <= 65535 * 4 && Hp * Wp < ((int64_t)1 << 31), "warp_pattern: image too large");
+  CTD_REQUIRE(H <= 65535 * (int64_t)WP_ROWS && Hp * Wp < ((int64_t)1 << 31), "warp_pattern: image too large");
   for (int64_t b0 = 0; b0 < B; b0 += 65535) {
     const int64_t nb = std::min<int64_t>(65535, B - b0);
     const dim3 grid((unsigned)cdiv(W, WP_T), (unsigned)cdiv(H, WP_ROWS), (unsigned)nb);
