@@ -34,6 +34,7 @@ SIGNATURES = {
     "ctd_host_photometric_fwd_f32": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _f32],
     "ctd_host_photometric_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _f32],
     "ctd_host_photometric_fwd_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _f32],
+    "ctd_host_photometric_fwd_bwd_masked_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _int, _int, _f32],
     "ctd_host_xcorrvol_f32": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _int],
     "ctd_host_proj_nn_f32": [_ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int],
     "ctd_host_nn_f32": [_ptr, _ptr, _ptr, _i64, _i64],

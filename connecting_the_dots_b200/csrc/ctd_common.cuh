@@ -20,10 +20,18 @@ void count_launch(int n = 1);
 void* scratch_alloc(size_t bytes, cudaStream_t st);
 void scratch_free(void* p, cudaStream_t st);
 
-// Ticket + block-partial workspace for kernels that end with finish_masked_sums (see ctd_core.cu); false when the
-// grid has more than MS_MAXBLK blocks (callers then take scratch memory and zero the ticket themselves).
-constexpr int MS_SLOTS = 64, MS_MAXBLK = 4096;  // 64 slots: kernels of a few CUDA graphs replayed on concurrent streams never share one
-bool masked_sums_slot(size_t nblocks, unsigned** ticket, double** partials);
+// Ticket + block-partial workspace for kernels that end with finish_masked_sums (ownership rules in ctd_core.cu): a
+// static slot private to the stream (eager) or to the captured call (graph capture), else stream-ordered scratch
+// memory with its ticket zeroed on the stream.  ms_acquire returns false only when no memory can be had at all;
+// ms_release goes right after the kernel launch.
+constexpr int MS_EAGER = 32, MS_GRAPH = 96, MS_MAXBLK = 4096;
+struct MsSlot {
+  unsigned* ticket;
+  double* partials;
+  void* scratch;
+};
+bool ms_acquire(size_t nblocks, cudaStream_t st, MsSlot* s);
+void ms_release(MsSlot* s, cudaStream_t st);
 
 // Check the launch that was just issued (no synchronisation, like a normal async API).
 int check_launch(const char* what);

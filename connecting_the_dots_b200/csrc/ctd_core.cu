@@ -55,31 +55,89 @@ static cudaMemPool_t scratch_pool() {
   return pools[dev];
 }
 
-// Workspace of finish_masked_sums (ticket + block partials): static device memory in MS_SLOTS rotating slots, so the
-// masked loss calls need no allocation, memset or free around the kernel (each of those is a graph node and ~1.5 us
-// on a 30 us kernel).  A slot's ticket is zero at load time and is reset by the block that finishes the sums.  Slots
-// are handed out round-robin: up to MS_SLOTS masked calls may be in flight at once (across all streams).
-__device__ __align__(16) unsigned char g_ms_slots[MS_SLOTS][16 + MS_MAXBLK * 16];
+// Workspace of finish_masked_sums (ticket + block partials): static device memory, so the masked loss calls need no
+// allocation, memset or free around the kernel (each of those is a graph node and ~1.5 us on a 30 us kernel).  A
+// slot's ticket is zero at load time and is reset by the block that finishes the sums.  Ownership rules (a slot is
+// never shared by two launches that may run concurrently):
+//   * eager launches: one slot per (device, stream), found in a small table -- launches on one stream are ordered, so
+//     the kernel that reuses the slot starts after its predecessor reset the ticket;
+//   * launches being captured into a CUDA graph: the slot address is baked into the graph, so every captured call gets
+//     a slot of its own from a separate pool that is never handed out twice (graphs may replay on any stream,
+//     concurrently with each other and with eager calls);
+//   * when a pool is exhausted (more than MS_EAGER streams, more than MS_GRAPH captured calls in the process), or the
+//     grid has more than MS_MAXBLK blocks, the workspace comes from the stream-ordered scratch pool with a memset node
+//     in front of the kernel: slower by ~1.5 us, never shared.
+// A kernel that dies (trap, illegal address) leaves the context unusable anyway (sticky CUDA error), so a ticket stuck
+// at a non-zero value cannot be observed by a later successful launch of the same process.
+__device__ __align__(16) unsigned char g_ms_slots[MS_EAGER + MS_GRAPH][16 + MS_MAXBLK * 16];
 
-bool masked_sums_slot(size_t nblocks, unsigned** ticket, double** partials) {
-  static std::atomic<unsigned> next{0};
-  static thread_local unsigned char* base = nullptr;
-  static thread_local int base_dev = -1;
-  int dev = 0;
-  if (nblocks > MS_MAXBLK || cudaGetDevice(&dev) != cudaSuccess) return false;
-  if (!base || base_dev != dev) {
+static unsigned char* ms_base(int dev) {
+  static std::mutex mtx;
+  static unsigned char* bases[64] = {};
+  if (dev < 0 || dev >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(mtx);
+  if (!bases[dev]) {
     void* p = nullptr;
     if (cudaGetSymbolAddress(&p, g_ms_slots) != cudaSuccess) {
       cudaGetLastError();
+      return nullptr;
+    }
+    bases[dev] = static_cast<unsigned char*>(p);
+  }
+  return bases[dev];
+}
+
+bool ms_acquire(size_t nblocks, cudaStream_t st, MsSlot* s) {
+  s->ticket = nullptr;
+  s->partials = nullptr;
+  s->scratch = nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  int slot = -1;
+  if (nblocks <= MS_MAXBLK && dev < 64) {
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
+      cudaGetLastError();
       return false;
     }
-    base = static_cast<unsigned char*>(p);
-    base_dev = dev;
+    static std::mutex mtx;
+    std::lock_guard<std::mutex> lk(mtx);
+    if (cap == cudaStreamCaptureStatusActive) {
+      static int next_graph[64] = {};
+      if (next_graph[dev] < MS_GRAPH) slot = MS_EAGER + next_graph[dev]++;
+    } else {
+      static cudaStream_t owner[64][MS_EAGER];
+      static int n_owner[64] = {};
+      for (int i = 0; i < n_owner[dev] && slot < 0; ++i)
+        if (owner[dev][i] == st) slot = i;
+      if (slot < 0 && n_owner[dev] < MS_EAGER) {
+        owner[dev][n_owner[dev]] = st;
+        slot = n_owner[dev]++;
+      }
+    }
   }
-  unsigned char* slot = base + (size_t)(next.fetch_add(1, std::memory_order_relaxed) % MS_SLOTS) * (16 + MS_MAXBLK * 16);
-  *ticket = reinterpret_cast<unsigned*>(slot);
-  *partials = reinterpret_cast<double*>(slot + 16);
+  unsigned char* base = slot >= 0 ? ms_base(dev) : nullptr;
+  if (base) {
+    unsigned char* p = base + (size_t)slot * (16 + MS_MAXBLK * 16);
+    s->ticket = reinterpret_cast<unsigned*>(p);
+    s->partials = reinterpret_cast<double*>(p + 16);
+    return true;
+  }
+  char* sc = static_cast<char*>(scratch_alloc(16 + nblocks * 16, st));
+  if (!sc || cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
+    cudaGetLastError();
+    scratch_free(sc, st);
+    return false;
+  }
+  s->scratch = sc;
+  s->ticket = reinterpret_cast<unsigned*>(sc);
+  s->partials = reinterpret_cast<double*>(sc + 16);
   return true;
+}
+
+void ms_release(MsSlot* s, cudaStream_t st) {
+  scratch_free(s->scratch, st);  // stream-ordered: after the kernel that was just enqueued
+  s->scratch = nullptr;
 }
 
 void* scratch_alloc(size_t bytes, cudaStream_t st) {

@@ -152,15 +152,17 @@ CTD_API int ctd_disparity_loss_f32(const float* disp, const float* edge, float* 
   CTD_REQUIRE(ntiles <= INT32_MAX, "disparity_loss: too many tiles");
   // one CTA per tile while the deterministic sum's workspace holds them, else persistent over the tile list
   const unsigned grid = (unsigned)(ntiles <= MS_MAXBLK ? ntiles : 148 * 6);
-  unsigned* ticket = nullptr;
-  double* partials = nullptr;
-  if (!masked_sums_slot(grid, &ticket, &partials)) return fail(CTD_ERR_NOMEM, "disparity_loss: no reduction workspace");
+  MsSlot ms;
+  if (!ms_acquire(grid, st, &ms)) return fail(CTD_ERR_NOMEM, "disparity_loss: no reduction workspace");
+  unsigned* ticket = ms.ticket;
+  double* partials = ms.partials;
   if (edge)
     disparity_loss_kernel<true><<<grid, 256, 0, st>>>(disp, edge, grad_disp, grad_edge, (int)H, (int)W, (int)tx, (int)ty, (int)ntiles,
                                                      scale, partials, ticket, sums2);
   else
     disparity_loss_kernel<false><<<grid, 256, 0, st>>>(disp, nullptr, grad_disp, nullptr, (int)H, (int)W, (int)tx, (int)ty,
                                                       (int)ntiles, scale, partials, ticket, sums2);
+  ms_release(&ms, st);
   count_launch();
   return check_launch("disparity_loss");
 }

@@ -242,12 +242,14 @@ CTD_API int ctd_depth_similarity_f32(const float* depthA, const float* depthB, c
   const int64_t per_img = std::max<int64_t>(1, std::min<int64_t>(cdiv(H * W, GEO_T * GEO_PX), cdiv(148 * GEO_CTAS, std::max<int64_t>(B, 1))));
   CTD_REQUIRE(per_img * B <= MS_MAXBLK, "depth_similarity: batch too large for the reduction workspace");
   const dim3 grid((unsigned)per_img, (unsigned)B);
-  unsigned* ticket = nullptr;
-  double* partials = nullptr;
-  if (!masked_sums_slot((size_t)(per_img * B), &ticket, &partials)) return fail(CTD_ERR_NOMEM, "depth_similarity: no reduction workspace");
+  MsSlot ms;
+  if (!ms_acquire((size_t)(per_img * B), st, &ms)) return fail(CTD_ERR_NOMEM, "depth_similarity: no reduction workspace");
+  unsigned* ticket = ms.ticket;
+  double* partials = ms.partials;
   const float inv_w = W > 1 ? 1.f / (float)(W - 1) : INFINITY, inv_h = H > 1 ? 1.f / (float)(H - 1) : INFINITY;
   depth_similarity_kernel<<<grid, GEO_T, 0, st>>>(depthA, depthB, ray, K, RA, tA, RB, tB, grad_depthA, grad_depthB, (int)H, (int)W,
                                                   inv_w, inv_h, clamp, scale, direct_accumulate, partials, ticket, sums2);
+  ms_release(&ms, st);
   count_launch();
   return check_launch("depth_similarity");
 }

@@ -10,12 +10,22 @@
 // (the upload of the next call runs under the download of the previous one), results are in host memory when
 // ctd_host_end_batch() returns.
 // There is no CPU compute path: without a CUDA device these calls fail with CTD_ERR_CUDA.
+#include <stdlib.h>
+
 #include <algorithm>
+#include <atomic>
 #include <vector>
 
 #include "ctd_common.cuh"
 
 namespace ctd {
+
+static std::atomic<bool> g_process_exiting{false};
+static void mark_exiting() { g_process_exiting.store(true, std::memory_order_relaxed); }
+static void register_exit_hook() {
+  static const int once = atexit(mark_exiting);
+  (void)once;
+}
 
 struct Workspace {
   int device = -1;
@@ -37,13 +47,40 @@ struct Workspace {
     char* dev;
   };
   std::vector<Upload> uploads;
+  // Downloads of the open batch that have been enqueued but not waited for: host ranges whose contents are not there
+  // yet.  A later call of the batch that reads such a range (LCN's std as the mask of the loss, ProjNN's indices as
+  // CrossCheck's input) must not upload it -- the host still holds the old bytes.  An exact match (same address, same
+  // size: the chunks of two image-wise calls line up) is served from the producer's device buffer, with no copy at all:
+  // every kernel of a batch runs on the one compute stream, after its producer.  Any other overlap waits for the
+  // downloads to land and then uploads what the host really holds.
+  std::vector<Upload> pending;
   uint64_t h2d_bytes = 0, h2d_saved = 0;  // statistics since ctd_host_begin_batch (ctd_host_batch_stats)
+
+  void note_download(const void* host, size_t bytes, char* dev) {
+    if (deferred && bytes) pending.push_back({host, bytes, dev});
+  }
 
   // device address holding `bytes` bytes of `host`: the earlier upload of this batch, or `dst` after enqueuing the copy
   int upload(cudaStream_t st, char* dst, const void* host, size_t bytes, char** dev) {
     *dev = dst;
     if (bytes == 0) return CTD_OK;
     if (deferred) {
+      const char* h0 = static_cast<const char*>(host);
+      bool overlap = false;
+      for (const Upload& u : pending) {
+        if (u.host == host && u.bytes == bytes) {
+          *dev = u.dev;
+          h2d_saved += bytes;
+          return CTD_OK;
+        }
+        const char* p0 = static_cast<const char*>(u.host);
+        overlap = overlap || (h0 < p0 + u.bytes && p0 < h0 + bytes);
+      }
+      if (overlap) {  // partial overlap with an output in flight: let the downloads finish, then the host copy is current
+        CTD_CUDA(cudaStreamSynchronize(s_out));
+        CTD_CUDA(cudaStreamSynchronize(stream));
+        pending.clear();
+      }
       for (const Upload& u : uploads)
         if (u.host == host && u.bytes == bytes) {
           *dev = u.dev;
@@ -82,6 +119,7 @@ struct Workspace {
       device = dev;
     }
     if (!stream) {
+      register_exit_hook();
       CTD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
       CTD_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
       CTD_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
@@ -98,6 +136,7 @@ struct Workspace {
         cap = 0;
         used = 0;
         uploads.clear();  // the device copies of this batch's earlier uploads went with the old workspace
+        pending.clear();  // ... and every download has landed
       }
       const size_t want = bytes + bytes / 8 + (1 << 20);
       if (cudaMalloc(&base, want) != cudaSuccess) {
@@ -128,7 +167,20 @@ struct Workspace {
     stream = nullptr;
     device = -1;
   }
-  ~Workspace() {}  // process teardown: the driver reclaims everything; do not touch CUDA here
+  // A host thread that ends gives its device workspace, streams and events back.  At process exit the destructors of
+  // the exiting thread's thread_local objects run before any atexit handler or static destructor (so the CUDA runtime
+  // is still up); g_process_exiting covers destructors that run later than that.
+  ~Workspace() {
+    if (g_process_exiting.load(std::memory_order_relaxed) || device < 0) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) {
+      cudaGetLastError();
+      return;
+    }
+    if (cudaSetDevice(device) == cudaSuccess) release();
+    cudaSetDevice(cur);
+    cudaGetLastError();
+  }
 };
 
 static thread_local Workspace g_ws;
@@ -157,13 +209,14 @@ static inline int chunk_count(int64_t B, bool deferred) {
 
 using namespace ctd;
 
-#define H2D(dst, src, bytes)                                                                   \
-  do {                                                                                         \
-    g_ws.h2d_bytes += (bytes);                                                                 \
-    CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyHostToDevice, g_ws.stream));     \
+// upload on the compute stream (the unpipelined ops); `devp` receives where the bytes are (an earlier copy of the batch or dst)
+#define H2D(devp, dst, src, bytes) RUN(g_ws.upload(g_ws.stream, (dst), (src), (bytes), &(devp)))
+#define D2H(dst, src, bytes) D2H_ON(g_ws.stream, dst, src, bytes)
+#define D2H_ON(st, dst, src, bytes)                                                        \
+  do {                                                                                     \
+    CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (st)));        \
+    g_ws.note_download((dst), (bytes), (char*)(src));                                      \
   } while (0)
-#define D2H(dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, g_ws.stream))
-#define D2H_ON(st, dst, src, bytes) CTD_CUDA(cudaMemcpyAsync((dst), (src), (bytes), cudaMemcpyDeviceToHost, (st)))
 #define RUN(call)                    \
   do {                               \
     if (int rc__ = (call)) return rc__; \
@@ -225,6 +278,69 @@ CTD_API int ctd_host_photometric_fwd_bwd_f32(const float* es, const float* ta, c
   return photometric_host(es, ta, go, out, gi, B, C, H, W, bs, type, eps);
 }
 
+// The reference caller's whole use of the loss (model/networks.py:376-377): loss map, d loss / d es for
+// grad_out (= mask / sum(mask) up to a scalar, supplied by the caller) and the two masked-mean terms
+// sums2 = (sum(mask * loss), sum(mask)) -- `out` may be NULL when the caller only wants the scalars and the gradient
+// (the loss map then never crosses the bus: 4 bytes per pixel less to download).  Chunks produce their own partial
+// sums on the device; one small kernel adds them in chunk order before the 8-byte download.
+namespace ctd {
+__global__ void add_pairs_kernel(const float* __restrict__ parts, int n, float* __restrict__ out2) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < n; ++i) {
+      a += (double)parts[2 * i];
+      b += (double)parts[2 * i + 1];
+    }
+    out2[0] = (float)a;
+    out2[1] = (float)b;
+  }
+}
+}  // namespace ctd
+
+CTD_API int ctd_host_photometric_fwd_bwd_masked_f32(const float* es, const float* ta, const float* go, const float* mask,
+                                                       float* out, float* gi, float* sums2, int64_t B, int64_t C, int64_t H,
+                                                       int64_t W, int bs, int type, float eps) {
+  CTD_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, "photometric: negative size");
+  CTD_REQUIRE(sums2, "photometric_fwd_bwd_masked: null sums2");
+  const size_t nin = (size_t)(B * C * H * W) * sizeof(float), nout = (size_t)(B * H * W) * sizeof(float);
+  if (nout == 0) {
+    sums2[0] = sums2[1] = 0.f;
+    return CTD_OK;
+  }
+  CTD_REQUIRE(es && ta && go && mask && gi, "photometric_fwd_bwd_masked: null pointer");
+  const int nch = chunk_count(B, g_ws.deferred);
+  Carver cv;
+  const size_t o_es = cv.add(nin), o_ta = cv.add(nin), o_go = cv.add(nout), o_mk = cv.add(nout), o_out = cv.add(nout),
+               o_gi = cv.add(nin), o_parts = cv.add(sizeof(float) * 2 * (Workspace::MAX_CHUNKS + 1));
+  char* b = nullptr;
+  RUN(g_ws.carve(cv.total, &b));
+  const size_t in_img = nin / B, out_img = nout / B;
+  float* parts = reinterpret_cast<float*>(b + o_parts);
+  for (int c = 0; c < nch; ++c) {
+    const int64_t i0 = chunk_lo(B, nch, c), nb = chunk_lo(B, nch, c + 1) - i0;
+    const size_t oi = (size_t)i0 * in_img, oo = (size_t)i0 * out_img;
+    char *d_es = nullptr, *d_ta = nullptr, *d_go = nullptr, *d_mk = nullptr;
+    RUN(g_ws.upload(g_ws.s_in, b + o_es + oi, (const char*)es + oi, nb * in_img, &d_es));
+    RUN(g_ws.upload(g_ws.s_in, b + o_ta + oi, (const char*)ta + oi, nb * in_img, &d_ta));
+    RUN(g_ws.upload(g_ws.s_in, b + o_go + oo, (const char*)go + oo, nb * out_img, &d_go));
+    RUN(g_ws.upload(g_ws.s_in, b + o_mk + oo, (const char*)mask + oo, nb * out_img, &d_mk));
+    CTD_CUDA(cudaEventRecord(g_ws.ev_in[c], g_ws.s_in));
+    CTD_CUDA(cudaStreamWaitEvent(g_ws.stream, g_ws.ev_in[c], 0));
+    RUN(ctd_photometric_fwd_bwd_masked_f32((float*)d_es, (float*)d_ta, (float*)d_go, (float*)d_mk, (float*)(b + o_out + oo),
+                                           (float*)(b + o_gi + oi), parts + 2 * c, nb, C, H, W, bs, type, eps, g_ws.stream));
+    if (c == nch - 1) {
+      add_pairs_kernel<<<1, 32, 0, g_ws.stream>>>(parts, nch, parts + 2 * Workspace::MAX_CHUNKS);
+      count_launch();
+    }
+    CTD_CUDA(cudaEventRecord(g_ws.ev_run[c], g_ws.stream));
+    CTD_CUDA(cudaStreamWaitEvent(g_ws.s_out, g_ws.ev_run[c], 0));
+    if (out) D2H_ON(g_ws.s_out, (char*)out + oo, b + o_out + oo, nb * out_img);
+    D2H_ON(g_ws.s_out, (char*)gi + oi, b + o_gi + oi, nb * in_img);
+    if (c == nch - 1) CTD_CUDA(cudaMemcpyAsync(sums2, parts + 2 * Workspace::MAX_CHUNKS, 2 * sizeof(float), cudaMemcpyDeviceToHost, g_ws.s_out));
+  }
+  return g_ws.finish(cv.total);
+}
+
 CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,
                                      int64_t W, int64_t D, int bs) {
   CTD_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0 && D >= 0, "xcorrvol: negative size");
@@ -262,14 +378,14 @@ CTD_API int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const flo
   const size_t o0 = cv.add(npt), o1 = cv.add(npt), ok = cv.add(9 * sizeof(float)), oo = cv.add(nout);
   char* b = nullptr;
   RUN(g_ws.carve(cv.total, &b));
+  char *d0 = b + o0, *d1 = b + o1, *dk = b + ok;
   if (nout) {
     CTD_REQUIRE(xyz0 && xyz1 && K && out, "proj_nn: null pointer");
-    H2D(b + o0, xyz0, npt);
-    H2D(b + o1, xyz1, npt);
-    H2D(b + ok, K, 9 * sizeof(float));
+    H2D(d0, b + o0, xyz0, npt);
+    H2D(d1, b + o1, xyz1, npt);
+    H2D(dk, b + ok, K, 9 * sizeof(float));
   }
-  RUN(ctd_proj_nn_f32((float*)(b + o0), (float*)(b + o1), (float*)(b + ok), (int64_t*)(b + oo), B, H, W, ps,
-                      g_ws.stream));
+  RUN(ctd_proj_nn_f32((float*)d0, (float*)d1, (float*)dk, (int64_t*)(b + oo), B, H, W, ps, g_ws.stream));
   if (nout) D2H(out, b + oo, nout);
   return g_ws.finish(cv.total);
 }
@@ -281,15 +397,16 @@ CTD_API int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, in
   const size_t o0 = cv.add(n0), o1 = cv.add(n1), oo = cv.add(no);
   char* b = nullptr;
   RUN(g_ws.carve(cv.total, &b));
+  char *d0 = b + o0, *d1 = b + o1;
   if (n0) {
     CTD_REQUIRE(in0 && out, "nn: null pointer");
-    H2D(b + o0, in0, n0);
+    H2D(d0, b + o0, in0, n0);
   }
   if (n1) {
     CTD_REQUIRE(in1, "nn: null pointer");
-    H2D(b + o1, in1, n1);
+    H2D(d1, b + o1, in1, n1);
   }
-  RUN(ctd_nn_f32((float*)(b + o0), (float*)(b + o1), (int64_t*)(b + oo), N0, N1, g_ws.stream));
+  RUN(ctd_nn_f32((float*)d0, (float*)d1, (int64_t*)(b + oo), N0, N1, g_ws.stream));
   if (no) D2H(out, b + oo, no);
   return g_ws.finish(cv.total);
 }
@@ -301,15 +418,16 @@ CTD_API int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t*
   const size_t o0 = cv.add(n0), o1 = cv.add(n1), oo = cv.add(no);
   char* b = nullptr;
   RUN(g_ws.carve(cv.total, &b));
+  char *d0 = b + o0, *d1 = b + o1;
   if (n0) {
     CTD_REQUIRE(in0 && out, "crosscheck: null pointer");
-    H2D(b + o0, in0, n0);
+    H2D(d0, b + o0, in0, n0);
   }
   if (n1) {
     CTD_REQUIRE(in1, "crosscheck: null pointer");
-    H2D(b + o1, in1, n1);
+    H2D(d1, b + o1, in1, n1);
   }
-  RUN(ctd_crosscheck((int64_t*)(b + o0), (int64_t*)(b + o1), (uint8_t*)(b + oo), N0, N1, g_ws.stream));
+  RUN(ctd_crosscheck((int64_t*)d0, (int64_t*)d1, (uint8_t*)(b + oo), N0, N1, g_ws.stream));
   if (no) D2H(out, b + oo, no);
   return g_ws.finish(cv.total);
 }
@@ -347,6 +465,7 @@ CTD_API int ctd_host_begin_batch(void) {
   g_ws.deferred = true;
   g_ws.used = 0;
   g_ws.uploads.clear();
+  g_ws.pending.clear();
   g_ws.h2d_bytes = g_ws.h2d_saved = 0;
   return CTD_OK;
 }
@@ -356,6 +475,7 @@ CTD_API int ctd_host_end_batch(void) {
   g_ws.deferred = false;
   g_ws.used = 0;
   g_ws.uploads.clear();
+  g_ws.pending.clear();
   if (g_ws.stream) {
     CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
     CTD_CUDA(cudaStreamSynchronize(g_ws.stream));

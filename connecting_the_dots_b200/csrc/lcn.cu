@@ -216,7 +216,8 @@ lcn_tma_kernel(const __grid_constant__ CUtensorMap map_x, float* __restrict__ lc
     // vertical pass: thread c owns needed column c (image column x0 - R + c), 0 <= c < 128 + 2R.  Tiles whose box
     // rows all lie inside the image (all but the first and last tile row) skip the per-row reflection remap.
     if (tid < LTM_W + 2 * R) {
-      const int cc = reflect(x0 - R + tid, W) - (x0 - LTM_XOFF);
+      // columns right of the last needed one (partial last tile) would reflect to a negative index: pin them to it
+      const int cc = reflect(min(x0 - R + tid, W - 1 + R), W) - (x0 - LTM_XOFF);
       auto vertical = [&](auto interior_tag) {
         constexpr bool INTERIOR = decltype(interior_tag)::value;
         double p1[K + 1], p2[K + 1];  // ring of prefix sums: slot j % (K+1) holds prefix through box row j-1

@@ -28,7 +28,7 @@ int box9_tma_bwd(const float* es, const float* ta, const float* go, float* gi, i
                  int64_t W, int type, cudaStream_t st);
 int box9_tma_fwd_bwd(const float* es, const float* ta, const float* go, float* out, float* gi, int64_t B, int64_t C,
                      int64_t H, int64_t W, int type, cudaStream_t st);
-void masked_sums_launch(const float* diff, const float* mask, int64_t n, float* out2, cudaStream_t st);
+int masked_sums_launch(const float* diff, const float* mask, int64_t n, float* out2, cudaStream_t st);
 int box9_tma_fwd_bwd_masked(const float* es, const float* ta, const float* go, const float* mask, float* out, float* gi,
                             float* sums2, int64_t B, int64_t C, int64_t H, int64_t W, int type, cudaStream_t st);
 int census_pairs_fwd(const float* es, const float* ta, float* out, int64_t B, int64_t C, int64_t H, int64_t W, int type,
@@ -800,20 +800,11 @@ static bool census_bwd_launch(const float* e, const float* t, const float* g, fl
                               int64_t H, int64_t W, int type, float eps, int vec, cudaStream_t st,
                               const float* mask = nullptr, float* sums2 = nullptr) {
   dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CB_H), nb);
-  char* sc = nullptr;
-  unsigned* ticket = nullptr;
-  double* partials = nullptr;
+  MsSlot ms = {nullptr, nullptr, nullptr};
   const size_t nblk = (size_t)grid.x * grid.y * grid.z;
-  if (mask && !masked_sums_slot(nblk, &ticket, &partials)) {
-    sc = static_cast<char*>(scratch_alloc(16 + nblk * 16, st));
-    if (!sc || cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
-      cudaGetLastError();
-      scratch_free(sc, st);
-      return false;
-    }
-    ticket = reinterpret_cast<unsigned*>(sc);
-    partials = reinterpret_cast<double*>(sc + 16);
-  }
+  if (mask && !ms_acquire(nblk, st, &ms)) return false;
+  unsigned* ticket = ms.ticket;
+  double* partials = ms.partials;
   const int iC = (int)C, iH = (int)H, iW = (int)W;
   if (type == 2) {
     if (out) photo_bwd_census9<2, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, mask, partials, ticket, sums2);
@@ -822,7 +813,7 @@ static bool census_bwd_launch(const float* e, const float* t, const float* g, fl
     if (out) photo_bwd_census9<3, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, mask, partials, ticket, sums2);
     else photo_bwd_census9<3, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, nullptr, nullptr, nullptr, nullptr);
   }
-  scratch_free(sc, st);
+  ms_release(&ms, st);
   return true;
 }
 
@@ -937,7 +928,7 @@ CTD_API int ctd_photometric_fwd_bwd_masked_f32(const float* es, const float* ta,
     if (type <= 1 && box9_tma_fwd_bwd_masked(es, ta, go, mask, out, gi, sums2, B, C, H, W, type, st))
       return check_launch("photometric_fwd_bwd_masked(box, fused)");
     if (type >= 2) {
-      const int vec = vec_ok(W, es, ta, go, gi) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+      const int vec = vec_ok(W, es, ta, go, gi) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
       if (census_bwd_launch(es, ta, go, gi, out, (int)B, C, H, W, type, eps, vec, st, mask, sums2)) {
         count_launch();
         return check_launch("photometric_fwd_bwd_masked(census, fused)");
@@ -945,7 +936,7 @@ CTD_API int ctd_photometric_fwd_bwd_masked_f32(const float* es, const float* ta,
     }
   }
   if (int rc = ctd_photometric_fwd_bwd_f32(es, ta, go, out, gi, B, C, H, W, bs, type, eps, stream)) return rc;
-  masked_sums_launch(out, mask, B * H * W, sums2, st);
+  if (int rc = masked_sums_launch(out, mask, B * H * W, sums2, st)) return rc;
   return check_launch("photometric_fwd_bwd_masked(separate)");
 }
 

@@ -461,15 +461,17 @@ int box9_tma_fwd_bwd_masked(const float* es, const float* ta, const float* go, c
   const int grid = std::min(ntiles, sm_count() * 2);
   const size_t smem = sizeof(FbSmem) + 128;
   if (!set_smem(type == 0 ? photo_fwd_bwd_box9_tma<0> : photo_fwd_bwd_box9_tma<1>, smem)) return 0;
-  double* partials = nullptr;
-  unsigned* ticket = nullptr;
-  if (mask && !masked_sums_slot((size_t)grid, &ticket, &partials)) return 0;  // grid <= 2 * SMs always fits a slot
+  MsSlot ms = {nullptr, nullptr, nullptr};
+  if (mask && !ms_acquire((size_t)grid, st, &ms)) return 0;
+  double* partials = ms.partials;
+  unsigned* ticket = ms.ticket;
   if (type == 0)
     photo_fwd_bwd_box9_tma<0><<<grid, 256, smem, st>>>(m_es, m_ta, m_go, out, gi, (int)H, (int)W, tiles_x, tiles_y, ntiles, mask,
                                                        partials, ticket, sums2);
   else
     photo_fwd_bwd_box9_tma<1><<<grid, 256, smem, st>>>(m_es, m_ta, m_go, out, gi, (int)H, (int)W, tiles_x, tiles_y, ntiles, mask,
                                                        partials, ticket, sums2);
+  ms_release(&ms, st);
   count_launch();
   return 1;
 }

@@ -78,17 +78,22 @@ masked_sums_kernel(const float* __restrict__ diff, const float* __restrict__ mas
 
 // library-internal form: workspace from the scratch pool (zeroed here), used by the unfused fall-back of
 // ctd_photometric_fwd_bwd_masked_f32
-void masked_sums_launch(const float* diff, const float* mask, int64_t n, float* out2, cudaStream_t st) {
+int masked_sums_launch(const float* diff, const float* mask, int64_t n, float* out2, cudaStream_t st) {
   const size_t bytes = 2 * RD_MAX_BLOCKS * sizeof(float) + 256;
   char* ws = static_cast<char*>(scratch_alloc(bytes, st));
-  if (!ws) return;
-  cudaMemsetAsync(ws, 0, 256, st);
+  if (!ws) return fail(CTD_ERR_NOMEM, "masked_sums: no scratch memory for the block partials");
+  if (cudaMemsetAsync(ws, 0, 256, st) != cudaSuccess) {
+    cudaGetLastError();
+    scratch_free(ws, st);
+    return fail(CTD_ERR_CUDA, "masked_sums: cannot zero the ticket");
+  }
   const int vec = ((reinterpret_cast<uintptr_t>(diff) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
   const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>(RD_MAX_BLOCKS, cdiv(n, RD_THREADS * 8)));
   masked_sums_kernel<<<blocks, RD_THREADS, 0, st>>>(diff, mask, n, out2, reinterpret_cast<float*>(ws + 256),
                                                     reinterpret_cast<unsigned int*>(ws), vec);
   count_launch();
   scratch_free(ws, st);
+  return CTD_OK;
 }
 
 }  // namespace ctd

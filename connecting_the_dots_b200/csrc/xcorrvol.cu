@@ -852,7 +852,8 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
   const size_t st_smem = sizeof(double) * 2 * (ST_H + 2 * R) * ST_W + sizeof(float) * (ST_H + 2 * R) * (ST_W + 2 * R);
   constexpr int TD = XS_TD;
   const size_t smem = sizeof(float) * TH * (XS_AW + XS_BW) + (16 / TD) * sizeof(XsStatRing<XsNst<TD>::value>);
-  static const bool attr_ok =
+  // the attribute belongs to the device (context), not to the process: set it on every call (a process may use several GPUs)
+  const bool attr_ok =
       cudaFuncSetAttribute(xcorr_stats_kernel<BS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem) == cudaSuccess &&
       cudaFuncSetAttribute(xcorr_sep_kernel<BS, TD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess &&
       cudaFuncSetAttribute(xcorr_sep_kernel<BS, TD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess;

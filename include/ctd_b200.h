@@ -161,6 +161,13 @@ int ctd_host_photometric_bwd_f32(const float* es, const float* ta, const float* 
 int ctd_host_photometric_fwd_bwd_f32(const float* es, const float* ta, const float* grad_out,
                                      float* out, float* grad_in, int64_t B, int64_t C, int64_t H,
                                      int64_t W, int block_size, int type, float eps);
+/* the whole use the reference's caller makes of the loss (model/networks.py:376-377) in one staged call: loss map
+ * (`out`, may be NULL: then it is not downloaded), d loss / d es for the caller's grad_out, and the masked-mean terms
+ * sums2[0] = sum(mask * loss), sums2[1] = sum(mask) (host float[2]) */
+int ctd_host_photometric_fwd_bwd_masked_f32(const float* es, const float* ta, const float* grad_out,
+                                            const float* mask, float* out, float* grad_in, float* sums2,
+                                            int64_t B, int64_t C, int64_t H, int64_t W, int block_size,
+                                            int type, float eps);
 int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C,
                           int64_t H, int64_t W, int64_t n_disps, int block_size);
 int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const float* K, int64_t* out,
@@ -173,7 +180,10 @@ int ctd_host_lcn_f32(const float* x, float* lcn, float* std, int64_t N, int64_t 
  * kernels (they return at once), so consecutive calls overlap on the bus; every result is in host memory when
  * ctd_host_end_batch() returns.  Input buffers must stay untouched, output buffers unread, until then.
  * An input that several photometric calls of one batch read (same host address and size: the image pair of two
- * loss types, the gradient weights) is uploaded once. */
+ * loss types, the gradient weights) is uploaded once.  An input that is an OUTPUT of an earlier call of the same batch
+ * (LCN's std used as the loss mask, ProjNN's indices fed to CrossCheck) is taken from that call's device buffer when
+ * address and size match exactly (no copy at all); any other overlap with an output still in flight first waits for
+ * the downloads, then uploads what the host holds. */
 int ctd_host_begin_batch(void);
 int ctd_host_end_batch(void);
 /* host-to-device bytes the calling thread's current (or last) batch copied, and bytes it did not have to copy again */

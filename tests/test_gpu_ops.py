@@ -280,6 +280,58 @@ def test_lcn_vs_oracle(tx, shape):
     assert torch.equal(l2, l) and torch.equal(s2, s)
 
 
+def _lcn_reference_recipe(x, r, e):
+    """model/networks.py:523-533 restated with the same torch ops (on whatever device x lives)."""
+    k = 2 * r + 1
+    w = torch.ones(1, 1, k, k, device=x.device)
+    pad = torch.nn.functional.pad(x, (r,) * 4, mode="reflect")
+    box, box2 = torch.nn.functional.conv2d(pad, w), torch.nn.functional.conv2d(pad * pad, w)
+    avg = box / k ** 2
+    std = torch.sqrt(box2 / k ** 2 - avg ** 2 + 1e-6) + e
+    return (x - avg) / std, std
+
+
+def test_lcn_vs_reference_recipe_on_baseline_frames(tx):
+    """How far two evaluations of the reference's own LCN recipe are apart (torch on the CPU vs torch on this GPU, TF32
+    off), and the kernel against both, on 8 BASELINE synthetic frames (480x640, camera noise: no exactly-flat windows).
+    The kernel has to be at least as close to each reference evaluation as they are to each other, and within the
+    north-star 1e-5 of the CPU evaluation when the two reference evaluations themselves agree to 1e-5."""
+    from connecting_the_dots_b200 import synth
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    x = torch.from_numpy(synth.make_batch(8)["im"])
+    lc, sc = _lcn_reference_recipe(x, 5, 0.05)
+    lg, sg = _lcn_reference_recipe(x.to(DEV), 5, 0.05)
+    l, s = tx.lcn(x.to(DEV), 5, 0.05)
+    rel = lambda a, b: float((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max())
+    ref_vs_ref = max(rel(lg, lc), rel(sg, sc))
+    k_cpu, k_gpu = max(rel(l, lc), rel(s, sc)), max(rel(l, lg.cpu()), rel(s, sg.cpu()))
+    print("LCN on BASELINE frames: reference cpu-vs-cuda %.2e, kernel-vs-cpu %.2e, kernel-vs-cuda %.2e" % (ref_vs_ref, k_cpu, k_gpu))
+    assert k_cpu <= max(1e-5, 2 * ref_vs_ref), (k_cpu, ref_vs_ref)
+    assert k_gpu <= max(1e-5, 2 * ref_vs_ref), (k_gpu, ref_vs_ref)
+    if ref_vs_ref <= 1e-5:
+        assert k_cpu <= 1e-5 and k_gpu <= 1e-5
+
+
+def test_lcn_reference_disagrees_with_itself_on_flat_fixture(tx, golden):
+    """The 2e-4 bound of test_lcn_golden is the reference's own: on the golden fixture (which contains an exactly flat
+    region, var = 1e-6 floor after cancellation) torch-on-CPU and torch-on-CUDA evaluations of networks.py:523-533 are
+    compared with each other; the kernel must be no further from either than 2e-4 and the fixture's two reference
+    evaluations are reported."""
+    torch.backends.cudnn.allow_tf32 = False
+    g = golden("lcn")
+    x = torch.from_numpy(g["x"])
+    lc, sc = _lcn_reference_recipe(x, 5, 0.05)
+    lg, sg = _lcn_reference_recipe(x.to(DEV), 5, 0.05)
+    rel = lambda a, b: float((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max())
+    print("LCN golden fixture: reference cpu-vs-cuda lcn %.2e std %.2e" % (rel(lg, lc), rel(sg, sc)))
+    l, s = tx.lcn(x.to(DEV), 5, 0.05)
+    for ref_l, ref_s in ((lc, sc), (lg, sg)):
+        assert rel(l, ref_l) <= 2e-4 and rel(s, ref_s) <= 2e-4
+    # the committed golden came from the reference's own class on CPU torch: same numbers as the recipe above
+    assert rel(lc, torch.from_numpy(g["r5_lcn"])) <= 1e-6
+
+
 def test_lcn_f64_and_errors(tx):
     rng = np.random.RandomState(2)
     x = rng.rand(2, 1, 30, 50)
@@ -392,6 +444,27 @@ def test_xcorrvol_full_size_properties(tx):
     assert torch.equal(one, vol[1])
 
 
+@pytest.mark.parametrize("bs", (9, 5))
+def test_xcorrvol_full_size_golden(tx, golden, bs):
+    """BASELINE configs[2] at its own size against the UNMODIFIED reference: 480x640, D = 128, the batched B = 8 call;
+    image 0 is compared with the rows of the reference's volume kept in tests/golden/xcorrvol_full.npz
+    (tests/golden/make_golden_full.py: oracle/_ref xcorrvol_cpu on the same synthetic LCN'd pair)."""
+    from connecting_the_dots_b200 import synth
+    g = golden("xcorrvol_full")
+    d = synth.make_batch(8)
+    in0, in1 = d["ta"], d["pat_lcn"]
+    # the fixture was made from the same seeded inputs
+    assert np.array_equal(in0[0, 0, 240], g["in0_row240"]) and np.array_equal(in1[0, 0, 240], g["in1_row240"])
+    assert float(in0[0].astype(np.float64).sum()) == float(g["in0_sum"])
+    vol = tx.xcorrvol(cu(in0), cu(in1), 128, bs)
+    assert vol.shape == (8, 128, 480, 640)
+    rows = torch.from_numpy(g["rows"]).to(DEV)
+    got = vol[0].index_select(1, rows).cpu().numpy()
+    assert_close(got, g["bs%d" % bs], what="xcorrvol 480x640 D128 bs%d vs reference" % bs)
+    one = tx.xcorrvol(cu(in0[0]), cu(in1[0]), 128, bs)   # the reference's unbatched 3-D signature, same result
+    assert torch.equal(one, vol[0])
+
+
 def test_xcorrvol_synthetic_lcn_data(tx):
     """LCN'd dot-pattern rows (the BASELINE config 3 data) on a crop the oracle finishes quickly."""
     from connecting_the_dots_b200 import synth
@@ -482,6 +555,39 @@ def test_geometric_step_composition(tx):
             assert np.array_equal(i01.cpu().numpy(), o01) and np.array_equal(i10.cpu().numpy(), o10)
             assert np.array_equal(m01.cpu().numpy(), oracle.crosscheck(o01.ravel(), o10.ravel()))
             assert np.array_equal(m10.cpu().numpy(), oracle.crosscheck(o10.ravel(), o01.ravel()))
+
+
+def test_geometric_step_full_size(tx):
+    """BASELINE configs[3] at its stated size: a 4-frame track at 480x640 -- ProjNN (patch 3) in both directions for the
+    6 frame pairs as ONE batched launch of 12 queries, CrossCheck in both directions, and PhotometricLoss census_sad
+    forward + backward on the 4 frames.  Indices and masks bit-exact, loss and gradient within 1e-5 of the oracle."""
+    from connecting_the_dots_b200 import synth
+    T, H, W = 4, 480, 640
+    xyz, K, poses = synth.make_clouds(T, H, W)
+    pairs = [(i, j) for i in range(T) for j in range(T) if i != j]
+    rev = [pairs.index((j, i)) for i, j in pairs]
+    x0 = np.stack([synth.transform(xyz[i], poses[j]) for i, j in pairs])
+    x1 = np.stack([xyz[j] for i, j in pairs])
+    idx = tx.proj_nn(cu(x0), cu(x1), cu(K), 3)
+    o_idx = oracle.proj_nn(x0, x1, K, 3)
+    assert np.array_equal(idx.cpu().numpy(), o_idx)
+    assert (o_idx >= 0).mean() > 0.5   # the synthetic track overlaps: the test is not vacuous
+    # CrossCheck pair p against its reverse pair, on per-image (shard-local) flat indices as the reference would see them
+    hw = H * W
+    loc = idx.view(len(pairs), -1) - (torch.arange(len(pairs), device=DEV) * hw).view(-1, 1)
+    loc = torch.where(idx.view(len(pairs), -1) >= 0, loc, idx.view(len(pairs), -1))
+    o_loc = np.where(o_idx.reshape(len(pairs), -1) >= 0, o_idx.reshape(len(pairs), -1) - (np.arange(len(pairs)) * hw)[:, None], -1)
+    n_mutual = 0
+    for p, q in enumerate(rev):
+        m = tx.crosscheck(loc[p].contiguous(), loc[q].contiguous())
+        om = oracle.crosscheck(o_loc[p], o_loc[q])
+        assert np.array_equal(m.cpu().numpy(), om)
+        n_mutual += int(om.sum())
+    assert n_mutual > 0
+    d = synth.make_batch(T, H, W)
+    fwd, bwd = photometric_both(tx, d["es"], d["ta"], d["go"], 9, 3, 0.5)
+    assert_close(fwd, oracle.photometric_loss_forward(d["es"], d["ta"], 9, 3, 0.5), what="census_sad fwd, 4 frames")
+    assert_close(bwd, oracle.photometric_loss_backward(d["es"], d["ta"], d["go"], 9, 3, 0.5), what="census_sad bwd, 4 frames")
 
 
 # ---------------------------------------------------------------- host-buffer C ABI
@@ -614,9 +720,139 @@ def test_host_api_deferred_batch_matches_synchronous_calls(tx):
         _lib.call("ctd_host_end_batch")  # no batch open
 
 
+def test_host_api_batch_output_feeds_later_call(tx):
+    """Inside a deferred batch an OUTPUT of one call that is an INPUT of a later one (LCN's lcn / std as the loss's target
+    and mask; ProjNN's indices into CrossCheck) must not be re-uploaded from the stale host buffer: exact matches are
+    served from the producer's device buffer, partial overlaps wait for the download.  Checked against the same calls
+    made synchronously, with the host output buffers poisoned beforehand."""
+    from connecting_the_dots_b200 import _lib, synth
+    B, H, W = 4, 64, 96
+    d = synth.make_batch(B, H, W)
+    P = lambda a, off=0: ctypes.c_void_p(a.ctypes.data + off)
+    xyz, K, poses = synth.make_clouds(2, H, W)
+    x01 = np.ascontiguousarray(synth.transform(xyz[0], poses[1])[None])
+    x10 = np.ascontiguousarray(synth.transform(xyz[1], poses[0])[None])
+    x0, x1 = np.ascontiguousarray(xyz[0][None]), np.ascontiguousarray(xyz[1][None])
+    res = []
+    for deferred in (False, True):
+        lcn, std = np.full_like(d["im"], 7.0), np.full_like(d["im"], 7.0)   # poison: a stale upload would show
+        out, gi = np.full_like(d["es"], 7.0), np.full_like(d["es"], 7.0)
+        gi_half = np.full_like(d["es"][:2], 7.0)
+        sums, sums_half = np.zeros(2, np.float32), np.zeros(2, np.float32)
+        i01, i10 = np.full((1, H, W), -5, np.int64), np.full((1, H, W), -5, np.int64)
+        m = np.full(H * W, 9, np.uint8)
+        if deferred:
+            _lib.call("ctd_host_begin_batch")
+        _lib.call("ctd_host_lcn_f32", P(d["im"]), P(lcn), P(std), B, H, W, 5, 0.05)
+        # exact match: ta = lcn output, mask = std output, same chunking
+        _lib.call("ctd_host_photometric_fwd_bwd_masked_f32", P(d["es"]), P(lcn), P(d["go"]), P(std), P(out), P(gi), P(sums),
+                  B, 1, H, W, 9, 3, 0.5)
+        # partial overlap: the first two images only, no loss map wanted
+        _lib.call("ctd_host_photometric_fwd_bwd_masked_f32", P(d["es"]), P(lcn), P(d["go"]), P(std), None, P(gi_half), P(sums_half),
+                  2, 1, H, W, 9, 1, 0.5)
+        _lib.call("ctd_host_proj_nn_f32", P(x01), P(x1), P(K), P(i01), 1, H, W, 3)
+        _lib.call("ctd_host_proj_nn_f32", P(x10), P(x0), P(K), P(i10), 1, H, W, 3)
+        _lib.call("ctd_host_crosscheck", P(i01), P(i10), P(m), H * W, H * W)
+        if deferred:
+            _lib.call("ctd_host_end_batch")
+        res.append((lcn, std, out, gi, gi_half, sums, sums_half, i01, i10, m))
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+    lcn, std, out, gi, gi_half, sums, sums_half, i01, i10, m = res[1]
+    lo, so = oracle.lcn(d["im"], 5, 0.05)
+    assert_close(lcn, lo, what="lcn")
+    assert_close(out, oracle.photometric_loss_forward(d["es"], lcn, 9, 3, 0.5), what="loss on the batch's own lcn")
+    assert_close(gi, oracle.photometric_loss_backward(d["es"], lcn, d["go"], 9, 3, 0.5), what="grad")
+    assert_close(gi_half, oracle.photometric_loss_backward(d["es"][:2], lcn[:2], d["go"][:2], 9, 1, 0.5), what="grad, half batch")
+    want = np.array([(std.astype(np.float64) * out).sum(), std.astype(np.float64).sum()])
+    assert np.abs(sums - want).max() <= 1e-5 * want.max()
+    o2 = oracle.photometric_loss_forward(d["es"][:2], lcn[:2], 9, 1, 0.5)
+    want = np.array([(std[:2].astype(np.float64) * o2).sum(), std[:2].astype(np.float64).sum()])
+    assert np.abs(sums_half - want).max() <= 1e-5 * want.max()
+    assert np.array_equal(m, oracle.crosscheck(i01.ravel(), i10.ravel())) and m.max() <= 1
+
+
+def test_masked_loss_calls_do_not_share_reduction_slots(tx):
+    """The ticket / block-partial workspace of the fused masked calls: captured calls own their slot, eager calls share
+    one per stream.  Two graphs replayed on two streams while eager calls run on a third must all keep producing the
+    sums of their own inputs."""
+    from connecting_the_dots_b200 import _lib
+    B, H, W = 2, 96, 160
+    torch.manual_seed(3)
+    def make(seed):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        t = {k: torch.randn(B, 1, H, W, generator=g).to(DEV) for k in ("es", "ta")}
+        t["go"] = torch.rand(B, 1, H, W, generator=g).to(DEV)
+        t["mask"] = torch.rand(B, 1, H, W, generator=g).to(DEV) + 0.5
+        t["out"], t["gi"], t["sums"] = torch.empty(B, 1, H, W, device=DEV), torch.empty(B, 1, H, W, device=DEV), torch.zeros(2, device=DEV)
+        return t
+    def launch(t, ty, st):
+        _lib.call("ctd_photometric_fwd_bwd_masked_f32", t["es"].data_ptr(), t["ta"].data_ptr(), t["go"].data_ptr(), t["mask"].data_ptr(),
+                  t["out"].data_ptr(), t["gi"].data_ptr(), t["sums"].data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
+    sets = [make(s) for s in range(3)]
+    want = []
+    for i, t in enumerate(sets):
+        launch(t, 3 if i != 1 else 1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        want.append(t["sums"].clone())
+        exp = torch.stack([(t["mask"].double() * t["out"].double()).sum(), t["mask"].double().sum()]).float()
+        assert torch.allclose(want[-1], exp, rtol=1e-5)
+    graphs = []
+    for i in (0, 1):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            launch(sets[i], 3 if i != 1 else 1, torch.cuda.current_stream().cuda_stream)
+        graphs.append(g)
+    s0, s1, s2 = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    for it in range(20):
+        for t in sets:
+            t["sums"].zero_()
+        torch.cuda.synchronize()
+        with torch.cuda.stream(s0):
+            graphs[0].replay()
+        with torch.cuda.stream(s1):
+            graphs[1].replay()
+        launch(sets[2], 3, s2.cuda_stream)
+        torch.cuda.synchronize()
+        for t, w in zip(sets, want):
+            assert torch.equal(t["sums"], w), it
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_xcorrvol_on_second_device(tx):
+    """Per-device kernel attributes (dynamic shared memory above 48 KB) are set for every device a process uses."""
+    rng = np.random.RandomState(0)
+    a = rng.rand(1, 40, 150).astype(np.float32)
+    b = rng.rand(1, 40, 150).astype(np.float32)
+    want = oracle.xcorrvol(a, b, 32, 9)
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        got = tx.xcorrvol(torch.from_numpy(a).to(dev), torch.from_numpy(b).to(dev), 32, 9)
+        assert_close(got.cpu().numpy(), want, what=dev)
+
+
 # ---------------------------------------------------------------- warp + fused loss (SURVEY 8f rank 1)
+class _OraclePhotometric(torch.autograd.Function):
+    """photometric_loss evaluated by the CPU ORACLE (forward and backward), so the reference recipe below does not lean
+    on the library under test for the loss half."""
+
+    @staticmethod
+    def forward(ctx, es, ta, bs, ty, eps):
+        ctx.save_for_backward(es, ta)
+        ctx.args = (bs, ty, eps)
+        out = oracle.photometric_loss_forward(es.detach().cpu().numpy(), ta.detach().cpu().numpy(), bs, ty, eps)
+        return torch.from_numpy(out).to(es.device)
+
+    @staticmethod
+    def backward(ctx, go):
+        es, ta = ctx.saved_tensors
+        bs, ty, eps = ctx.args
+        gi = oracle.photometric_loss_backward(es.detach().cpu().numpy(), ta.detach().cpu().numpy(),
+                                              np.ascontiguousarray(go.detach().cpu().numpy()), bs, ty, eps)
+        return torch.from_numpy(gi).to(es.device), None, None, None, None
+
+
 def _reference_pattern_loss(disp, pattern, im, std, loss_type, eps, tx):
-    """model/networks.py:358-378 with torch ops (grid_sample on the GPU) and the drop-in photometric_loss."""
+    """model/networks.py:358-378 with torch ops (grid_sample on the GPU) and the ORACLE's photometric loss."""
     B, _, H, W = disp.shape
     v, u = torch.meshgrid(torch.arange(H, device=disp.device, dtype=torch.float32),
                           torch.arange(W, device=disp.device, dtype=torch.float32), indexing="ij")
@@ -628,7 +864,7 @@ def _reference_pattern_loss(disp, pattern, im, std, loss_type, eps, tx):
     uv1 = uv1.view(-1, H, W, 2).clone()
     pat = pattern.expand(B, *pattern.shape[1:])
     proj = torch.nn.functional.grid_sample(pat, uv1, padding_mode="border", align_corners=False)
-    diff = tx.photometric_loss(proj.contiguous(), im.contiguous(), 9, loss_type, eps)
+    diff = _OraclePhotometric.apply(proj.contiguous(), im.contiguous(), 9, loss_type, eps)
     return (std * diff).sum() / std.sum(), proj
 
 

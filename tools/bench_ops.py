@@ -58,7 +58,7 @@ def timeit(fn, iters, warmup=5, nrep=NREP):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--only", default="calib,photometric,warp,pyramid,geometric,disparity,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce")
+    ap.add_argument("--only", default="calib,photometric,warp,pyramid,geometric,disparity,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce,gpu_reference")
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
     only = set(args.only.split(","))
@@ -312,6 +312,26 @@ def main():
         ms, mn = timeit(f, args.iters)
         res["ops"]["nn_16384x16384"] = {"ms_median": ms, "ms_min": mn, "gpair_s": n * n / ms / 1e6}
         print("nn", res["ops"]["nn_16384x16384"], file=sys.stderr)
+    if "gpu_reference" in only:
+        # the reference's OWN CUDA extension (oracle/_ref/ctd_ref_ext_cuda.so, unmodified, sm_100) on the same box and the
+        # same rotating buffers: the "existing GPU kernel" bar.  Stream launches on the legacy default stream, as the
+        # reference issues them.
+        import ref_gpu  # oracle/: comparison leg only
+        T = 4
+        xyz, K, poses = synth.make_clouds(T, H, W)
+        pairs = [(i, j) for i in range(T) for j in range(T) if i != j]
+        x0 = torch.from_numpy(np.stack([synth.transform(xyz[i], poses[j]) for i, j in pairs])).to(dev)
+        x1 = torch.from_numpy(np.stack([xyz[j] for i, j in pairs])).to(dev)
+        r = ref_gpu.time_ops(sets, B, H, W, iters=5, clouds=(x0, x1, torch.from_numpy(K).to(dev)), xcorr_images=min(B, 2))
+        if r is None:
+            res["gpu_reference"] = {"unavailable": "oracle/_ref/ctd_ref_ext_cuda.so not built"}
+        else:
+            res["gpu_reference"] = r
+            for name, v in r.items():
+                mine = res["ops"].get(name)
+                if mine:
+                    v["speedup_vs_reference_cuda"] = v["ms"] / mine["ms_median"]
+            print("gpu_reference", json.dumps(r), file=sys.stderr, flush=True)
     print(json.dumps(res))
 
 
