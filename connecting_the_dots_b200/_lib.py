@@ -4,7 +4,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libctd_b200.so")
+LIB_PATH = os.environ.get("CTD_B200_LIB") or os.path.join(_HERE, "libctd_b200.so")  # the override is for A/B builds of experiments
 
 _i64, _int, _f32, _f64, _ptr = ctypes.c_int64, ctypes.c_int, ctypes.c_float, ctypes.c_double, ctypes.c_void_p
 

@@ -80,12 +80,12 @@ __device__ __forceinline__ float4 ldg4_volatile(const float* p) {
 }
 
 // Two global sums (the caller's masked-mean numerator and denominator, model/networks.py:377) produced by a kernel
-// that has other work to do: every thread of a 256-thread block passes its share, the block's partial goes to
+// that has other work to do: every thread of the block (a whole number of warps) passes its share, the block's partial goes to
 // `partials[2 * block]`, and the last block to arrive (ticket counter, zero before the launch) adds all partials in
 // index order in fp64 and writes out2 -- deterministic for a given grid, no floating-point atomics.
 __device__ __forceinline__ void finish_masked_sums(double num, double den, double* __restrict__ partials,
                                                    unsigned* __restrict__ ticket, float* __restrict__ out2) {
-  __shared__ double s_num[8], s_den[8];
+  __shared__ double s_num[32], s_den[32];  // one per warp, up to 1024 threads
   __shared__ bool s_last;
   const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
   const unsigned nblocks = gridDim.x * gridDim.y * gridDim.z;

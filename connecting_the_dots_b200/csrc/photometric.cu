@@ -33,6 +33,9 @@ int box9_tma_fwd_bwd_masked(const float* es, const float* ta, const float* go, c
                             float* sums2, int64_t B, int64_t C, int64_t H, int64_t W, int type, cudaStream_t st);
 int census_pairs_fwd(const float* es, const float* ta, float* out, int64_t B, int64_t C, int64_t H, int64_t W, int type,
                      float eps, cudaStream_t st);
+// census_sym.cu: every pixel pair evaluated once (forward, backward or both, optional masked sums); false = not taken
+bool census_sym_launch(const float* es, const float* ta, const float* go, float* out, float* gi, const float* mask, float* sums2,
+                       int64_t B, int64_t C, int64_t H, int64_t W, int type, float eps, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------
 // generic kernels (any block size, channel count, size; float or double)
@@ -832,6 +835,8 @@ CTD_API int ctd_photometric_fwd_f32(const float* es, const float* ta, float* out
   if (!fast9_ok(bs, H, W) || C < 1 || B < 1) return fwd_impl<float>(es, ta, out, B, C, H, W, bs, type, eps, st);
   if (int rc = check_common(es, ta, out, B, C, H, W, bs, type)) return rc;
   if (type <= 1 && box9_tma_fwd(es, ta, out, B, C, H, W, type, st)) return check_launch("photometric_fwd(tma)");
+  if (type >= 2 && es && ta && out && census_sym_launch(es, ta, nullptr, out, nullptr, nullptr, nullptr, B, C, H, W, type, eps, st))
+    return check_launch("photometric_fwd(census, pair-symmetric)");
   if (type >= 2 && census_pairs_fwd(es, ta, out, B, C, H, W, type, eps, st)) return check_launch("photometric_fwd(census pairs)");
   const int vec = vec_ok(W, es, ta, out, out);
   for (int64_t b0 = 0; b0 < B; b0 += 32768) {
@@ -866,6 +871,8 @@ CTD_API int ctd_photometric_bwd_f32(const float* es, const float* ta, const floa
   if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
   CTD_REQUIRE(go, "photometric_bwd: null grad_out");
   if (type <= 1 && box9_tma_bwd(es, ta, go, gi, B, C, H, W, type, st)) return check_launch("photometric_bwd(tma)");
+  if (type >= 2 && es && ta && gi && census_sym_launch(es, ta, go, nullptr, gi, nullptr, nullptr, B, C, H, W, type, eps, st))
+    return check_launch("photometric_bwd(census, pair-symmetric)");
   const int vec = vec_ok(W, es, ta, go, gi);
   for (int64_t b0 = 0; b0 < B; b0 += 32768) {
     const int nb = (int)std::min<int64_t>(32768, B - b0);
@@ -896,6 +903,8 @@ CTD_API int ctd_photometric_fwd_bwd_f32(const float* es, const float* ta, const 
   if (type >= 2 && type <= 3 && fast9_ok(bs, H, W) && C >= 1 && B >= 1) {
     if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
     CTD_REQUIRE(go && out, "photometric_fwd_bwd: null pointer");
+    if (es && ta && gi && census_sym_launch(es, ta, go, out, gi, nullptr, nullptr, B, C, H, W, type, eps, st))
+      return check_launch("photometric_fwd_bwd(census, pair-symmetric)");
     const int vec = vec_ok(W, es, ta, go, gi) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     for (int64_t b0 = 0; b0 < B; b0 += 32768) {
       const int nb = (int)std::min<int64_t>(32768, B - b0);
@@ -927,6 +936,8 @@ CTD_API int ctd_photometric_fwd_bwd_masked_f32(const float* es, const float* ta,
   if (fast9_ok(bs, H, W) && C >= 1 && B >= 1 && B <= 32768) {
     if (type <= 1 && box9_tma_fwd_bwd_masked(es, ta, go, mask, out, gi, sums2, B, C, H, W, type, st))
       return check_launch("photometric_fwd_bwd_masked(box, fused)");
+    if (type >= 2 && es && ta && gi && census_sym_launch(es, ta, go, out, gi, mask, sums2, B, C, H, W, type, eps, st))
+      return check_launch("photometric_fwd_bwd_masked(census, pair-symmetric)");
     if (type >= 2) {
       const int vec = vec_ok(W, es, ta, go, gi) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
       if (census_bwd_launch(es, ta, go, gi, out, (int)B, C, H, W, type, eps, vec, st, mask, sums2)) {

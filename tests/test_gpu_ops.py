@@ -108,6 +108,7 @@ def test_census_pair_kernels_match_gather_kernels(tx, ty):
     es = rng.randn(2, 1, 150, 280).astype(np.float32)
     ta = (es + 0.5 * rng.randn(2, 1, 150, 280)).astype(np.float32)
     go = rng.rand(2, 1, 150, 280).astype(np.float32)
+    _lib.set_option("census_sym", 0)   # the gather-era kernels: forward-only pair kernel vs shared-memory gather
     _lib.set_option("census_pairs", 1)
     try:
         fwd, bwd = photometric_both(tx, es, ta, go, 9, ty, 0.5)
@@ -115,6 +116,7 @@ def test_census_pair_kernels_match_gather_kernels(tx, ty):
         fwd0, bwd0 = photometric_both(tx, es, ta, go, 9, ty, 0.5)
     finally:
         _lib.set_option("census_pairs", 2)
+        _lib.set_option("census_sym", 2)
     assert_close(fwd, fwd0, what="pairs vs gather fwd")
     assert_close(bwd, bwd0, what="pairs vs gather bwd")
     assert_close(fwd, oracle.photometric_loss_forward(es, ta, 9, ty, 0.5), what="pairs vs oracle fwd")
@@ -128,6 +130,7 @@ def test_census_pair_kernel_strip_layouts(tx, shape):
     rng = np.random.RandomState(W)
     es = rng.randn(B, C, H, W).astype(np.float32)
     ta = (es + 0.7 * rng.randn(B, C, H, W)).astype(np.float32)
+    _lib.set_option("census_sym", 0)
     _lib.set_option("census_pairs", 1)
     try:
         for ty in (2, 3):
@@ -135,6 +138,100 @@ def test_census_pair_kernel_strip_layouts(tx, shape):
             assert_close(got, oracle.photometric_loss_forward(es, ta, 9, ty, 0.5), what="pairs fwd %s" % TYPES[ty])
     finally:
         _lib.set_option("census_pairs", 2)
+        _lib.set_option("census_sym", 2)
+
+
+SYM_SHAPES = [(1, 16, 16), (2, 33, 132), (1, 40, 67), (1, 130, 200), (1, 250, 48), (3, 128, 36), (1, 129, 150), (2, 61, 301)]
+
+
+def _census_all_entry_points(tx, es, ta, go, mask, ty, eps=0.5):
+    """forward, backward, fused forward+backward and the fused masked call of one census mode -> dict of numpy arrays"""
+    from connecting_the_dots_b200 import _lib
+    B, _, H, W = es.shape
+    e, t, g, m = cu(es), cu(ta), cu(go), cu(mask)
+    r = {"fwd": tx.ext_cuda.photometric_loss_forward(e, t, 9, ty, eps), "bwd": tx.ext_cuda.photometric_loss_backward(e, t, g, 9, ty, eps)}
+    r["f_fwd"], r["f_bwd"] = tx.ext_cuda.photometric_loss_forward_backward(e, t, g, 9, ty, eps)
+    out, gi, sums = torch.empty_like(e), torch.empty_like(e), torch.zeros(2, device=DEV)
+    _lib.call("ctd_photometric_fwd_bwd_masked_f32", e.data_ptr(), t.data_ptr(), g.data_ptr(), m.data_ptr(), out.data_ptr(), gi.data_ptr(),
+              sums.data_ptr(), B, 1, H, W, 9, ty, eps, torch.cuda.current_stream().cuda_stream)
+    r["m_fwd"], r["m_bwd"], r["sums"] = out, gi, sums
+    return {k: v.cpu().numpy() for k, v in r.items()}
+
+
+@pytest.mark.parametrize("shape", SYM_SHAPES)
+@pytest.mark.parametrize("ty", (2, 3))
+def test_census_pair_symmetric_kernel_vs_oracle(tx, shape, ty):
+    """census_sym.cu (every pixel pair evaluated once) through all four entry points against the oracle: one and several
+    strips (120 useful rows each), one and several column tiles, widths that are / are not multiples of four (128-bit
+    and scalar staging), rows below the last strip, the clamped border band."""
+    B, H, W = shape
+    rng = np.random.RandomState(H * 1000 + W + ty)
+    es = rng.randn(B, 1, H, W).astype(np.float32)
+    ta = (es + 0.6 * rng.randn(B, 1, H, W)).astype(np.float32)
+    go = rng.randn(B, 1, H, W).astype(np.float32)
+    mask = (rng.rand(B, 1, H, W) + 0.5).astype(np.float32)
+    from connecting_the_dots_b200 import _lib
+    _lib.set_option("census_sym", 1)   # every entry point through the pair-symmetric kernel (default: forward only)
+    try:
+        r = _census_all_entry_points(tx, es, ta, go, mask, ty)
+    finally:
+        _lib.set_option("census_sym", 2)
+    of, ob = oracle.photometric_loss_forward(es, ta, 9, ty, 0.5), oracle.photometric_loss_backward(es, ta, go, 9, ty, 0.5)
+    for k in ("fwd", "f_fwd", "m_fwd"):
+        assert_close(r[k], of, what=k)
+    for k in ("bwd", "f_bwd", "m_bwd"):
+        assert_close(r[k], ob, what=k)
+    want = np.array([(mask.astype(np.float64) * of).sum(), mask.astype(np.float64).sum()])
+    assert np.abs(r["sums"] - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("ty", (2, 3))
+def test_census_pair_symmetric_kernel_matches_gather_kernels(tx, ty):
+    """A/B inside the library at the bench size: pair-symmetric kernel (census_sym = 1) against the gather kernels."""
+    from connecting_the_dots_b200 import _lib, synth
+    d = synth.make_batch(3)
+    _lib.set_option("census_sym", 1)
+    try:
+        a = _census_all_entry_points(tx, d["es"], d["ta"], d["go"], d["std"], ty)
+        again = _census_all_entry_points(tx, d["es"], d["ta"], d["go"], d["std"], ty)
+        _lib.set_option("census_sym", 0)
+        b = _census_all_entry_points(tx, d["es"], d["ta"], d["go"], d["std"], ty)
+    finally:
+        _lib.set_option("census_sym", 2)
+    for k in a:
+        if k == "sums":
+            assert np.abs(a[k] - b[k]).max() <= 1e-5 * np.abs(b[k]).max()
+        else:
+            assert_close(a[k], b[k], what=k)
+    for k in a:
+        assert np.array_equal(a[k], again[k]), "run-to-run difference in " + k
+
+
+def test_census_pair_symmetric_kernel_exact_sign_decisions(tx):
+    """census_sad's sign(): images quantised to a few levels make many window terms EXACTLY zero (sign 0 in the reference)
+    or equal up to rounding; every such pixel has to come out of the exact pass like ext_cpu's.  Also a constant image
+    (every pair a tie) and a pair of images that differ in one pixel."""
+    rng = np.random.RandomState(5)
+    B, H, W = 2, 70, 120
+    es = rng.randint(0, 3, (B, 1, H, W)).astype(np.float32)
+    ta = rng.randint(0, 3, (B, 1, H, W)).astype(np.float32)
+    go = rng.rand(B, 1, H, W).astype(np.float32)
+    cases = [(es, ta), (es, es.copy()), (np.full_like(es, 0.25), np.full_like(es, 0.75))]
+    one = es.copy()
+    one[0, 0, 30, 50] += 1.0
+    cases.append((one, es))
+    from connecting_the_dots_b200 import _lib
+    for mode in (1, 2):   # the pair-symmetric kernel's exact pass, then the default dispatch (gather kernel's exact pass)
+        _lib.set_option("census_sym", mode)
+        try:
+            for e, t in cases:
+                fwd, bwd = photometric_both(tx, e, t, go, 9, 3, 0.5)
+                assert_close(fwd, oracle.photometric_loss_forward(e, t, 9, 3, 0.5), what="quantised fwd")
+                ob = oracle.photometric_loss_backward(e, t, go, 9, 3, 0.5)
+                scale = max(float(np.abs(ob).max()), 1e-30)
+                assert float(np.abs(bwd - ob).max()) <= 1e-5 * scale + 1e-12, "quantised bwd"
+        finally:
+            _lib.set_option("census_sym", 2)
 
 
 @pytest.mark.parametrize("shape", [(2, 1, 40, 72), (1, 2, 33, 50), (1, 1, 96, 160), (1, 1, 7, 9)])
@@ -283,7 +380,7 @@ def test_lcn_vs_oracle(tx, shape):
 def _lcn_reference_recipe(x, r, e):
     """model/networks.py:523-533 restated with the same torch ops (on whatever device x lives)."""
     k = 2 * r + 1
-    w = torch.ones(1, 1, k, k, device=x.device)
+    w = torch.ones(1, 1, k, k, device=x.device, dtype=x.dtype)
     pad = torch.nn.functional.pad(x, (r,) * 4, mode="reflect")
     box, box2 = torch.nn.functional.conv2d(pad, w), torch.nn.functional.conv2d(pad * pad, w)
     avg = box / k ** 2
@@ -292,25 +389,44 @@ def _lcn_reference_recipe(x, r, e):
 
 
 def test_lcn_vs_reference_recipe_on_baseline_frames(tx):
-    """How far two evaluations of the reference's own LCN recipe are apart (torch on the CPU vs torch on this GPU, TF32
-    off), and the kernel against both, on 8 BASELINE synthetic frames (480x640, camera noise: no exactly-flat windows).
-    The kernel has to be at least as close to each reference evaluation as they are to each other, and within the
-    north-star 1e-5 of the CPU evaluation when the two reference evaluations themselves agree to 1e-5."""
+    """The kernel against the reference's own LCN recipe (networks.py:523-533) evaluated by torch on the CPU and on this
+    GPU (TF32 off), and all three against the same recipe in float64, on 8 BASELINE synthetic frames (480x640).
+    Measured (recorded by the print below): the two fp32 reference evaluations differ from each other by ~3e-5 and from
+    the float64 value by ~1e-4 in `std`, all of it on the ~2 % of windows that are flat (image clipped at 0 / 1), where
+    var = E[x^2] - avg^2 cancels to fp32 rounding noise above the 1e-6 floor.  Asserted:
+      * on every window with raw std > 0.02 (97.7 % of the pixels) the kernel matches BOTH reference evaluations to the
+        north-star 1e-5, lcn and std;
+      * everywhere, the kernel is closer to the float64 value than either fp32 reference evaluation is (exact box sums),
+        and within 2e-4 of both (the bound the formula allows, test_lcn_golden)."""
     from connecting_the_dots_b200 import synth
     torch.backends.cudnn.allow_tf32 = False
     torch.backends.cuda.matmul.allow_tf32 = False
     x = torch.from_numpy(synth.make_batch(8)["im"])
     lc, sc = _lcn_reference_recipe(x, 5, 0.05)
-    lg, sg = _lcn_reference_recipe(x.to(DEV), 5, 0.05)
-    l, s = tx.lcn(x.to(DEV), 5, 0.05)
-    rel = lambda a, b: float((a.double().cpu() - b.double().cpu()).abs().max() / b.double().abs().max())
-    ref_vs_ref = max(rel(lg, lc), rel(sg, sc))
-    k_cpu, k_gpu = max(rel(l, lc), rel(s, sc)), max(rel(l, lg.cpu()), rel(s, sg.cpu()))
-    print("LCN on BASELINE frames: reference cpu-vs-cuda %.2e, kernel-vs-cpu %.2e, kernel-vs-cuda %.2e" % (ref_vs_ref, k_cpu, k_gpu))
-    assert k_cpu <= max(1e-5, 2 * ref_vs_ref), (k_cpu, ref_vs_ref)
-    assert k_gpu <= max(1e-5, 2 * ref_vs_ref), (k_gpu, ref_vs_ref)
-    if ref_vs_ref <= 1e-5:
-        assert k_cpu <= 1e-5 and k_gpu <= 1e-5
+    lg, sg = (t.cpu() for t in _lcn_reference_recipe(x.to(DEV), 5, 0.05))
+    l64, s64 = _lcn_reference_recipe(x.double(), 5, 0.05)
+    l, s = (t.cpu() for t in tx.lcn(x.to(DEV), 5, 0.05))
+    textured = (s64 - 0.05) > 0.02
+
+    def rel(a, b, where=None):
+        d = (a.double() - b.double()).abs()
+        if where is not None:
+            d = d[where]
+        return float(d.max() / b.double().abs().max())
+
+    rows = {"ref cpu-vs-cuda": (rel(lg, lc), rel(sg, sc)), "ref cpu vs f64": (rel(lc, l64), rel(sc, s64)),
+            "ref cuda vs f64": (rel(lg, l64), rel(sg, s64)), "kernel vs f64": (rel(l, l64), rel(s, s64)),
+            "kernel vs ref cpu": (rel(l, lc), rel(s, sc)), "kernel vs ref cuda": (rel(l, lg), rel(s, sg)),
+            "kernel vs ref cpu, textured": (rel(l, lc, textured), rel(s, sc, textured)),
+            "kernel vs ref cuda, textured": (rel(l, lg, textured), rel(s, sg, textured))}
+    print("LCN on BASELINE frames (lcn, std), textured fraction %.4f: " % float(textured.float().mean())
+          + "; ".join("%s %.2e %.2e" % (k, *v) for k, v in rows.items()))
+    assert float(textured.float().mean()) > 0.95
+    for k in ("kernel vs ref cpu, textured", "kernel vs ref cuda, textured"):
+        assert max(rows[k]) <= 1e-5, (k, rows[k])
+    for q in (0, 1):
+        assert rows["kernel vs f64"][q] <= 1.2 * min(rows["ref cpu vs f64"][q], rows["ref cuda vs f64"][q]) + 1e-6, rows
+        assert max(rows["kernel vs ref cpu"][q], rows["kernel vs ref cuda"][q]) <= 2e-4, rows
 
 
 def test_lcn_reference_disagrees_with_itself_on_flat_fixture(tx, golden):
@@ -711,7 +827,8 @@ def test_host_api_deferred_batch_matches_synchronous_calls(tx):
             copied, saved = ctypes.c_uint64(0), ctypes.c_uint64(0)
             _lib.lib().ctd_host_batch_stats(ctypes.byref(copied), ctypes.byref(saved))
             plane = B * H * W * 4
-            assert saved.value == 3 * plane and copied.value >= 4 * plane
+            # ... and so did the point cloud that proj_nn reads as both xyz0 and xyz1 (3 floats per pixel)
+            assert saved.value == (3 + 3) * plane and copied.value >= 4 * plane
         res.append((lcn, std, o1, g1, o3, g3, idx))
     for a, b in zip(*res):
         assert np.array_equal(a, b)
