@@ -55,14 +55,24 @@ def timeit(fn, iters, warmup=5, nrep=NREP):
     return float(np.median(ts)), float(np.min(ts))
 
 
+ALL = "calib,photometric,warp,pyramid,geometric,disparity,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce,gpu_reference"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
-    ap.add_argument("--only", default="calib,photometric,warp,pyramid,geometric,disparity,lcn,xcorrvol,proj_nn,config4,nn,crosscheck,reduce,gpu_reference")
+    ap.add_argument("--only", default=ALL)
     ap.add_argument("--batch", type=int, default=8)
     args = ap.parse_args()
-    only = set(args.only.split(","))
-    dev = torch.device("cuda", 0)
+    print(json.dumps(run(args.only, args.iters, args.batch)))
+
+
+def run(only=ALL, iters=30, batch=8, device_index=0, verbose=True):
+    """Times the selected op families and returns the result dict (bench.py calls this for the ops beyond its step)."""
+    import types
+    args = types.SimpleNamespace(iters=iters, batch=batch)
+    only = set(only.split(","))
+    dev = torch.device("cuda", device_index)
     tx = ctd.torchext
     B = args.batch
     npx = B * H * W
@@ -74,7 +84,8 @@ def main():
         if extra:
             r.update(extra)
         res["ops"][name] = r
-        print(name, json.dumps(r), file=sys.stderr, flush=True)
+        if verbose:
+            print(name, json.dumps(r), file=sys.stderr, flush=True)
 
     NS = 5
     base = synth.make_batch(B, H, W)
@@ -311,7 +322,8 @@ def main():
             _lib.call("ctd_nn_f32", p0.data_ptr(), p1.data_ptr(), out.data_ptr(), n, n, st)
         ms, mn = timeit(f, args.iters)
         res["ops"]["nn_16384x16384"] = {"ms_median": ms, "ms_min": mn, "gpair_s": n * n / ms / 1e6}
-        print("nn", res["ops"]["nn_16384x16384"], file=sys.stderr)
+        if verbose:
+            print("nn", res["ops"]["nn_16384x16384"], file=sys.stderr)
     if "gpu_reference" in only:
         # the reference's OWN CUDA extension (oracle/_ref/ctd_ref_ext_cuda.so, unmodified, sm_100) on the same box and the
         # same rotating buffers: the "existing GPU kernel" bar.  Stream launches on the legacy default stream, as the
@@ -331,8 +343,9 @@ def main():
                 mine = res["ops"].get(name)
                 if mine:
                     v["speedup_vs_reference_cuda"] = v["ms"] / mine["ms_median"]
-            print("gpu_reference", json.dumps(r), file=sys.stderr, flush=True)
-    print(json.dumps(res))
+            if verbose:
+                print("gpu_reference", json.dumps(r), file=sys.stderr, flush=True)
+    return res
 
 
 if __name__ == "__main__":
