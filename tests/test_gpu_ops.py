@@ -721,7 +721,7 @@ def test_host_api(golden):
     assert_close(gi, oracle.photometric_loss_backward(es, ta, go, 9, 3, 0.5))
     out2 = np.empty_like(go)
     _lib.call("ctd_host_photometric_fwd_f32", P(es), P(ta), P(out2), 2, 1, 40, 72, 9, 3, 0.5)
-    assert np.array_equal(out, out2)
+    assert_close(out2, out, tol=2e-6)   # forward-only call: pair-symmetric kernel, fused call: gather kernel (other summation order)
     l, s = np.empty_like(es), np.empty_like(es)
     _lib.call("ctd_host_lcn_f32", P(es), P(l), P(s), 2, 40, 72, 5, 0.05)
     lo, so = oracle.lcn(es, 5, 0.05)
