@@ -287,6 +287,38 @@ def lcn_forward(x, radius, epsilon):
     return out, std
 
 
+def lcn_backward(x, lcn, std, grad_lcn, grad_std, radius, epsilon):
+    """Gradient of model/networks.py:523-533 w.r.t. its input (what autograd produces through the reference's torch
+    ops), from the forward's input and outputs and the upstream gradients of (lcn, std); either gradient may be None.
+    float32, [N,1,H,W]."""
+    for t, n in ((x, "x"), (lcn, "lcn"), (std, "std")):
+        _check_input_cuda(t, n)
+        _check(t.dtype == torch.float32, "lcn_backward is float32 only")
+    _check(x.dim() == 4 and x.size(1) == 1 and lcn.shape == x.shape and std.shape == x.shape, "x, lcn, std have to be N x 1 x H x W")
+    for t, n in ((grad_lcn, "grad_lcn"), (grad_std, "grad_std")):
+        if t is not None:
+            _check_input_cuda(t, n)
+            _check(t.shape == x.shape and t.dtype == torch.float32, n + " has to match x")
+    N, _, H, W = x.shape
+    gx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.call("ctd_lcn_bwd_f32", x.data_ptr(), lcn.data_ptr(), std.data_ptr(), 0 if grad_lcn is None else grad_lcn.data_ptr(),
+                  0 if grad_std is None else grad_std.data_ptr(), gx.data_ptr(), N, H, W, int(radius), float(epsilon), _stream(x))
+    return gx
+
+
+def lcn_cython(img, kernel_size, epsilon):
+    """data/lcn/lcn.pyx:16-58 `normalize` for one image [M,N] or a batch [B,M,N]: (lcn, std), zeros in the border."""
+    _check_input_cuda(img, "img")
+    _check(img.dtype == torch.float32 and img.dim() in (2, 3), "img has to be float32 [M,N] or [B,M,N]")
+    B = 1 if img.dim() == 2 else img.size(0)
+    M, N = img.shape[-2:]
+    out, std = torch.empty_like(img), torch.empty_like(img)
+    with torch.cuda.device(img.device):
+        _lib.call("ctd_lcn_cython_f32", img.data_ptr(), out.data_ptr(), std.data_ptr(), B, M, N, int(kernel_size), float(epsilon), _stream(img))
+    return out, std
+
+
 _reduce_ws = {}
 
 

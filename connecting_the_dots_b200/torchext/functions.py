@@ -259,25 +259,62 @@ def disparity_loss(disp, edge=None):
 
 
 class LCNFunction(torch.autograd.Function):
-    """Fused local contrast normalisation (model/networks.py:507-533); forward only -- in the
-    reference the gradient flows to an input image nobody reads (exp_synph.py:80-91)."""
+    """Fused local contrast normalisation (model/networks.py:507-533) with its gradient: the forward is one kernel, the
+    backward (ctd_lcn_bwd_f32) is what autograd produces through the reference's torch ops for upstream gradients of
+    both outputs.  (In the reference the gradient flows to an input image nobody reads, exp_synph.py:80-91.)"""
 
     @staticmethod
     def forward(ctx, x, radius, epsilon):
         if not x.is_cuda:
             raise RuntimeError("torchext.lcn: connecting_the_dots_b200 has no CPU implementation")
         out, std = ext_cuda.lcn_forward(x, radius, epsilon)
-        ctx.mark_non_differentiable(out, std)
+        ctx.radius, ctx.epsilon = radius, epsilon
+        if x.dtype == torch.float32 and x.requires_grad:
+            ctx.save_for_backward(x.detach(), out, std)
+        else:
+            ctx.mark_non_differentiable(out, std)
         return out, std
 
     @staticmethod
-    def backward(ctx, g0, g1):
-        return None, None, None
+    def backward(ctx, g_lcn, g_std):
+        x, out, std = ctx.saved_tensors
+        gl = None if g_lcn is None else g_lcn.contiguous()
+        gs = None if g_std is None else g_std.contiguous()
+        return ext_cuda.lcn_backward(x, out, std, gl, gs, ctx.radius, ctx.epsilon), None, None
 
 
 def lcn(x, radius=5, epsilon=0.05):
     """(x - box_mean) / (box_std + epsilon) over a (2*radius+1)^2 reflection-padded window -> (lcn, std)."""
     return LCNFunction.apply(x, radius, epsilon)
+
+
+def lcn_normalize(img, kernel_size=4, epsilon=0.01):
+    """The data generator's offline LCN, data/lcn/lcn.pyx:16-58 `normalize(img, kernel_size, epsilon)` (called at
+    data/create_syn_data.py:182): img [M,N] (or a batch [B,M,N]) -> (img_lcn, img_std), a border of kernel_size pixels left
+    at 0, std = sqrt of the centred two-pass variance.  Bit-identical to the Cython build; CUDA tensors only."""
+    if not img.is_cuda:
+        raise RuntimeError("torchext.lcn_normalize: connecting_the_dots_b200 has no CPU implementation")
+    return ext_cuda.lcn_cython(img.contiguous(), kernel_size, epsilon)
+
+
+def pyramid_pattern_similarity_loss(disps, patterns, ims, stds, loss_type="census_sad", loss_eps=0.5, block_size=9):
+    """The photometric part of the trainer's loss_forward (model/exp_synph.py:107-111) over the image pyramid
+    (exp_synph.py:25-27: 480x640 halved three times): for every scale s, RectifiedPatternSimilarityLoss(disps[s],
+    ims[s], stds[s]) with that scale's pattern (exp_synph.py:62-71).  `patterns` is one [1,1,Hp,Wp] tensor per scale (or
+    one tensor used for all).  Returns (vals: list of scalar tensors, pattern_proj of scale 0, detached) as the reference
+    keeps them; 3 kernels per scale forward+backward (warp, fused loss + gradient + masked mean, warp gradient), all
+    capture-safe, so the whole pyramid replays as one CUDA graph."""
+    if torch.is_tensor(patterns):
+        patterns = [patterns] * len(disps)
+    if not (len(disps) == len(patterns) == len(ims) == len(stds)):
+        raise RuntimeError("pyramid_pattern_similarity_loss: one disparity, pattern, image and std per scale")
+    vals, proj0 = [], None
+    for s, (d, p, im, sd) in enumerate(zip(disps, patterns, ims, stds)):
+        val, proj = pattern_similarity_loss(d, p, im, sd, loss_type, loss_eps, block_size)
+        if s == 0:
+            proj0 = proj.detach()
+        vals.append(val)
+    return vals, proj0
 
 
 def masked_mean_terms(diff, mask):

@@ -143,6 +143,17 @@ int ctd_lcn_f32(const float* x, float* lcn, float* std, int64_t N, int64_t H, in
 int ctd_lcn_f64(const double* x, double* lcn, double* std, int64_t N, int64_t H, int64_t W,
                 int radius, double epsilon, ctd_stream_t stream);
 
+/* ---- LCN backward: what autograd produces for networks.LCN (model/networks.py:523-533) w.r.t. its input, given the
+ * forward's input x, its outputs (lcn, std) and upstream gradients for both outputs (either may be NULL = zero). */
+int ctd_lcn_bwd_f32(const float* x, const float* lcn, const float* std, const float* grad_lcn, const float* grad_std,
+                    float* grad_x, int64_t N, int64_t H, int64_t W, int radius, float epsilon, ctd_stream_t stream);
+
+/* ---- the data generator's offline LCN: data/lcn/lcn.pyx:16-58 `normalize(img, kernel_size, epsilon)` (called at
+ * data/create_syn_data.py:182) for a batch of B images [M,N] -- no padding (a border of kernel_size pixels stays 0),
+ * centred two-pass variance, std = sqrt(var); bit-identical to the Cython build. */
+int ctd_lcn_cython_f32(const float* img, float* lcn, float* std, int64_t B, int64_t M, int64_t N, int kernel_size,
+                       float epsilon, ctd_stream_t stream);
+
 /* ---- masked loss reduction of the caller, model/networks.py:377: val = (mask*diff).sum() / mask.sum().
  * out2[0] = sum(mask*diff), out2[1] = sum(mask), deterministic.  `workspace`: device memory of
  * ctd_masked_sums_workspace_bytes() bytes, zero-filled once before first use, one per concurrent stream. */

@@ -49,3 +49,29 @@ void ctdo_crosscheck(const long long* in0, const long long* in1, uint8_t* out, l
     out[i] = (uint8_t)(j >= 0 && in1[j] >= 0 && (long long)i == in1[j]);
   }
 }
+
+/* data/lcn/lcn.pyx:16-58 `normalize(img, kernel_size, epsilon)`: the OFFLINE local contrast normalisation of the data
+ * generator (create_syn_data.py:182).  img [M,N] fp32 -> lcn, std [M,N]; a border of ks pixels stays 0 (lcn.pyx:22-23,
+ * 36-37).  All arithmetic in float, sums in the reference's order (rows outer, columns inner, lcn.pyx:40-50); the
+ * reference's `sqrt` is C's double sqrt applied to a float and rounded back to float (lcn.pyx:5-6), which equals sqrtf.
+ * Pinned bit-for-bit against the Cython build by tests/golden/lcn_cython.npz (make_golden_lcn_cython.py). */
+void ctdo_lcn_cython_f32(const float* img, float* lcn, float* sd, long M, long N, long ks, float eps) {
+  const float num = (float)((ks * 2 + 1) * (ks * 2 + 1));          /* lcn.pyx:33 */
+  for (long i = 0; i < M * N; ++i) lcn[i] = sd[i] = 0.0f;            /* lcn.pyx:22-23 */
+  for (long m = ks; m < M - ks; ++m)
+    for (long n = ks; n < N - ks; ++n) {
+      float mean = 0.0f;
+      for (long i = -ks; i <= ks; ++i)
+        for (long j = -ks; j <= ks; ++j) mean += img[(m + i) * N + n + j];      /* lcn.pyx:40-43 */
+      mean = mean / num;
+      float stddev = 0.0f;
+      for (long i = -ks; i <= ks; ++i)
+        for (long j = -ks; j <= ks; ++j) {
+          const float d = img[(m + i) * N + n + j] - mean;
+          stddev = stddev + d * d;                                                 /* lcn.pyx:47-50 */
+        }
+      stddev = (float)sqrt((double)(stddev / num));                                /* lcn.pyx:51 */
+      lcn[m * N + n] = (img[m * N + n] - mean) / (stddev + eps);                   /* lcn.pyx:54 */
+      sd[m * N + n] = stddev;                                                      /* lcn.pyx:55 */
+    }
+}

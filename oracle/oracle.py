@@ -121,3 +121,13 @@ def lcn(x, radius, epsilon):
     e = ctypes.c_float(epsilon) if x.dtype == np.float32 else ctypes.c_double(epsilon)
     getattr(lib(), "ctdo_lcn" + sfx)(_p(x), _p(o), _p(s), L(N), L(H), L(W), L(radius), e)
     return o, s
+
+
+def lcn_cython(img, kernel_size=4, epsilon=0.01):
+    """data/lcn/lcn.pyx:16-58 normalize(img [M,N] float32, kernel_size, epsilon) -> (lcn, std)."""
+    img = np.ascontiguousarray(img, dtype=np.float32)
+    M, N = img.shape
+    o, s = np.empty_like(img), np.empty_like(img)
+    L = ctypes.c_long
+    lib().ctdo_lcn_cython_f32(_p(img), _p(o), _p(s), L(M), L(N), L(kernel_size), ctypes.c_float(epsilon))
+    return o, s

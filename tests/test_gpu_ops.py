@@ -448,6 +448,44 @@ def test_lcn_reference_disagrees_with_itself_on_flat_fixture(tx, golden):
     assert rel(lc, torch.from_numpy(g["r5_lcn"])) <= 1e-6
 
 
+def test_lcn_normalize_matches_reference_cython_build(tx, golden):
+    """torchext.lcn_normalize = data/lcn/lcn.pyx normalize (the data generator's offline LCN): bit-identical to the
+    reference's Cython build on the golden inputs, and to the oracle on a 480x640 frame, single and batched."""
+    g = golden("lcn_cython")
+    for n in "abcde":
+        ks, eps = g[n + "_args"]
+        l, s = tx.lcn_normalize(cu(g[n + "_x"]), int(ks), float(eps))
+        assert np.array_equal(l.cpu().numpy(), g[n + "_lcn"]) and np.array_equal(s.cpu().numpy(), g[n + "_std"]), n
+    from connecting_the_dots_b200 import synth
+    im = synth.make_batch(2)["im"][:, 0]
+    l, s = tx.lcn_normalize(cu(im), 5, 0.1)          # create_syn_data.py:182 arguments
+    for b in range(2):
+        lo, so = oracle.lcn_cython(im[b], 5, 0.1)
+        assert np.array_equal(l[b].cpu().numpy(), lo) and np.array_equal(s[b].cpu().numpy(), so)
+    with pytest.raises(RuntimeError):
+        tx.lcn_normalize(torch.rand(8, 8), 2, 0.1)   # no CPU path
+
+
+@pytest.mark.parametrize("shape", [(2, 40, 70, 5), (1, 16, 16, 5), (1, 33, 45, 2), (1, 480, 640, 5), (2, 12, 9, 8)])
+def test_lcn_backward_matches_autograd_of_reference_recipe(tx, shape):
+    """d loss / d x of networks.LCN for upstream gradients of BOTH outputs, against torch autograd through the reference's
+    own recipe (networks.py:523-533) in float64; reflection-padded borders, mirrored windows from both sides on small images."""
+    N, H, W, r = shape
+    g = torch.Generator(device="cpu").manual_seed(H * W)
+    x = torch.rand(N, 1, H, W, generator=g)
+    gl, gs = torch.randn(N, 1, H, W, generator=g), torch.randn(N, 1, H, W, generator=g)
+    xd = x.double().requires_grad_(True)
+    l64, s64 = _lcn_reference_recipe(xd, r, 0.05)
+    (ref,) = torch.autograd.grad((l64 * gl.double()).sum() + (s64 * gs.double()).sum(), xd)
+    xg = x.to(DEV).requires_grad_(True)
+    l, s = tx.lcn(xg, r, 0.05)
+    (got,) = torch.autograd.grad((l * gl.to(DEV)).sum() + (s * gs.to(DEV)).sum(), xg)
+    assert_close(got.cpu().numpy(), ref.numpy(), tol=2e-5, what="lcn backward")
+    (got_l,) = torch.autograd.grad(tx.lcn(xg, r, 0.05)[0].mul(gl.to(DEV)).sum(), xg)     # only one output used
+    (ref_l,) = torch.autograd.grad((_lcn_reference_recipe(xd, r, 0.05)[0] * gl.double()).sum(), xd)
+    assert_close(got_l.cpu().numpy(), ref_l.numpy(), tol=2e-5, what="lcn backward, lcn output only")
+
+
 def test_lcn_f64_and_errors(tx):
     rng = np.random.RandomState(2)
     x = rng.rand(2, 1, 30, 50)
@@ -616,6 +654,34 @@ def test_proj_nn_vs_oracle(tx, dt):
     xb = np.stack([xyz[0], xyz[1]]).astype(dt)
     got = tx.proj_nn(cu(xb), cu(xb[::-1].copy()), cu(K), 3).cpu().numpy()   # batch offset in the flat index
     assert np.array_equal(got, oracle.proj_nn(xb, xb[::-1].copy(), K, 3))
+
+
+@pytest.mark.parametrize("ps", (1, 2, 3, 5, 7, 9))
+def test_proj_nn_tile_kernel_matches_oracle_and_row_kernel(tx, ps):
+    """The shared-memory tile kernel (window of xyz1 staged per 32x8 query tile) against the oracle and the row-segment
+    kernel: smooth geometry (window staged), wild geometry (projections all over the image: window too large, global
+    fallback inside the same kernel), queries that miss the image, ragged image sizes."""
+    from connecting_the_dots_b200 import _lib, synth
+    xyz, K, poses = synth.make_clouds(2, 61, 83, seed=3)
+    cases = [(synth.transform(xyz[0], poses[1])[None], xyz[1][None], K)]
+    rng = np.random.RandomState(ps)
+    wild0 = (xyz[0] * rng.uniform(0.2, 3.0, xyz[0].shape)).astype(np.float32)[None]      # projections scattered
+    wild0[0, 5, 7] = [np.nan, 1, 1]
+    wild0[0, 6, 7] = [1, 1, 0]
+    wild0[0, 40:, :40] *= np.float32(-1.0)                                                # behind the camera: still valid indices
+    cases.append((wild0, xyz[1][None], K))
+    far = (xyz[0] + np.float32([5.0, 0, 0]))[None]                                        # everything projects outside
+    cases.append((far.astype(np.float32), xyz[1][None], K))
+    for x0, x1, K_ in cases:
+        want = oracle.proj_nn(x0, x1, K_, ps)
+        got = tx.proj_nn(cu(x0), cu(x1), cu(K_), ps).cpu().numpy()
+        assert np.array_equal(got, want)
+        _lib.set_option("proj_nn_tile", 0)
+        try:
+            row = tx.proj_nn(cu(x0), cu(x1), cu(K_), ps).cpu().numpy()
+        finally:
+            _lib.set_option("proj_nn_tile", 1)
+        assert np.array_equal(row, want)
 
 
 def test_nn_golden_and_split(tx, golden):
@@ -1017,6 +1083,42 @@ def test_pattern_similarity_loss_matches_reference_recipe(tx, loss_type):
     assert abs(val.item() - ref.item()) <= 1e-5 * abs(ref.item())
     assert_close(proj.detach().cpu().numpy(), proj_ref.detach().cpu().numpy(), what="pattern_proj")
     assert_close(g_.cpu().numpy(), gref.cpu().numpy(), what="d loss / d disp")
+
+
+def test_pyramid_pattern_similarity_loss(tx):
+    """The photometric part of exp_synph.loss_forward over the four pyramid levels (exp_synph.py:25-27,107-111): every
+    level's value and d value / d disp against the reference recipe (torch grid_sample + the ORACLE's photometric loss),
+    and the whole pyramid (forward and backward) replayed as one CUDA graph giving the same numbers."""
+    from connecting_the_dots_b200 import synth
+    levels = [synth.make_batch(2, 480 >> s, 640 >> s) for s in range(4)]
+    pats = [cu(d["pat_lcn"][:1]) for d in levels]
+    ims, stds = [cu(d["ta"]) for d in levels], [cu(d["std"]) for d in levels]
+    disps = [cu(d["disp"]).clone().requires_grad_(True) for d in levels]
+    vals, proj0 = tx.pyramid_pattern_similarity_loss(disps, pats, ims, stds)
+    grads = torch.autograd.grad(sum(vals), disps)
+    assert len(vals) == 4 and proj0.shape == (2, 1, 480, 640) and not proj0.requires_grad
+    for s in (1, 2, 3):   # the reference recipe on every level the oracle finishes quickly (level 0: test_pattern_similarity_loss...)
+        ref, _ = _reference_pattern_loss(disps[s], pats[s], ims[s], stds[s], "census_sad", 0.5, tx)
+        (gref,) = torch.autograd.grad(ref, disps[s])
+        assert abs(vals[s].item() - ref.item()) <= 1e-5 * abs(ref.item()), s
+        assert_close(grads[s].cpu().numpy(), gref.cpu().numpy(), what="level %d d loss / d disp" % s)
+    # one graph for the 12 kernels of the pyramid
+    static_d = [d.detach().clone().requires_grad_(True) for d in disps]
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        v_, _ = tx.pyramid_pattern_similarity_loss(static_d, pats, ims, stds)   # warm-up outside capture
+        torch.autograd.grad(sum(v_), static_d)
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(g):
+        gv, _ = tx.pyramid_pattern_similarity_loss(static_d, pats, ims, stds)
+        gg = torch.autograd.grad(sum(gv), static_d)
+    g.replay()
+    torch.cuda.synchronize()
+    for s in range(4):
+        assert torch.equal(gv[s], vals[s]) and torch.equal(gg[s], grads[s]), s
 
 
 def test_loss_path_is_cuda_graph_capturable(tx):

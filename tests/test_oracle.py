@@ -192,3 +192,13 @@ def test_disparity_loss_restatement_golden(golden, name):
     if e is not None:
         assert_close(e.grad.numpy(), g[name + "_gedge"], tol=1e-6, what=name + " grad edge")
 
+
+
+def test_lcn_cython_oracle_matches_reference_build(golden):
+    """oracle.lcn_cython (data/lcn/lcn.pyx:16-58 restated in C) against outputs of the reference's own Cython module
+    (tests/golden/make_golden_lcn_cython.py): bit for bit, including the zero border and a flat window."""
+    g = golden("lcn_cython")
+    for n in "abcde":
+        ks, eps = g[n + "_args"]
+        l, s = oracle.lcn_cython(g[n + "_x"], int(ks), float(eps))
+        assert np.array_equal(l, g[n + "_lcn"]) and np.array_equal(s, g[n + "_std"]), n
