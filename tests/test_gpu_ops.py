@@ -674,14 +674,14 @@ def test_proj_nn_tile_kernel_matches_oracle_and_row_kernel(tx, ps):
     cases.append((far.astype(np.float32), xyz[1][None], K))
     for x0, x1, K_ in cases:
         want = oracle.proj_nn(x0, x1, K_, ps)
-        got = tx.proj_nn(cu(x0), cu(x1), cu(K_), ps).cpu().numpy()
-        assert np.array_equal(got, want)
-        _lib.set_option("proj_nn_tile", 0)
-        try:
-            row = tx.proj_nn(cu(x0), cu(x1), cu(K_), ps).cpu().numpy()
-        finally:
-            _lib.set_option("proj_nn_tile", 1)
+        row = tx.proj_nn(cu(x0), cu(x1), cu(K_), ps).cpu().numpy()     # default: row-segment kernel
         assert np.array_equal(row, want)
+        _lib.set_option("proj_nn_tile", 1)
+        try:
+            got = tx.proj_nn(cu(x0), cu(x1), cu(K_), ps).cpu().numpy()
+        finally:
+            _lib.set_option("proj_nn_tile", 0)
+        assert np.array_equal(got, want)
 
 
 def test_nn_golden_and_split(tx, golden):

@@ -6,7 +6,7 @@ import connecting_the_dots_b200 as ctd
 from connecting_the_dots_b200 import synth, _lib
 tx = ctd.torchext
 cu = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-H, W, D, BS = 480, 640, 128, 9
+H, W, D, BS = 480, 640, 128, (int(sys.argv[1]) if len(sys.argv) > 1 else 9)
 R = BS // 2
 for n in (0, 3):
     d = synth.make_pair(n, H, W)
@@ -17,7 +17,7 @@ for n in (0, 3):
     full = tx.xcorrvol(cu(d["ta"][None]), cu(d["pat_lcn"][None]), D, BS).cpu().numpy()
     ap = np.pad(a, R, mode="edge")
     bp = np.pad(np.pad(b, ((0, 0), (D - 1, 0)), mode="edge"), R, mode="edge")   # columns u = -(D-1) ..
-    def box(x):  # 9x9 sums, valid
+    def box(x):  # BS x BS sums, valid
         c = np.cumsum(np.cumsum(np.pad(x, ((1, 0), (1, 0))), 0), 1)
         return c[BS:, BS:] - c[:-BS, BS:] - c[BS:, :-BS] + c[:-BS, :-BS]
     N = BS * BS
