@@ -273,7 +273,9 @@ def run_b200_arm(args, rank, world, local_rank):
     base = synth.make_batch(min(B, 8), H, W)
     if B > 8:  # synthetic frames repeat beyond 8 (generation is the slow part, not the content)
         base = {k: np.concatenate([v] * ((B + 7) // 8))[:B] for k, v in base.items()}
-    sums_all = torch.zeros(NSETS, 2, 2, device=dev)   # every set's four loss scalars, contiguous: ONE all-reduce covers NSETS steps
+    # every set's four loss scalars, contiguous, in TWO slots: ONE all-reduce covers the NSETS steps of a round, and the
+    # rounds alternate between the slots so that round r+1 never waits for the reduction of round r
+    sums_all = torch.zeros(2, NSETS, 2, 2, device=dev)
     sets, host_sets = [], []
     for s in range(NSETS):
         arrs = {k: np.ascontiguousarray(np.roll(base[k], 3 * s + rank, axis=2)) for k in ("im", "es", "ta", "go")}
@@ -285,7 +287,8 @@ def run_b200_arm(args, rank, world, local_rank):
         d = {k: host[k].to(dev) for k in ("im", "es", "ta", "go")}
         for k in ("lcn", "std", "out_sad", "gi_sad", "out_cs", "gi_cs"):
             d[k] = torch.empty(B, 1, H, W, device=dev)
-        d["sums"] = sums_all[s]
+        d["sums"] = sums_all[0, s]
+        d["sums1"] = sums_all[1, s]
         sets.append(d)
     ws = torch.zeros(int(L.ctd_masked_sums_workspace_bytes()), dtype=torch.uint8, device=dev)
     footprint_mb = NSETS * 10 * npx * 4 / 1e6
@@ -294,8 +297,10 @@ def run_b200_arm(args, rank, world, local_rank):
     OPS = ("lcn_fwd", "sad_fwd_bwd", "census_sad_fwd_bwd")  # the fused calls include the masked sums
     OPS_SEP = ("lcn_fwd", "sad_fwd", "sad_bwd", "census_sad_fwd", "census_sad_bwd", "masked_sums")
 
-    def launch_chain(d, st_, mark, fused=True):
+    def launch_chain(d, st_, mark, fused=True, slot=0):
         p = {n: t.data_ptr() for n, t in d.items()}
+        if slot:
+            p["sums"] = p["sums1"]
         i = 0
         mark(i)
         _lib.call("ctd_lcn_f32", p["im"], p["lcn"], p["std"], B, H, W, LCN_R, LCN_EPS, st_)
@@ -332,8 +337,10 @@ def run_b200_arm(args, rank, world, local_rank):
     # runs beside the issue-bound census kernel instead of in front of it.
     side = torch.cuda.Stream(dev)
 
-    def launch_forked(d, cs):
+    def launch_forked(d, cs, slot=0):
         p = {n: t.data_ptr() for n, t in d.items()}
+        if slot:
+            p["sums"] = p["sums1"]
         _lib.call("ctd_lcn_f32", p["im"], p["lcn"], p["std"], B, H, W, LCN_R, LCN_EPS, cs.cuda_stream)
         side.wait_stream(cs)
         first, second = (side, cs) if args.fork == 1 else (cs, side)
@@ -362,19 +369,25 @@ def run_b200_arm(args, rank, world, local_rank):
                     launch_chain(sets[si], cs.cuda_stream, lambda i, si=si, cs=cs: set_events[si][i].record(cs))
                 graphs.append(g)
                 kernels_per_graph = _lib.launch_count() - c0  # kernel nodes captured (counted by the library)
-                g = torch.cuda.CUDAGraph()  # the same step without the event-record nodes, the two losses as branches
-                with torch.cuda.graph(g):
-                    cs = torch.cuda.current_stream(dev)
-                    if args.fork:
-                        launch_forked(sets[si], cs)
-                    else:
-                        launch_chain(sets[si], cs.cuda_stream, lambda i: None)
-                plain_graphs.append(g)
-                g = torch.cuda.CUDAGraph()  # the step as ONE chain without event nodes (the un-overlapped figure)
-                with torch.cuda.graph(g):
-                    cs = torch.cuda.current_stream(dev)
-                    launch_chain(sets[si], cs.cuda_stream, lambda i: None)
-                chain_graphs.append(g)
+                pair = []
+                for slot in (0, 1):  # the same step without the event-record nodes, the two losses as branches
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        cs = torch.cuda.current_stream(dev)
+                        if args.fork:
+                            launch_forked(sets[si], cs, slot)
+                        else:
+                            launch_chain(sets[si], cs.cuda_stream, lambda i: None, slot=slot)
+                    pair.append(g)
+                plain_graphs.append(pair)
+                pair = []
+                for slot in (0, 1):  # the step as ONE chain without event nodes (the un-overlapped figure)
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        cs = torch.cuda.current_stream(dev)
+                        launch_chain(sets[si], cs.cuda_stream, lambda i: None, slot=slot)
+                    pair.append(g)
+                chain_graphs.append(pair)
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
                     cs = torch.cuda.current_stream(dev)
@@ -390,13 +403,13 @@ def run_b200_arm(args, rank, world, local_rank):
     # (a per-step 4-float all-reduce cost ~5 % of an 0.16 ms step at 8 GPUs: pure latency).  The kernels that overwrite a
     # set's scalars wait for the reduction that read them.
     comm_stream = torch.cuda.Stream(dev) if world > 1 else None
-    state = {"comm_done": None, "reduces": 0}
+    state = {"comm_done": [None, None], "reduces": 0}
 
-    def reduce_scalars(after):
+    def reduce_scalars(after, slot):
         comm_stream.wait_stream(after)
         with torch.cuda.stream(comm_stream):
-            dist.all_reduce(sums_all)
-            state["comm_done"] = comm_stream.record_event()
+            dist.all_reduce(sums_all[slot])
+            state["comm_done"][slot] = comm_stream.record_event()
         state["reduces"] += 1
 
     def sync_all():
@@ -416,26 +429,30 @@ def run_b200_arm(args, rank, world, local_rank):
         e0.record(stream)
         for other in lanes[1:]:
             other.wait_stream(stream)  # no lane starts before the timed region does
+        state["reduces"] = 0
         for k in range(n_steps):
             si = k % NSETS
             evented = k >= n_steps - evented_tail
+            slot = 0 if (evented or graph_list in (graphs, sep_graphs)) else (k // NSETS) % 2
             lane = stream if evented else lanes[k % len(lanes)]
             if evented:
                 for other in lanes[1:]:
                     stream.wait_stream(other)   # the evented replays run alone: their per-op times are undisturbed
-            if world > 1 and si == 0 and state["comm_done"] is not None:
+            if world > 1 and state["comm_done"][slot] is not None and (si == 0 or evented):
                 for ln in lanes:
-                    ln.wait_event(state["comm_done"])  # the previous round's scalars have been reduced
+                    ln.wait_event(state["comm_done"][slot])  # this slot's previous scalars (two rounds ago) have been reduced
             if use_graph:
                 with torch.cuda.stream(lane):
-                    (graphs if evented else graph_list)[si].replay()
+                    g = (graphs if evented else graph_list)[si]
+                    (g[slot] if isinstance(g, list) else g).replay()
             else:
                 launch_chain(sets[si], st, lambda i: set_events[si][i].record(stream))
-            if world > 1 and (si == NSETS - 1 or k == n_steps - 1):
+            if world > 1 and (si == NSETS - 1 or k == n_steps - 1 or evented):
+                # the reduction waits for the round's steps (on all lanes); the lanes do not wait for it
                 for other in lanes:
                     if other is not lane:
-                        lane.wait_stream(other)
-                reduce_scalars(lane)
+                        comm_stream.wait_stream(other)
+                reduce_scalars(lane, slot)
         for other in lanes[1:]:
             stream.wait_stream(other)
         if world > 1:
@@ -566,7 +583,7 @@ def run_b200_arm(args, rank, world, local_rank):
             "config": cfg,
             "timing": {"footprint_mb": footprint_mb,
                        "launch": ("one CUDA graph replay per step" + (", consecutive steps on %d alternating streams" % min(max(args.pipeline, 1), NSETS) if args.pipeline > 1 else "") + (", the sad and the census loss as parallel branches behind LCN (both need its std, not each other)" if args.fork else "") + "; the last replay of each buffer set in the timed region is the plain chain with the event-record nodes the per-op durations are read from") if use_graph else "stream launches",
-                       "parallelism": "batch-sharded x%d; one packed NCCL all-reduce of %d floats per %d steps on a side stream (%d reductions in the timed region)" % (world, NSETS * 4, NSETS, state["reduces"]) if world > 1 else "one GPU"},
+                       "parallelism": "batch-sharded x%d; one packed NCCL all-reduce of %d floats per %d steps on a side stream, two alternating scalar slots so no step waits for the previous round's reduction" % (world, NSETS * 4, NSETS) if world > 1 else "one GPU"},
             "sequential": {"ms_per_step": seq_ms, "value": npx_global / (seq_ms * 1e-3) / 1e6, "steps": seq_steps,
                            "note": "the same steps on ONE stream as ONE chain (no overlap between steps or between the two losses): what a training step that needs each loss before the next op would see"},
             "clocks": clocks, "gpu_launches": int(launches),
@@ -740,18 +757,18 @@ def main():
     ap.add_argument("--no-strong", action="store_true", help="skip the `strong` block (BASELINE configs[4]: global batch 64 over the ranks)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra op timings (XCorrVol, ProjNN, ...) and the reference CUDA extension leg")
     args = ap.parse_args()
-    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world)
-        return
-    if world == 1 and args.gpus > 1:
-        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU
+    if args.impl != "reference" and world == 1 and args.gpus > 1:
+        # plain `python bench.py --gpus N`: re-launch under torchrun, one rank per GPU (before stdout is re-pointed)
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
                "--master-addr", "127.0.0.1", "--master-port", str(29400 + os.getpid() % 500), os.path.abspath(__file__)] + sys.argv[1:]
         sys.exit(subprocess.call(cmd))
+    claim_stdout()
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
     run_b200_arm(args, rank, world, local_rank)
 
 
