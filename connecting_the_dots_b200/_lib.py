@@ -30,6 +30,7 @@ SIGNATURES = {
     "ctd_crosscheck": [_ptr, _ptr, _ptr, _i64, _i64, _ptr],
     "ctd_lcn_f32": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _f32, _ptr],
     "ctd_lcn_f64": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _f64, _ptr],
+    "ctd_pattern_similarity_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _i64, _i64, _i64, _int, _f32, _ptr],
     "ctd_lcn_bwd_f32": [_ptr, _ptr, _ptr, _ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _f32, _ptr],
     "ctd_lcn_cython_f32": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _f32, _ptr],
     "ctd_masked_sums_f32": [_ptr, _ptr, _i64, _ptr, _ptr, _ptr],

@@ -388,6 +388,87 @@ static_assert(CT_H % 16 == 0, "census tile height");
 constexpr int CE_W = CT_W + 2 * R9;  // 72
 constexpr int CE_H = CT_H + 2 * R9;  // 40
 
+// ---- the disparity warp in front of the loss (model/networks.py:362-371), same arithmetic as warp.cu ----------------
+struct WarpArgs {
+  const float* pattern;  // [Bp,1,Hp,Wp]
+  float* proj;           // pattern_proj out [B,1,H,W]
+  int Bp, Hp, Wp;
+  float inv_w, inv_h;    // 1 / (W - 1), 1 / (H - 1)
+};
+
+struct WarpTaps {
+  float nw, ne, sw, se, wy0, wy1, mult_x;  // the four pattern values (0 outside), the row weights, d ix / d gx
+  float ix, iy;
+  int x0, y0;
+};
+
+__device__ __forceinline__ WarpTaps warp_taps(const float* __restrict__ p, float disp, int u, int v, float inv_w, float inv_h, int Hp, int Wp) {
+  WarpTaps t;
+  const float gx = 2.f * __fsub_rn(__fmul_rn(__fsub_rn((float)u, disp), inv_w), 0.5f);
+  const float gy = 2.f * __fsub_rn(__fmul_rn((float)v, inv_h), 0.5f);
+  float ix = fmaf(gx + 1.f, (float)Wp, -1.f) / 2.f, iy = fmaf(gy + 1.f, (float)Hp, -1.f) / 2.f;
+  t.mult_x = (float)Wp / 2.f;
+  if (ix <= 0.f) {
+    ix = 0.f;
+    t.mult_x = 0.f;
+  } else if (ix >= (float)(Wp - 1)) {
+    ix = (float)(Wp - 1);
+    t.mult_x = 0.f;
+  }
+  iy = fminf((float)(Hp - 1), fmaxf(iy, 0.f));
+  t.ix = ix;
+  t.iy = iy;
+  t.x0 = (int)floorf(ix);
+  t.y0 = (int)floorf(iy);
+  const bool xin = t.x0 + 1 < Wp, yin = t.y0 + 1 < Hp;
+  const float* r0 = p + t.y0 * Wp + t.x0;
+  t.nw = __ldg(r0);
+  t.ne = xin ? __ldg(r0 + 1) : 0.f;
+  t.sw = yin ? __ldg(r0 + Wp) : 0.f;
+  t.se = xin && yin ? __ldg(r0 + Wp + 1) : 0.f;
+  t.wy1 = (float)(t.y0 + 1) - iy;
+  t.wy0 = iy - (float)t.y0;
+  return t;
+}
+
+// grid_sample value: ATen's nw, ne, sw, se accumulation (taps outside the pattern are skipped there; adding 0 * w is the same)
+__device__ __forceinline__ float warp_value(const WarpTaps& t) {
+  const float x1 = (float)(t.x0 + 1), fx0 = (float)t.x0;
+  float acc = 0.f;
+  acc = fmaf(t.nw, (x1 - t.ix) * t.wy1, acc);
+  acc = fmaf(t.ne, (t.ix - fx0) * t.wy1, acc);
+  acc = fmaf(t.sw, (x1 - t.ix) * t.wy0, acc);
+  acc = fmaf(t.se, (t.ix - fx0) * t.wy0, acc);
+  return acc;
+}
+
+// d pattern_proj / d disp times g (warp_bwd_kernel's sequence)
+__device__ __forceinline__ float warp_grad_disp(const WarpTaps& t, float g, float inv_w) {
+  float gix = 0.f;
+  gix -= t.nw * t.wy1 * g;
+  gix += t.ne * t.wy1 * g;
+  gix -= t.sw * t.wy0 * g;
+  gix += t.se * t.wy0 * g;
+  return -__fmul_rn(2.f * (t.mult_x * gix), inv_w);
+}
+
+// the estimate's halo tile computed on the fly: es = pattern warped by the disparity, replicate-clamped like load_halo_tile<true>;
+// the tile's own pixels are also written out as pattern_proj (the reference returns it, networks.py:378)
+template <int ROWS, int OWN_H>
+__device__ __forceinline__ void load_warp_tile(float (*S)[72], const WarpArgs& wa, const float* __restrict__ pat,
+                                               const float* __restrict__ disp, float* __restrict__ proj, int x0, int y0, int H, int W,
+                                               int tid) {
+  for (int i = tid; i < ROWS * 72; i += 256) {
+    const int r = i / 72, c = i % 72;
+    const int uy = y0 - 4 + r, ux = x0 - 4 + c;
+    const int gy = clampi(uy, 0, H - 1), gx = clampi(ux, 0, W - 1);
+    const WarpTaps t = warp_taps(pat, __ldg(disp + (int64_t)gy * W + gx), gx, gy, wa.inv_w, wa.inv_h, wa.Hp, wa.Wp);
+    const float v = warp_value(t);
+    S[r][c] = v;
+    if (r >= 4 && r < 4 + OWN_H && c >= 4 && c < 68 && uy < H && ux < W) proj[(int64_t)uy * W + ux] = v;
+  }
+}
+
 // load a (CE_H x CE_W) halo tile; REPL: replicate-clamped (es, ta), else zero padded (grad_out)
 template <bool REPL, int ROWS = CE_H>
 __device__ __forceinline__ void load_halo_tile(float (*S)[CE_W], const float* __restrict__ src, int x0,
@@ -556,11 +637,12 @@ __device__ __forceinline__ void unpack_row(float* d, const float* srow) {  // NP
   }
 }
 
-template <int TYPE, bool BORDER, bool FUSE, int NPX>
+template <int TYPE, bool BORDER, bool FUSE, int NPX, bool WARP = false>
 __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[CE_W], float (*Gs)[CE_W],
                                                 float* __restrict__ gi, int x0, int y0, int H, int W,
                                                 float eps, int vec, int tx, int ty, unsigned short* s_fix, unsigned* s_nfix,
-                                                float (*facc)[NPX]) {
+                                                float (*facc)[NPX], const WarpArgs* wa = nullptr, const float* __restrict__ pat = nullptr,
+                                                const float* __restrict__ disp = nullptr) {
   constexpr int RPP = 256 / (CT_W / NPX);  // tile rows per pass
 #pragma unroll 1
   for (int half = 0; half < CB_H / RPP; ++half) {
@@ -655,6 +737,14 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
       for (int k = 0; k < NPX; ++k)
         if (near0[k] < SIGN_GUARD && gx + k < W) s_fix[atomicAdd(s_nfix, 1u)] = (unsigned short)(yl * CT_W + NPX * tx + k);
     }
+    if (WARP) {  // chain through the warp: the gradient w.r.t. the disparity leaves the kernel, not the one w.r.t. es
+#pragma unroll
+      for (int k = 0; k < NPX; ++k)
+        if (gx + k < W) {
+          const WarpTaps t = warp_taps(pat, __ldg(disp + (int64_t)gy * W + gx + k), gx + k, gy, wa->inv_w, wa->inv_h, wa->Hp, wa->Wp);
+          r[k] = warp_grad_disp(t, r[k], wa->inv_w);
+        }
+    }
     float* dst = gi + (int64_t)gy * W + gx;
     if (vec) {
       if (gx < W) {
@@ -669,12 +759,14 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
   }
 }
 
-template <int TYPE, bool FUSE, int NPX>
+// WARP: `es` is the DISPARITY; the estimate's tile is the pattern warped by it on the fly (model/networks.py:362-371), the
+// tile's own pixels go out as pattern_proj, and `gi` receives d loss / d disp (C = 1).
+template <int TYPE, bool FUSE, int NPX, bool WARP = false>
 __global__ void __launch_bounds__(256, NPX == 4 ? 2 : CTD_CB_MINB)
 photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
                   float* __restrict__ gi, float* __restrict__ out, int C, int H, int W, float eps, int vec,
                   const float* __restrict__ mask, double* __restrict__ partials, unsigned* __restrict__ ticket,
-                  float* __restrict__ sums2) {
+                  float* __restrict__ sums2, const WarpArgs wa = WarpArgs()) {
   __shared__ __align__(16) float Es[CBE_H][CE_W];
   __shared__ __align__(16) float Ts[CBE_H][CE_W];
   __shared__ __align__(16) float Gs[CBE_H][CE_W];
@@ -693,19 +785,28 @@ photo_bwd_census9(const float* __restrict__ es, const float* __restrict__ ta, co
   for (int c = 0; c < C; ++c) {
     if (c) __syncthreads();
     if (tid == 0) s_nfix = 0;
-    load_halo_tile<true, CBE_H>(Es, es + (n * C + c) * plane, x0, y0, H, W, vec, tid);
+    const float* pat = WARP ? wa.pattern + (wa.Bp == 1 ? 0 : n) * (int64_t)wa.Hp * wa.Wp : nullptr;
+    const float* dpl = es + (n * C + c) * plane;  // WARP: the disparity plane
+    if (WARP) load_warp_tile<CBE_H, CB_H>(Es, wa, pat, dpl, wa.proj + n * plane, x0, y0, H, W, tid);
+    else load_halo_tile<true, CBE_H>(Es, es + (n * C + c) * plane, x0, y0, H, W, vec, tid);
     load_halo_tile<true, CBE_H>(Ts, ta + (n * C + c) * plane, x0, y0, H, W, vec, tid);
     __syncthreads();
     float* gic = gi + (n * C + c) * plane;
-    if (border) census_bwd_tile<TYPE, true, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, s_fix, &s_nfix, facc);
-    else census_bwd_tile<TYPE, false, FUSE, NPX>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, s_fix, &s_nfix, facc);
+    if (border) census_bwd_tile<TYPE, true, FUSE, NPX, WARP>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, s_fix, &s_nfix, facc, &wa, pat, dpl);
+    else census_bwd_tile<TYPE, false, FUSE, NPX, WARP>(Es, Ts, Gs, gic, x0, y0, H, W, eps, vec, tx, ty, s_fix, &s_nfix, facc, &wa, pat, dpl);
     if (TYPE == 3) {  // exact pass over the near-tie pixels of this tile, straight from the staged tiles
       __syncthreads();
       const unsigned nfix = s_nfix;
       for (unsigned i = tid >> 5; i < nfix; i += 8) {
         const int li = s_fix[i], yl = li / CT_W, xl = li % CT_W;
-        const float v = census_sad_bwd_exact_smem(Es, Ts, Gs, xl, yl, x0 + xl, y0 + yl, H, W, eps, tid & 31);
-        if ((tid & 31) == 0) gic[(int64_t)(y0 + yl) * W + x0 + xl] = v;
+        float v = census_sad_bwd_exact_smem(Es, Ts, Gs, xl, yl, x0 + xl, y0 + yl, H, W, eps, tid & 31);
+        if ((tid & 31) == 0) {
+          if (WARP) {
+            const int64_t o = (int64_t)(y0 + yl) * W + x0 + xl;
+            v = warp_grad_disp(warp_taps(pat, __ldg(dpl + o), x0 + xl, y0 + yl, wa.inv_w, wa.inv_h, wa.Hp, wa.Wp), v, wa.inv_w);
+          }
+          gic[(int64_t)(y0 + yl) * W + x0 + xl] = v;
+        }
       }
     }
   }
@@ -816,6 +917,22 @@ static bool census_bwd_launch(const float* e, const float* t, const float* g, fl
     if (out) photo_bwd_census9<3, true, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, mask, partials, ticket, sums2);
     else photo_bwd_census9<3, false, CB_NPX><<<grid, 256, 0, st>>>(e, t, g, o, out, iC, iH, iW, eps, vec, nullptr, nullptr, nullptr, nullptr);
   }
+  ms_release(&ms, st);
+  return true;
+}
+
+// the whole RectifiedPatternSimilarityLoss step in ONE kernel: warp + census loss + gradient w.r.t. the disparity + masked sums
+static bool census_warp_launch(const float* disp, const float* ta, const float* go, float* gd, float* out, int nb, int64_t H, int64_t W,
+                               int type, float eps, int vec, cudaStream_t st, const float* mask, float* sums2, const WarpArgs& wa) {
+  dim3 grid((unsigned)cdiv(W, CT_W), (unsigned)cdiv(H, CB_H), nb);
+  MsSlot ms = {nullptr, nullptr, nullptr};
+  const size_t nblk = (size_t)grid.x * grid.y * grid.z;
+  if (mask && !ms_acquire(nblk, st, &ms)) return false;
+  const int iH = (int)H, iW = (int)W;
+  if (type == 2)
+    photo_bwd_census9<2, true, CB_NPX, true><<<grid, 256, 0, st>>>(disp, ta, go, gd, out, 1, iH, iW, eps, vec, mask, ms.partials, ms.ticket, sums2, wa);
+  else
+    photo_bwd_census9<3, true, CB_NPX, true><<<grid, 256, 0, st>>>(disp, ta, go, gd, out, 1, iH, iW, eps, vec, mask, ms.partials, ms.ticket, sums2, wa);
   ms_release(&ms, st);
   return true;
 }
@@ -955,4 +1072,38 @@ CTD_API int ctd_photometric_bwd_f64(const double* es, const double* ta, const do
                                        int64_t B, int64_t C, int64_t H, int64_t W, int bs, int type, float eps,
                                        ctd_stream_t stream) {
   return bwd_impl<double>(es, ta, go, gi, B, C, H, W, bs, type, eps, as_stream(stream));
+}
+
+// RectifiedPatternSimilarityLoss.tforward (model/networks.py:358-378) and its backward to the disparity as ONE kernel for the
+// census modes, block 9: pattern_proj = grid_sample(pattern, grid(disp)) is formed inside the loss kernel's tile loader (the
+// pattern is L2-resident), the loss map, the masked-mean terms and d loss / d disp for grad_out (w.r.t. the loss map; the
+// caller's is mask / sum(mask) up to a scalar) come out of the same pass.  pattern [Bp,1,Hp,Wp] (Bp = 1 or B), disp / ta /
+// grad_out / mask / pattern_proj / out / grad_disp [B,1,H,W]; sums2 = (sum(mask * out), sum(mask)).
+CTD_API int ctd_pattern_similarity_f32(const float* pattern, const float* disp, const float* ta, const float* grad_out, const float* mask,
+                                       float* pattern_proj, float* out, float* grad_disp, float* sums2, int64_t B, int64_t Bp,
+                                       int64_t Hp, int64_t Wp, int64_t H, int64_t W, int type, float eps, ctd_stream_t stream) {
+  cudaStream_t st = as_stream(stream);
+  CTD_REQUIRE(B >= 0 && H >= 0 && W >= 0, "pattern_similarity: negative size");
+  CTD_REQUIRE(type == 2 || type == 3, "pattern_similarity: the fused kernel covers census_mse (2) and census_sad (3), got %d", type);
+  CTD_REQUIRE(Bp >= 1 && Hp >= 1 && Wp >= 1 && (Bp == 1 || Bp == B), "pattern_similarity: pattern batch %lld must be 1 or %lld", (long long)Bp, (long long)B);
+  CTD_REQUIRE(sums2, "pattern_similarity: null sums2");
+  if (B * H * W == 0) {
+    CTD_CUDA(cudaMemsetAsync(sums2, 0, 2 * sizeof(float), st));
+    return CTD_OK;
+  }
+  CTD_REQUIRE(pattern && disp && ta && grad_out && mask && pattern_proj && out && grad_disp, "pattern_similarity: null pointer");
+  CTD_REQUIRE(H >= 9 && W >= 9 && H * W < ((int64_t)1 << 31) && Hp * Wp < ((int64_t)1 << 31) && B <= 32768, "pattern_similarity: size out of range");
+  WarpArgs wa;
+  wa.pattern = pattern;
+  wa.proj = pattern_proj;
+  wa.Bp = (int)Bp;
+  wa.Hp = (int)Hp;
+  wa.Wp = (int)Wp;
+  wa.inv_w = W > 1 ? 1.f / (float)(W - 1) : INFINITY;
+  wa.inv_h = H > 1 ? 1.f / (float)(H - 1) : INFINITY;
+  const int vec = vec_ok(W, disp, ta, grad_out, grad_disp) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
+  if (!census_warp_launch(disp, ta, grad_out, grad_disp, out, (int)B, H, W, type, eps, vec, st, mask, sums2, wa))
+    return fail(CTD_ERR_NOMEM, "pattern_similarity: no reduction workspace");
+  count_launch();
+  return check_launch("pattern_similarity(fused)");
 }

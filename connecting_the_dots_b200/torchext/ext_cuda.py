@@ -219,6 +219,24 @@ def warp_pattern_backward(pattern, disp, grad_out):
     return gd
 
 
+def pattern_similarity(pattern, disp, ta, grad_out, mask, type, eps):
+    """model/networks.py:358-378 as ONE kernel (ctd_pattern_similarity_f32; census modes, block 9): returns (pattern_proj,
+    loss map, d loss / d disp for grad_out, sums float32 [2] = (sum(mask * loss), sum(mask)))."""
+    _warp_args(pattern, disp)
+    for t, n in ((ta, "ta"), (grad_out, "grad_out"), (mask, "mask")):
+        _check_input_cuda(t, n)
+        _check(t.dtype == torch.float32 and t.numel() == disp.numel(), n + " has to be float32 and match disp")
+        _same(disp, t, "disp", n)
+    B, _, H, W = disp.shape
+    Bp, _, Hp, Wp = pattern.shape
+    proj, out, gd = torch.empty_like(disp), torch.empty_like(disp), torch.empty_like(disp)
+    sums = torch.empty(2, dtype=torch.float32, device=disp.device)
+    with torch.cuda.device(disp.device):
+        _lib.call("ctd_pattern_similarity_f32", pattern.data_ptr(), disp.data_ptr(), ta.data_ptr(), grad_out.data_ptr(), mask.data_ptr(),
+                  proj.data_ptr(), out.data_ptr(), gd.data_ptr(), sums.data_ptr(), B, Bp, Hp, Wp, H, W, int(type), float(eps), _stream(disp))
+    return proj, out, gd, sums
+
+
 def depth_similarity(depth0, depth1, ray, K, R0, t0, R1, t1, clamp=-1.0):
     """model/networks.py:500-503 (ProjectionDepthSimilarityLoss.tforward): both directions of the projected depth
     difference, loss sums and gradients in two kernels.  depth0/1 [B,1,H,W]; ray [H*W,3] or [1,H*W,3]; K [3,3] or

@@ -184,11 +184,39 @@ def warp_pattern(pattern, disp):
     return WarpPatternFunction.apply(pattern, disp)
 
 
-def pattern_similarity_loss(disp, pattern, im, std=None, loss_type="census_sad", loss_eps=0.5, block_size=9):
-    """RectifiedPatternSimilarityLoss.tforward (model/networks.py:358-378) as three kernels: warp, fused loss
-    forward+backward+masked mean, and (in autograd's backward) the warp's gradient.  Returns (val, pattern_proj)."""
-    pattern_proj = warp_pattern(pattern, disp)
+class PatternSimilarityFunction(torch.autograd.Function):
+    """RectifiedPatternSimilarityLoss.tforward (model/networks.py:358-378) with its backward to the disparity as ONE
+    kernel (census modes, block 9): the disparity warp of the pattern happens inside the loss kernel's tile loader, so
+    pattern_proj and d loss / d es never make a round trip through HBM as separate kernels' outputs and inputs.  The upstream
+    gradient of the value is a scalar; autograd's backward is a scalar multiply."""
+
+    @staticmethod
+    def forward(ctx, disp, pattern, im, mask, type, eps):
+        d = disp.detach().contiguous()
+        m = mask.detach().contiguous()
+        proj, out, gd, sums = ext_cuda.pattern_similarity(pattern.detach().contiguous(), d, im.detach().contiguous(), m, m, type, eps)
+        ctx.save_for_backward(gd, sums)
+        ctx.mark_non_differentiable(proj, out)
+        return sums[0] / sums[1], proj, out
+
+    @staticmethod
+    def backward(ctx, g_val, g_proj, g_map):
+        gd, sums = ctx.saved_tensors
+        return gd * (g_val / sums[1]), None, None, None, None, None
+
+
+def pattern_similarity_loss(disp, pattern, im, std=None, loss_type="census_sad", loss_eps=0.5, block_size=9, fused=True):
+    """RectifiedPatternSimilarityLoss.tforward (model/networks.py:358-378).  Returns (val, pattern_proj).
+    census modes with block 9 on CUDA float32 (the reference's configuration, networks.py:344,376): ONE kernel forward +
+    backward (PatternSimilarityFunction); otherwise, or with fused=False, three kernels (warp, fused loss forward + backward
+    + masked mean, and in autograd's backward the warp's gradient)."""
     mask = torch.ones_like(im) if std is None else std
+    ty = _loss_type_id(loss_type)
+    if (fused and ty >= 2 and block_size == 9 and disp.is_cuda and disp.dtype == torch.float32 and disp.dim() == 4 and disp.size(1) == 1
+            and disp.size(2) >= 9 and disp.size(3) >= 9):
+        val, pattern_proj, _ = PatternSimilarityFunction.apply(disp, pattern, im, mask, ty, loss_eps)
+        return val, pattern_proj
+    pattern_proj = warp_pattern(pattern, disp)
     val, _ = weighted_photometric_loss(pattern_proj, im.contiguous(), mask, block_size, loss_type, loss_eps)
     return val, pattern_proj
 

@@ -143,6 +143,15 @@ int ctd_lcn_f32(const float* x, float* lcn, float* std, int64_t N, int64_t H, in
 int ctd_lcn_f64(const double* x, double* lcn, double* std, int64_t N, int64_t H, int64_t W,
                 int radius, double epsilon, ctd_stream_t stream);
 
+/* ---- RectifiedPatternSimilarityLoss.tforward + backward to the disparity, model/networks.py:358-378, as ONE kernel
+ * (census modes, block 9): grid_sample(pattern, grid(disp), border) formed inside the loss kernel's tile loader, loss map,
+ * masked-mean terms sums2 = (sum(mask * out), sum(mask)) and d loss / d disp for `grad_out` (w.r.t. the loss map).
+ * pattern [Bp,1,Hp,Wp] with Bp = 1 or B; everything else [B,1,H,W]. */
+int ctd_pattern_similarity_f32(const float* pattern, const float* disp, const float* ta, const float* grad_out,
+                               const float* mask, float* pattern_proj, float* out, float* grad_disp, float* sums2,
+                               int64_t B, int64_t Bp, int64_t Hp, int64_t Wp, int64_t H, int64_t W, int type, float eps,
+                               ctd_stream_t stream);
+
 /* ---- LCN backward: what autograd produces for networks.LCN (model/networks.py:523-533) w.r.t. its input, given the
  * forward's input x, its outputs (lcn, std) and upstream gradients for both outputs (either may be NULL = zero). */
 int ctd_lcn_bwd_f32(const float* x, const float* lcn, const float* std, const float* grad_lcn, const float* grad_std,

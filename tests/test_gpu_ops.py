@@ -1078,11 +1078,35 @@ def test_pattern_similarity_loss_matches_reference_recipe(tx, loss_type):
     disp = cu(d["disp"] if d["disp"].ndim == 4 else d["disp"][:, None]).clone().requires_grad_(True)
     ref, proj_ref = _reference_pattern_loss(disp, pattern, im, std, loss_type, 0.5, tx)
     (gref,) = torch.autograd.grad(ref, disp)
-    val, proj = tx.pattern_similarity_loss(disp, pattern, im, std, loss_type, 0.5)
-    (g_,) = torch.autograd.grad(val, disp)
-    assert abs(val.item() - ref.item()) <= 1e-5 * abs(ref.item())
-    assert_close(proj.detach().cpu().numpy(), proj_ref.detach().cpu().numpy(), what="pattern_proj")
-    assert_close(g_.cpu().numpy(), gref.cpu().numpy(), what="d loss / d disp")
+    for fused in (True, False):   # one kernel (census modes) and the three-kernel composition
+        val, proj = tx.pattern_similarity_loss(disp, pattern, im, std, loss_type, 0.5, fused=fused)
+        (g_,) = torch.autograd.grad(val, disp)
+        assert abs(val.item() - ref.item()) <= 1e-5 * abs(ref.item())
+        assert_close(proj.detach().cpu().numpy(), proj_ref.detach().cpu().numpy(), what="pattern_proj")
+        assert_close(g_.cpu().numpy(), gref.cpu().numpy(), what="d loss / d disp")
+
+
+@pytest.mark.parametrize("shape", [(2, 96, 160, 96, 160), (1, 60, 83, 120, 160), (2, 33, 50, 33, 50), (1, 480, 640, 480, 640)])
+@pytest.mark.parametrize("loss_type", ("census_sad", "census_mse"))
+def test_pattern_similarity_single_kernel_matches_three_kernels(tx, shape, loss_type):
+    """ctd_pattern_similarity_f32 (warp inside the census kernel's tile loader, gradient chained to the disparity in its
+    epilogue) against the three-kernel composition: same pattern_proj bit for bit, same value and gradient; disparities
+    that send samples off both sides of the pattern, ragged sizes, a pattern of another size than the image."""
+    B, H, W, Hp, Wp = shape
+    g = torch.Generator(device="cpu").manual_seed(H + W)
+    pattern = torch.randn(1, 1, Hp, Wp, generator=g).to(DEV)
+    disp = (torch.rand(B, 1, H, W, generator=g) * (W * 0.3) - 6).to(DEV)
+    im = torch.randn(B, 1, H, W, generator=g).to(DEV)
+    std = (torch.rand(B, 1, H, W, generator=g) + 0.1).to(DEV)
+    res = []
+    for fused in (True, False):
+        d = disp.clone().requires_grad_(True)
+        val, proj = tx.pattern_similarity_loss(d, pattern, im, std, loss_type, 0.5, fused=fused)
+        (gd,) = torch.autograd.grad(val, d)
+        res.append((val.detach(), proj.detach(), gd))
+    assert torch.equal(res[0][1], res[1][1]), "pattern_proj differs"
+    assert abs(res[0][0].item() - res[1][0].item()) <= 1e-6 * abs(res[1][0].item())
+    assert_close(res[0][2].cpu().numpy(), res[1][2].cpu().numpy(), tol=1e-6, what="d loss / d disp")
 
 
 def test_pyramid_pattern_similarity_loss(tx):

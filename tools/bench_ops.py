@@ -140,6 +140,13 @@ def run(only=ALL, iters=30, batch=8, device_index=0, verbose=True):
             _lib.call("ctd_warp_pattern_bwd_f32", pat.data_ptr(), disps[i % NS].data_ptr(), gis[i % NS].data_ptr(), d["o2"].data_ptr(), B, 1, H, W, H, W, st)
         add("pattern_similarity_loss_step", *timeit(f, args.iters), (8 + 24 + 12) * npx,
             extra={"note": "RectifiedPatternSimilarityLoss.tforward + backward to the disparity: warp, fused census_sad loss, warp gradient"})
+        projs = [torch.empty(B, 1, H, W, device=dev) for _ in range(NS)]
+        def f(i, st):
+            d = sets[i % NS]
+            _lib.call("ctd_pattern_similarity_f32", pat.data_ptr(), disps[i % NS].data_ptr(), d["ta"].data_ptr(), d["std"].data_ptr(), d["std"].data_ptr(),
+                      projs[i % NS].data_ptr(), d["o1"].data_ptr(), d["o2"].data_ptr(), sums.data_ptr(), B, 1, H, W, H, W, 3, 0.5, st)
+        add("pattern_similarity_loss_step_one_kernel", *timeit(f, args.iters), (4 + 8 + 4 + 4 + 4) * npx,
+            extra={"note": "the same step as ONE kernel (ctd_pattern_similarity_f32): disp, im, std in; pattern_proj, loss map, d loss / d disp out"})
     if "pyramid" in only:
         # the loss at the model's four pyramid levels (exp_synph.py:25-27,107-111) -- 4 x (warp, fused
         # census_sad loss, warp gradient) = 12 kernels.  Every entry point is capture-safe, so the whole pyramid is ONE
@@ -160,7 +167,13 @@ def run(only=ALL, iters=30, batch=8, device_index=0, verbose=True):
                 _lib.call("ctd_photometric_fwd_bwd_masked_f32", t_["proj"].data_ptr(), t_["ta"].data_ptr(), t_["std"].data_ptr(), t_["std"].data_ptr(),
                           t_["loss"].data_ptr(), t_["gi"].data_ptr(), t_["sums"].data_ptr(), B, 1, h_, w_, 9, 3, 0.5, st)
                 _lib.call("ctd_warp_pattern_bwd_f32", t_["pat"].data_ptr(), t_["disp"].data_ptr(), t_["gi"].data_ptr(), t_["gd"].data_ptr(), B, 1, h_, w_, h_, w_, st)
+        def chain1(st):
+            for h_, w_, t_ in levels:
+                _lib.call("ctd_pattern_similarity_f32", t_["pat"].data_ptr(), t_["disp"].data_ptr(), t_["ta"].data_ptr(), t_["std"].data_ptr(), t_["std"].data_ptr(),
+                          t_["proj"].data_ptr(), t_["loss"].data_ptr(), t_["gd"].data_ptr(), t_["sums"].data_ptr(), B, 1, h_, w_, h_, w_, 3, 0.5, st)
         px_all = sum(B * h_ * w_ for h_, w_, _ in levels)
+        add("pyramid_4_levels_graph_one_kernel_per_level", *timeit(lambda i, st: chain1(st), args.iters, nrep=1), 24 * px_all, px=px_all,
+            extra={"note": "one CUDA graph replay = 4 kernels (ctd_pattern_similarity_f32 per level)"})
         add("pyramid_4_levels_graph", *timeit(lambda i, st: chain(st), args.iters, nrep=1), 44 * px_all, px=px_all,
             extra={"note": "one CUDA graph replay = 12 kernels (4 levels x warp, fused census_sad loss, warp gradient)"})
         cur = torch.cuda.current_stream().cuda_stream
