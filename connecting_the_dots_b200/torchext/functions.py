@@ -205,11 +205,13 @@ class PatternSimilarityFunction(torch.autograd.Function):
         return gd * (g_val / sums[1]), None, None, None, None, None
 
 
-def pattern_similarity_loss(disp, pattern, im, std=None, loss_type="census_sad", loss_eps=0.5, block_size=9, fused=True):
+def pattern_similarity_loss(disp, pattern, im, std=None, loss_type="census_sad", loss_eps=0.5, block_size=9, fused=False):
     """RectifiedPatternSimilarityLoss.tforward (model/networks.py:358-378).  Returns (val, pattern_proj).
-    census modes with block 9 on CUDA float32 (the reference's configuration, networks.py:344,376): ONE kernel forward +
-    backward (PatternSimilarityFunction); otherwise, or with fused=False, three kernels (warp, fused loss forward + backward
-    + masked mean, and in autograd's backward the warp's gradient)."""
+    Default: three kernels (warp; fused loss forward + backward + masked mean; in autograd's backward the warp's gradient).
+    fused=True (census modes, block 9, CUDA float32 -- the reference's configuration, networks.py:344,376): ONE kernel forward
+    + backward (PatternSimilarityFunction).  Measured on B200 at batch 8 x 480x640 (profiles/r02_ops_b8.json): 175 us for
+    the one kernel against 164 us for the three -- the tile loader warps 1.7 pixels per output pixel (halo) behind two
+    dependent global loads, which costs more than the 27 us of the two stand-alone warp kernels -- so it is not the default."""
     mask = torch.ones_like(im) if std is None else std
     ty = _loss_type_id(loss_type)
     if (fused and ty >= 2 and block_size == 9 and disp.is_cuda and disp.dtype == torch.float32 and disp.dim() == 4 and disp.size(1) == 1
