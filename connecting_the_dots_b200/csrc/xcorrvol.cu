@@ -828,6 +828,35 @@ xcorr_fixup_kernel(const float* __restrict__ in0, const float* __restrict__ in1,
   if (nq > 0) drain(nq);
 }
 
+// a non-blocking side stream and four events per host thread and device, for the fork / join inside one call
+struct SideStream {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {};
+  int device = -1;
+};
+int g_xcorr_serial = 0;  // ctd_set_option("xcorr_serial", 1): every kernel of the call on the caller's stream (A/B runs)
+static SideStream* side_stream() {
+  static thread_local SideStream ss[8];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0) return nullptr;
+  SideStream& s = ss[dev % 8];
+  if (s.device != dev) {
+    if (s.stream != nullptr) return nullptr;  // slot taken by another device (more than 8 devices per thread): serialise
+    if (cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaGetLastError();
+      s.stream = nullptr;
+      return nullptr;
+    }
+    for (int i = 0; i < 4; ++i)
+      if (cudaEventCreateWithFlags(&s.ev[i], cudaEventDisableTiming) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+      }
+    s.device = dev;
+  }
+  return &s;
+}
+
 template <int BS>
 static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int64_t B, int64_t H, int64_t W, int64_t D,
                              cudaStream_t st) {
@@ -862,22 +891,43 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
     scratch_free(scratch, st);
     return false;
   }
+  // Fork / join inside the call (legal under stream capture: the side stream joins the capture through the events): the
+  // statistics of the two images run side by side, and the sweep over the listed windows -- which needs only the grades
+  // -- runs beside the main kernel instead of behind it.  The side stream and the events belong to the calling thread.
+  SideStream* ss = side_stream();
+  const bool fork = ss != nullptr && !g_xcorr_serial;
+  cudaStream_t sd = fork ? ss->stream : st;
+  if (fork) {
+    cudaEventRecord(ss->ev[0], st);
+    cudaStreamWaitEvent(sd, ss->ev[0], 0);
+  }
+  xcorr_stats_kernel<BS><<<dim3((unsigned)cdiv(ws1, ST_W), (unsigned)cdiv(H, ST_H), (unsigned)B), 256, st_smem, sd>>>(
+      in1, st1, g1, (int)H, (int)W, (int)ws1, (int)uoff, 1.0f, 0x80000000u, list, count);
   xcorr_stats_kernel<BS><<<dim3((unsigned)cdiv(ws0, ST_W), (unsigned)cdiv(H, ST_H), (unsigned)B), 256, st_smem, st>>>(
       in0, st0, g0, (int)H, (int)W, (int)ws0, 0, float(BS * BS), 0u, list, count);
-  xcorr_stats_kernel<BS><<<dim3((unsigned)cdiv(ws1, ST_W), (unsigned)cdiv(H, ST_H), (unsigned)B), 256, st_smem, st>>>(
-      in1, st1, g1, (int)H, (int)W, (int)ws1, (int)uoff, 1.0f, 0x80000000u, list, count);
+  if (fork) {
+    cudaEventRecord(ss->ev[1], sd);
+    cudaStreamWaitEvent(st, ss->ev[1], 0);   // the main kernel needs both statistics planes
+    cudaEventRecord(ss->ev[2], st);
+    cudaStreamWaitEvent(sd, ss->ev[2], 0);   // ... and so does the sweep
+  }
   const int vec = (W % 4 == 0) && !((reinterpret_cast<uintptr_t>(in0) | reinterpret_cast<uintptr_t>(in1) |
                                      reinterpret_cast<uintptr_t>(out)) & 15);
   const dim3 sgrid((unsigned)cdiv(W, XS_W), (unsigned)cdiv(H, XH), (unsigned)(B * ndchunks));
+  if (!g_xcorr_nofix)
+    xcorr_sweep_kernel<<<148 * 8, 256, 0, sd>>>(g0, g1, list, count, hits, count + 1, (unsigned)cap, (int)H, (int)W, (int)D,
+                                               (int)ws0, (int)ws1, (int)uoff);
   if (vec)
     xcorr_sep_kernel<BS, TD, true><<<sgrid, 512 / TD, smem, st>>>(in0, in1, out, st0, st1, (int)H, (int)W, (int)D, (int)ws0,
                                                                  (int)ws1, (int)uoff, (int)ndchunks);
   else
     xcorr_sep_kernel<BS, TD, false><<<sgrid, 512 / TD, smem, st>>>(in0, in1, out, st0, st1, (int)H, (int)W, (int)D, (int)ws0,
                                                                   (int)ws1, (int)uoff, (int)ndchunks);
+  if (fork) {
+    cudaEventRecord(ss->ev[3], sd);
+    cudaStreamWaitEvent(st, ss->ev[3], 0);   // join: the evaluation of the hits overwrites outputs of the main kernel
+  }
   if (!g_xcorr_nofix) {
-    xcorr_sweep_kernel<<<148 * 8, 256, 0, st>>>(g0, g1, list, count, hits, count + 1, (unsigned)cap, (int)H, (int)W, (int)D,
-                                               (int)ws0, (int)ws1, (int)uoff);
     xcorr_eval_kernel<BS><<<148 * 8, 256, 0, st>>>(in0, in1, out, st0, st1, g0, g1, hits, count + 1, (unsigned)cap, (int)H,
                                                   (int)W, (int)D, (int)ws0, (int)ws1, (int)uoff);
     xcorr_fixup_kernel<BS><<<148 * 3, 256, 0, st>>>(in0, in1, out, st0, st1, g0, g1, list, count, count + 1, (unsigned)cap,

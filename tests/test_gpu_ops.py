@@ -619,6 +619,36 @@ def test_xcorrvol_full_size_golden(tx, golden, bs):
     assert torch.equal(one, vol[0])
 
 
+def test_xcorrvol_fork_join_matches_serial_and_is_capturable(tx):
+    """The call forks inside (the two statistics passes side by side, the sweep beside the main kernel) and joins before
+    the hits are evaluated: same volume as with every kernel on the caller's stream, on a non-default stream, and when
+    the call is captured into a CUDA graph and replayed."""
+    from connecting_the_dots_b200 import _lib, synth
+    d = synth.make_batch(2, 96, 256)
+    a, b = cu(d["ta"]), cu(d["pat_lcn"])
+    _lib.set_option("xcorr_serial", 1)
+    try:
+        ref = tx.xcorrvol(a, b, 48, 9)
+    finally:
+        _lib.set_option("xcorr_serial", 0)
+    assert torch.equal(tx.xcorrvol(a, b, 48, 9), ref)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        on_s = tx.xcorrvol(a, b, 48, 9)
+    s.synchronize()
+    assert torch.equal(on_s, ref)
+    out = torch.zeros_like(ref)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        _lib.call("ctd_xcorrvol_f32", a.data_ptr(), b.data_ptr(), out.data_ptr(), 2, 1, 96, 256, 48, 9, torch.cuda.current_stream().cuda_stream)
+    for _ in range(3):
+        out.zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+
+
 def test_xcorrvol_synthetic_lcn_data(tx):
     """LCN'd dot-pattern rows (the BASELINE config 3 data) on a crop the oracle finishes quickly."""
     from connecting_the_dots_b200 import synth
