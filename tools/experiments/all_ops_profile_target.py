@@ -27,7 +27,7 @@ gd = synth.make_depth_pairs(B, H, W, seed=0); g = {k: cu(v) for k, v in gd.items
 ga, gb, gs = torch.empty(B, 1, H, W, device=dev), torch.zeros(B, 1, H, W, device=dev), torch.zeros(2, 2, device=dev)
 edge = torch.sigmoid(torch.randn(B, 1, H, W, device=dev))
 pat = d["pat_lcn"][:1].contiguous()
-vol = torch.empty(B, 128, H, W, device=dev)
+vol = torch.empty(B, 128, H, W, device=dev) if "--xcorr" in sys.argv else None
 flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)   # 256 MB: evict L2 between the profiled launches
 def run():
     c = lambda *a: _lib.call(*a)
@@ -47,9 +47,8 @@ def run():
     c("ctd_depth_similarity_f32", P(g["depth0"]), P(g["depth1"]), P(ray), P(g["K"]), P(g["R0"]), P(g["t0"]), P(g["R1"]), P(g["t1"]), P(ga), P(gb), P(gs[0]), B, H, W, 0.1, 1.0 / (B * H * W), 0, st); flush.zero_()
     c("ctd_disparity_loss_f32", P(d["disp"]), P(edge), P(o1), P(o2), P(sums), B, H, W, 1.0 / (B * H * W), st); flush.zero_()
     c("ctd_masked_sums_f32", P(d["es"]), P(d["std"]), B * H * W, P(sums), P(ws), st); flush.zero_()
-    c("ctd_xcorrvol_f32", P(d["ta"]), P(d["pat_lcn"]), P(vol), B, 1, H, W, 128, 9, st)
+    if "--xcorr" in sys.argv:
+        c("ctd_xcorrvol_f32", P(d["ta"]), P(d["pat_lcn"]), P(vol), B, 1, H, W, 128, 9, st)
 ws = torch.zeros(int(_lib.lib().ctd_masked_sums_workspace_bytes()), dtype=torch.uint8, device=dev)
 _lib.set_option("xcorr_serial", 1)
-run(); torch.cuda.synchronize()
-print("PROFILE_START", flush=True)
-run(); torch.cuda.synchronize()
+run(); torch.cuda.synchronize()   # the profiled pass: run under `ncu -c N`, the kernels appear in the order of run()
