@@ -49,6 +49,7 @@ extern int g_force_generic;
 // hand-over barriers and near-tie pass cost more than the halved MUFU count saves.
 int g_census_sym = 2;
 int g_census_sym_noguard = 0;  // experiments only: never take the near-tie path (wrong signs at near-ties)
+int g_census_sym_dbg = 0;  // experiments only (wrong results): 1 = no global loads in the staging, 2 = no stores in the write-out, 4 = no band CTAs, 8 = no masked sums
 long long* g_census_sym_timeline = nullptr;  // experiments only: 16 x 8 int64 per CTA: per warp the globaltimer at start / staged / walked / exact done / end / walk end / carry end, smid
 
 namespace {
@@ -272,7 +273,7 @@ template <int TYPE, bool FWD, bool BWD>
 __global__ void __launch_bounds__(CS_NW * 32, CS_MINB)
 census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go, float* __restrict__ out,
                   float* __restrict__ gi, const float* __restrict__ mask, const SymGeom g, float eps, float guard, double* __restrict__ partials,
-                  unsigned* __restrict__ ticket, float* __restrict__ sums2, long long* __restrict__ timeline) {
+                  unsigned* __restrict__ ticket, float* __restrict__ sums2, long long* __restrict__ timeline, int dbg) {
   extern __shared__ __align__(16) float smem[];
   float* E = smem;
   float* T = E + CS_TC * CS_PT;
@@ -302,7 +303,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
   // launch (measured: the band as the last CTAs extended a 120 us launch by 20 us).
   if ((int)blockIdx.x < g.nbandcta) {  // block-uniform
     band_block<TYPE, FWD, BWD>(es, ta, go, out, gi, mask, g, eps, (int64_t)blockIdx.x * (CS_NW * 32) + tid, mnum, mden);
-    if (FWD && mask != nullptr) finish_masked_sums((double)mnum, (double)mden, partials, ticket, sums2);
+    if (FWD && mask != nullptr && !(dbg & 8)) finish_masked_sums((double)mnum, (double)mden, partials, ticket, sums2);
     stamp(4);
     return;
   }
@@ -333,7 +334,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
 #pragma unroll
       for (int it = 0; it < NIT; ++it) {
         const int idx = tid + it * (CS_NW * 32), r = idx % CS_ROWS, q = idx / CS_ROWS, y = R0 + r;
-        if (idx < nitems && y < H) {
+        if (idx < nitems && y < H && !(dbg & 1)) {
           const int64_t o = (int64_t)y * W + (c0 - 4 + 4 * q);
           ve[it] = ldg4(ep + o);
           vt[it] = ldg4(tp + o);
@@ -347,7 +348,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
         float* de = E + (4 * q) * CS_PT + 4 + r;
         float* dt = T + (4 * q) * CS_PT + 4 + r;
         float* dg = G + (4 * q) * CS_PT + 4 + r;
-        if (y < H) {
+        if (y < H && !(dbg & 1)) {
           de[0] = ve[it].x; de[CS_PT] = ve[it].y; de[2 * CS_PT] = ve[it].z; de[3 * CS_PT] = ve[it].w;
           dt[0] = vt[it].x; dt[CS_PT] = vt[it].y; dt[2 * CS_PT] = vt[it].z; dt[3 * CS_PT] = vt[it].w;
           if (BWD) {
@@ -588,7 +589,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
         if (FWD) {
           const float* s = SO + (4 * q) * CS_ROWS + r;
           const float4 v = make_float4(s[0] * sf, s[CS_ROWS] * sf, s[2 * CS_ROWS] * sf, s[3 * CS_ROWS] * sf);
-          *reinterpret_cast<float4*>(outp + o) = v;
+          if (!(dbg & 2)) *reinterpret_cast<float4*>(outp + o) = v;
           if (mp != nullptr) {
             const float4 m = ldg4(mp + o);
             mnum = fmaf(m.x, v.x, fmaf(m.y, v.y, fmaf(m.z, v.z, fmaf(m.w, v.w, mnum))));
@@ -597,7 +598,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
         }
         if (BWD) {
           const float* s = SG + (4 * q) * CS_ROWS + r;
-          *reinterpret_cast<float4*>(gip + o) = make_float4(s[0] * sb, s[CS_ROWS] * sb, s[2 * CS_ROWS] * sb, s[3 * CS_ROWS] * sb);
+          if (!(dbg & 2)) *reinterpret_cast<float4*>(gip + o) = make_float4(s[0] * sb, s[CS_ROWS] * sb, s[2 * CS_ROWS] * sb, s[3 * CS_ROWS] * sb);
         }
       }
     } else {
@@ -618,7 +619,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
       }
     }
   }
-  if (FWD && mask != nullptr) finish_masked_sums((double)mnum, (double)mden, partials, ticket, sums2);  // block-uniform
+  if (FWD && mask != nullptr && !(dbg & 8)) finish_masked_sums((double)mnum, (double)mden, partials, ticket, sums2);  // block-uniform
   stamp(4);
 }
 
@@ -632,7 +633,7 @@ static bool launch_variant(const float* es, const float* ta, const float* go, fl
     cudaGetLastError();
     return false;
   }
-  kernel<<<grid, CS_NW * 32, CS_SMEM, st>>>(es, ta, go, out, gi, mask, g, eps, g_census_sym_noguard ? 0.f : SIGN_GUARD, ms.partials, ms.ticket, sums2, g_census_sym_timeline);
+  kernel<<<grid, CS_NW * 32, CS_SMEM, st>>>(es, ta, go, out, gi, mask, g, eps, g_census_sym_noguard ? 0.f : SIGN_GUARD, ms.partials, ms.ticket, sums2, g_census_sym_timeline, g_census_sym_dbg);
   return true;
 }
 
@@ -658,7 +659,7 @@ bool census_sym_launch(const float* es, const float* ta, const float* go, float*
   const int64_t ntiles = B * g.nstrips * g.nct;
   g.band_per_image = 8 * (int)W + 8 * ((int)H - 8);
   g.nband = B * g.band_per_image;
-  const int64_t nbandcta = cdiv(g.nband, CS_NW * 32);
+  const int64_t nbandcta = (g_census_sym_dbg & 4) ? 0 : cdiv(g.nband, CS_NW * 32);
   if (ntiles + nbandcta > (int64_t)INT32_MAX) return false;
   g.ntiles = (int)ntiles;
   g.nbandcta = (int)nbandcta;

@@ -18,6 +18,7 @@ extern int g_census_sym;
 extern int g_xcorr_serial;
 extern int g_proj_nn_tile;
 extern int g_census_sym_noguard;
+extern int g_census_sym_dbg;
 int g_disable_tma = 0;    // tests / A-B runs: use the shared-memory tile kernels instead of the TMA ones
 static std::atomic<uint64_t> g_launches{0};
 
@@ -208,6 +209,10 @@ CTD_API int ctd_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "proj_nn_tile")) {
     ctd::g_proj_nn_tile = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "census_sym_dbg")) {
+    ctd::g_census_sym_dbg = value;
     return CTD_OK;
   }
   if (name && !strcmp(name, "census_sym_noguard")) {

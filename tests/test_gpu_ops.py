@@ -362,7 +362,7 @@ def test_lcn_golden(tx, golden, r, e):
 
 
 @pytest.mark.parametrize("shape", [(1, 480, 640, 5), (3, 37, 130, 5), (2, 16, 12, 3), (1, 61, 259, 7), (1, 40, 40, 17),
-                                   (1, 6, 6, 5), (2, 100, 128, 0), (1, 9, 1000, 2)])
+                                   (1, 6, 6, 5), (2, 100, 128, 0), (1, 9, 1000, 2), (1, 20, 32, 5), (2, 20, 132, 5)])
 def test_lcn_vs_oracle(tx, shape):
     N, H, W, r = shape
     rng = np.random.RandomState(N * 7 + H)
