@@ -37,6 +37,12 @@ int fail(int code, const char* fmt, ...) {
 
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 
+struct RelaxedCaptureMode {
+  cudaStreamCaptureMode mode = cudaStreamCaptureModeRelaxed;
+  RelaxedCaptureMode() { cudaThreadExchangeStreamCaptureMode(&mode); }
+  ~RelaxedCaptureMode() { cudaThreadExchangeStreamCaptureMode(&mode); }
+};
+
 static cudaMemPool_t scratch_pool() {
   static std::mutex mtx;
   static cudaMemPool_t pools[64] = {};
@@ -44,6 +50,9 @@ static cudaMemPool_t scratch_pool() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   std::lock_guard<std::mutex> lk(mtx);
   if (!pools[dev]) {
+    // the first use may come from inside a stream capture (global capture mode forbids allocation-like calls there):
+    // create the pool in relaxed mode, the capture is not affected
+    RelaxedCaptureMode relaxed;
     cudaMemPoolProps props = {};
     props.allocType = cudaMemAllocationTypePinned;
     props.location.type = cudaMemLocationTypeDevice;
@@ -82,6 +91,7 @@ static unsigned char* ms_base(int dev) {
   if (dev < 0 || dev >= 64) return nullptr;
   std::lock_guard<std::mutex> lk(mtx);
   if (!bases[dev]) {
+    RelaxedCaptureMode relaxed;  // may load the module: not a capturable operation
     void* p = nullptr;
     if (cudaGetSymbolAddress(&p, g_ms_slots) != cudaSuccess) {
       cudaGetLastError();
@@ -92,6 +102,8 @@ static unsigned char* ms_base(int dev) {
   return bases[dev];
 }
 
+int g_ms_force_scratch = 0;  // tests: always take the scratch-memory path (as if the static slots were exhausted)
+
 bool ms_acquire(size_t nblocks, cudaStream_t st, MsSlot* s) {
   s->ticket = nullptr;
   s->partials = nullptr;
@@ -99,7 +111,7 @@ bool ms_acquire(size_t nblocks, cudaStream_t st, MsSlot* s) {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return false;
   int slot = -1;
-  if (nblocks <= MS_MAXBLK && dev < 64) {
+  if (nblocks <= MS_MAXBLK && dev < 64 && !g_ms_force_scratch) {
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cap) != cudaSuccess) {
       cudaGetLastError();
@@ -129,7 +141,9 @@ bool ms_acquire(size_t nblocks, cudaStream_t st, MsSlot* s) {
     return true;
   }
   char* sc = static_cast<char*>(scratch_alloc(16 + nblocks * 16, st));
-  if (!sc || cudaMemsetAsync(sc, 0, 16, st) != cudaSuccess) {
+  cudaError_t e = sc ? cudaMemsetAsync(sc, 0, 16, st) : cudaErrorMemoryAllocation;
+  if (e != cudaSuccess) {
+    fail(CTD_ERR_NOMEM, "reduction workspace from the scratch pool: %s", cudaGetErrorString(e));
     cudaGetLastError();
     scratch_free(sc, st);
     return false;
@@ -209,6 +223,10 @@ CTD_API int ctd_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "proj_nn_tile")) {
     ctd::g_proj_nn_tile = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "ms_force_scratch")) {
+    ctd::g_ms_force_scratch = value;
     return CTD_OK;
   }
   if (name && !strcmp(name, "census_sym_dbg")) {

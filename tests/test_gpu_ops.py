@@ -1031,6 +1031,41 @@ def test_masked_loss_calls_do_not_share_reduction_slots(tx):
             assert torch.equal(t["sums"], w), it
 
 
+def test_masked_calls_under_capture_when_static_slots_are_exhausted(tx):
+    """When the static reduction slots run out (more than 96 captured masked calls in a process) the workspace comes from
+    the stream-ordered scratch pool with a memset node: captured and replayed like any other call, same sums.  Runs in a
+    fresh process so that the scratch pool's FIRST use happens inside the capture (pool creation must not break it)."""
+    import subprocess, sys, os
+    code = """
+import sys, torch
+sys.path.insert(0, %r)
+from connecting_the_dots_b200 import _lib
+B, H, W = 2, 64, 96
+g = torch.Generator(device="cpu").manual_seed(1)
+t = {k: torch.randn(B, 1, H, W, generator=g).cuda() for k in ("es", "ta")}
+t["go"], t["mask"] = torch.rand(B, 1, H, W, generator=g).cuda(), torch.rand(B, 1, H, W, generator=g).cuda() + 0.5
+out, gi, sums = torch.empty(B, 1, H, W, device="cuda"), torch.empty(B, 1, H, W, device="cuda"), torch.zeros(3, 2, device="cuda")
+def launch(ty, k, st):
+    _lib.call("ctd_photometric_fwd_bwd_masked_f32", t["es"].data_ptr(), t["ta"].data_ptr(), t["go"].data_ptr(), t["mask"].data_ptr(),
+              out.data_ptr(), gi.data_ptr(), sums[k].data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
+_lib.set_option("ms_force_scratch", 1)
+gr = torch.cuda.CUDAGraph()
+with torch.cuda.graph(gr):
+    st = torch.cuda.current_stream().cuda_stream
+    launch(1, 0, st); launch(3, 1, st)
+for _ in range(3):
+    sums.zero_(); gr.replay(); torch.cuda.synchronize()
+got = sums[:2].clone()
+_lib.set_option("ms_force_scratch", 0)
+launch(1, 0, torch.cuda.current_stream().cuda_stream); launch(3, 1, torch.cuda.current_stream().cuda_stream)
+torch.cuda.synchronize()
+assert torch.equal(got, sums[:2]), (got, sums)
+print("OK")
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "OK" in r.stdout, r.stderr[-2000:]
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
 def test_xcorrvol_on_second_device(tx):
     """Per-device kernel attributes (dynamic shared memory above 48 KB) are set for every device a process uses."""
