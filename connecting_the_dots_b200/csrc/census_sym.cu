@@ -33,7 +33,8 @@
 //     in a bitmap; after the walk the CTA recomputes those pixels' gradients from the staged tiles with the
 //     reference's IEEE operation sequence (one warp per pixel), so every sign decision matches ext_cpu.
 //   * the 4-pixel band along the image border, whose windows are replicate-clamped (a tap can hit the same pixel
-//     several times), is computed by extra CTAs of the same launch with the direct gather (3 % of a 480x640 image).
+//     several times), is computed by extra CTAs of the same launch with the direct gather from small shared-memory
+//     tiles (3 % of a 480x640 image); they come first in the grid and share the SMs with the first tiles.
 #include <algorithm>
 
 #include "ctd_common.cuh"
@@ -79,8 +80,7 @@ struct SymGeom {
   int vec;              // 128-bit global accesses (W % 4 == 0, 16-byte aligned pointers): tiles start on a quad
   int ntiles;           // B * nstrips * nct
   int nbandcta;         // CTAs of the border band (they come first in the grid)
-  int band_per_image;   // 8 W + 8 (H - 8)
-  int64_t nband;        // B * band_per_image
+  int pf_stride;        // tiles resident at a time (2 per SM): tile t prefetches tile t + pf_stride into L2
 };
 
 __device__ __forceinline__ float or_sign(float mag, float s) {  // mag > 0 with the sign bit of s
@@ -127,7 +127,10 @@ __device__ __forceinline__ void ld4(float* d, const float* p) {
 }
 
 // Rare path: this lane saw |dd| < SIGN_GUARD among the pairs of (tile column x, offset column dx).  Find them again
-// (same arithmetic) and flag both pixels of each.  Tile rows live at index row + 4 of a column.
+// (same arithmetic), evaluate the two sign decisions of each with the reference's IEEE operation sequence (ext.h:321-330;
+// the pair enters both pixels' sums in two roles, "tap" and "centre") and flag both pixels ONLY when a decision differs
+// from the fast path's sign(dd) -- most near-ties agree, and an exact +-0 (sign 0 in the reference) never does.
+// Tile rows live at index row + 4 of a column.
 __device__ __noinline__ void flag_near_ties(const float* __restrict__ E, const float* __restrict__ T, unsigned* flags, int x, int dx,
                                             int lane, float eps) {
   for (int k = 0; k < 4; ++k) {
@@ -141,8 +144,15 @@ __device__ __noinline__ void flag_near_ties(const float* __restrict__ E, const f
       const float r2 = rsqrt_approx(fmaf(dta, dta, eps));
       const float dd = fmaf(des, r1, -(dta * r2));
       if (fabsf(dd) < SIGN_GUARD) {
-        atomicOr(&flags[x * CS_FLAGW + (ri >> 5)], 1u << (ri & 31));
-        atomicOr(&flags[(x + dx) * CS_FLAGW + (rq >> 5)], 1u << (rq & 31));
+        const float q1 = __fdiv_rn(des, __fsqrt_rn(__fadd_rn(__fmul_rn(des, des), eps)));
+        const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
+        const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));    // h(es_i - es_q) - h(ta_i - ta_q)
+        const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));  // h(es_q - es_i) - h(ta_q - ta_i)
+        const float sf = (__float_as_uint(dd) & 0x80000000u) ? -1.f : 1.f;                       // what or_sign() applied
+        if (sgnf(d_tap) != sf || sgnf(d_ctr) != -sf) {
+          atomicOr(&flags[x * CS_FLAGW + (ri >> 5)], 1u << (ri & 31));
+          atomicOr(&flags[(x + dx) * CS_FLAGW + (rq >> 5)], 1u << (rq & 31));
+        }
       }
     }
   }
@@ -174,30 +184,61 @@ __device__ __forceinline__ float exact_sad_sum(const float* __restrict__ E, cons
   return acc;
 }
 
-// ---- the border band: one thread per pixel, direct gather with clamp multiplicities -------------------------------
+// ---- the border band: direct gather with clamp multiplicities, from shared-memory tiles ---------------------------
 // grad_in[i] = K * sum over the 81 window offsets of phi(dd(i,t)) r1^3 (go[i] + [p real] M(i,p) go[p]), t the clamped tap,
 // p = i + offset unclamped, M(i,p) = how many offsets of p clamp onto i (1 unless i lies on the image border).
+// A band CTA owns 256 band pixels -- 64 columns of the first / last four rows, or 64 rows of the first / last four columns
+// -- and stages their halo (replicate-clamped es / ta, grad_out zero outside the image) in shared memory first: with one
+// thread per pixel reading global memory the band was a chain of dependent loads that held an SM slot for 17-22 us.
+constexpr int BD_LONG = 64, BD_SHORT = 4;
+
+struct BandTile {
+  int64_t n;
+  int ox0, oy0, ow, oh;  // output region (may stick out of the image / the band at its far end)
+  int ymin, ymax;        // rows of the region that belong to this part of the band: [ymin, ymax)
+};
+
+__device__ __forceinline__ BandTile band_tile(const SymGeom& g, int cta) {
+  BandTile b;
+  const int ntx = (g.W + BD_LONG - 1) / BD_LONG, nty = (g.H - 8 + BD_LONG - 1) / BD_LONG, per = 2 * ntx + 2 * nty;
+  b.n = cta / per;
+  int k = cta % per;
+  if (k < 2 * ntx) {  // rows 0..3 and H-4..H-1
+    b.ow = BD_LONG; b.oh = BD_SHORT;
+    b.ox0 = (k % ntx) * BD_LONG;
+    b.oy0 = k < ntx ? 0 : g.H - 4;
+    b.ymin = b.oy0; b.ymax = b.oy0 + 4;
+  } else {            // columns 0..3 and W-4..W-1 of the rows between
+    k -= 2 * ntx;
+    b.ow = BD_SHORT; b.oh = BD_LONG;
+    b.ox0 = k < nty ? 0 : g.W - 4;
+    b.oy0 = 4 + (k % nty) * BD_LONG;
+    b.ymin = b.oy0; b.ymax = min(b.oy0 + BD_LONG, g.H - 4);
+  }
+  return b;
+}
+
 template <int TYPE, bool FWD, bool BWD, bool EXACT>
-__device__ __forceinline__ void band_pixel_sums(const float* __restrict__ ep, const float* __restrict__ tp, const float* __restrict__ gp,
-                                                int x, int y, int H, int W, float eps, float& facc, float& acc, float& near0) {
-  const float ei = __ldg(ep + (int64_t)y * W + x), ti = __ldg(tp + (int64_t)y * W + x);
-  const float gc = BWD ? __ldg(gp + (int64_t)y * W + x) : 0.f;
+__device__ __forceinline__ void band_pixel_sums(const float* __restrict__ Eb, const float* __restrict__ Tb, const float* __restrict__ Gb, int pitch,
+                                                int lx, int ly, int x, int y, int H, int W, float eps, float& facc, float& acc, float& near0) {
+  const float ei = Eb[(ly + 4) * pitch + lx + 4], ti = Tb[(ly + 4) * pitch + lx + 4];
+  const float gc = BWD ? Gb[(ly + 4) * pitch + lx + 4] : 0.f;
   facc = 0.f;
   acc = 0.f;
   near0 = 1.f;
   for (int dy = -R9; dy <= R9; ++dy) {
     const int py = y + dy, ty = clampi(py, 0, H - 1);
     const float my = y == 0 ? float(R9 + 1 - dy) : (y == H - 1 ? float(R9 + 1 + dy) : 1.f);
+    const int ro = (ly + 4 + dy) * pitch + lx + 4;
 #pragma unroll
     for (int dx = -R9; dx <= R9; ++dx) {
       const int px = x + dx, tx = clampi(px, 0, W - 1);
-      const int64_t o = (int64_t)ty * W + tx;
-      const float des = ei - __ldg(ep + o), dta = ti - __ldg(tp + o);
+      const float des = ei - Eb[ro + dx], dta = ti - Tb[ro + dx];
       const bool self = ty == y && tx == x;
-      float gq = 0.f;  // grad_out of p = i + offset times M(i,p) when p is a real pixel (i is a tap of its window)
-      if (BWD && py == ty && px == tx) {
+      float gq = 0.f;  // grad_out of p = i + offset (zero in the tile when p is not a real pixel) times M(i,p)
+      if (BWD) {
         const float mx = x == 0 ? float(R9 + 1 - dx) : (x == W - 1 ? float(R9 + 1 + dx) : 1.f);
-        gq = (mx * my) * __ldg(gp + o);
+        gq = (mx * my) * Gb[ro + dx];
       }
       if (!EXACT) {
         const float r1 = rsqrt_approx(fmaf(des, des, eps));
@@ -223,34 +264,40 @@ __device__ __forceinline__ void band_pixel_sums(const float* __restrict__ ep, co
 }
 
 template <int TYPE, bool FWD, bool BWD>
-__device__ __forceinline__ void band_block(const float* __restrict__ es, const float* __restrict__ ta, const float* __restrict__ go,
-                                           float* __restrict__ out, float* __restrict__ gi, const float* __restrict__ mask,
-                                           const SymGeom& g, float eps, int64_t idx, float& mnum, float& mden) {
-  if (idx >= g.nband) return;
+__device__ __forceinline__ void band_block(float* __restrict__ sm, const float* __restrict__ es, const float* __restrict__ ta,
+                                           const float* __restrict__ go, float* __restrict__ out, float* __restrict__ gi,
+                                           const float* __restrict__ mask, const SymGeom& g, float eps, int cta, int tid, float& mnum,
+                                           float& mden) {
+  const BandTile b = band_tile(g, cta);
   const int H = g.H, W = g.W;
-  const int64_t n = idx / g.band_per_image;
-  int j = (int)(idx - n * g.band_per_image), x, y;
-  if (j < 8 * W) {  // the first and last four rows
-    y = j / W;
-    x = j - y * W;
-    if (y >= 4) y += H - 8;
-  } else {          // the first and last four columns of the rows between
-    j -= 8 * W;
-    y = 4 + j / 8;
-    x = j % 8;
-    if (x >= 4) x += W - 8;
-  }
   const int64_t plane = (int64_t)H * W;
-  const float* ep = es + n * plane;
-  const float* tp = ta + n * plane;
-  const float* gp = BWD ? go + n * plane : nullptr;
+  const float* ep = es + b.n * plane;
+  const float* tp = ta + b.n * plane;
+  const float* gp = BWD ? go + b.n * plane : nullptr;
+  const int pitch = b.ow + 8, rows = b.oh + 8, nel = pitch * rows;  // 72 x 12 or 12 x 72
+  float* Eb = sm;
+  float* Tb = Eb + 864;
+  float* Gb = Tb + 864;
+  for (int i = tid; i < nel; i += CS_NW * 32) {
+    const int r = i / pitch, c = i % pitch;
+    const int uy = b.oy0 - 4 + r, ux = b.ox0 - 4 + c;
+    const int64_t o = (int64_t)clampi(uy, 0, H - 1) * W + clampi(ux, 0, W - 1);
+    Eb[i] = __ldg(ep + o);
+    Tb[i] = __ldg(tp + o);
+    if (BWD) Gb[i] = (uy >= 0 && uy < H && ux >= 0 && ux < W) ? __ldg(gp + o) : 0.f;
+  }
+  __syncthreads();
+  if (tid >= BD_LONG * BD_SHORT) return;
+  const int lx = tid % b.ow, ly = tid / b.ow;
+  const int x = b.ox0 + lx, y = b.oy0 + ly;
+  if (x >= W || y < b.ymin || y >= b.ymax) return;
   float facc, acc, near0;
-  band_pixel_sums<TYPE, FWD, BWD, false>(ep, tp, gp, x, y, H, W, eps, facc, acc, near0);
+  band_pixel_sums<TYPE, FWD, BWD, false>(Eb, Tb, Gb, pitch, lx, ly, x, y, H, W, eps, facc, acc, near0);
   if (BWD && TYPE == 3 && near0 < SIGN_GUARD) {
     float f2, n2;
-    band_pixel_sums<TYPE, false, true, true>(ep, tp, gp, x, y, H, W, eps, f2, acc, n2);
+    band_pixel_sums<TYPE, false, true, true>(Eb, Tb, Gb, pitch, lx, ly, x, y, H, W, eps, f2, acc, n2);
   }
-  const int64_t o = n * plane + (int64_t)y * W + x;
+  const int64_t o = b.n * plane + (int64_t)y * W + x;
   if (FWD) {
     const float v = facc * ((TYPE == 2 ? 0.25f : 0.5f) * INV81);
     out[o] = v;
@@ -302,7 +349,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
   // uses little of an SM, so it should share the SMs with the first tiles instead of running alone at the end of the
   // launch (measured: the band as the last CTAs extended a 120 us launch by 20 us).
   if ((int)blockIdx.x < g.nbandcta) {  // block-uniform
-    band_block<TYPE, FWD, BWD>(es, ta, go, out, gi, mask, g, eps, (int64_t)blockIdx.x * (CS_NW * 32) + tid, mnum, mden);
+    band_block<TYPE, FWD, BWD>(smem, es, ta, go, out, gi, mask, g, eps, (int)blockIdx.x, tid, mnum, mden);
     if (FWD && mask != nullptr && !(dbg & 8)) finish_masked_sums((double)mnum, (double)mden, partials, ticket, sums2);
     stamp(4);
     return;
@@ -390,6 +437,23 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
   }
   __syncthreads();
   stamp(1);
+  // The tiles of the next wave start with a 20 MB burst from DRAM (every SM stages two tiles at once) while this wave
+  // uses no DRAM bandwidth at all during its walk: ask L2 for the tile that runs pf_stride tiles later.
+  if (tile + g.pf_stride < g.ntiles) {
+    const int t2 = tile + g.pf_stride;
+    const int ct2 = t2 % g.nct, strip2 = (t2 / g.nct) % g.nstrips;
+    const int64_t n2 = t2 / (g.nct * g.nstrips);
+    const int a0 = tile_col0(g, ct2) - 4, a1 = tile_col0(g, ct2 + 1) + 4;   // columns [a0, a1)
+    const int lines = ((a1 - a0) * 4 + 127) / 128 + 1;                       // 128-byte lines per row (unaligned start)
+    const int rows2 = min(CS_ROWS, H - strip2 * CS_USE);
+    for (int i = tid; i < rows2 * lines; i += CS_NW * 32) {
+      const int r = i / lines, l = i % lines;
+      const int64_t o = n2 * plane + (int64_t)(strip2 * CS_USE + r) * W + min(a0 + 32 * l, W - 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(es + o));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(ta + o));
+      if (BWD) asm volatile("prefetch.global.L2 [%0];" ::"l"(go + o));
+    }
+  }
 
   // ---- roles: slot x = tile column x = output column x - 4.  Warp 0 walks the run-in (slots 0..3: only the offsets that
   // reach columns >= c0, 2.25 columns' worth of pairs); warp w >= 1 walks the four output columns 4(w-1) .. 4w-1.
@@ -623,6 +687,12 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
   stamp(4);
 }
 
+static int sm_count_cs() {
+  int dev = 0, v = 148;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  return v > 0 ? v : 148;
+}
+
 template <int TYPE, bool FWD, bool BWD>
 static bool launch_variant(const float* es, const float* ta, const float* go, float* out, float* gi, const float* mask,
                            const SymGeom& g, float eps, unsigned grid, MsSlot& ms, float* sums2, cudaStream_t st) {
@@ -657,9 +727,8 @@ bool census_sym_launch(const float* es, const float* ta, const float* go, float*
   g.nstrips = (int)cdiv(H - 8, CS_USE);
   g.nct = g.vec ? (int)cdiv(g.ncol / 4, CS_XC / 4) : (int)cdiv(g.ncol, CS_XC);
   const int64_t ntiles = B * g.nstrips * g.nct;
-  g.band_per_image = 8 * (int)W + 8 * ((int)H - 8);
-  g.nband = B * g.band_per_image;
-  const int64_t nbandcta = (g_census_sym_dbg & 4) ? 0 : cdiv(g.nband, CS_NW * 32);
+  const int64_t nbandcta = (g_census_sym_dbg & 4) ? 0 : B * (2 * cdiv(W, BD_LONG) + 2 * cdiv(H - 8, BD_LONG));
+  g.pf_stride = 2 * sm_count_cs();
   if (ntiles + nbandcta > (int64_t)INT32_MAX) return false;
   g.ntiles = (int)ntiles;
   g.nbandcta = (int)nbandcta;
