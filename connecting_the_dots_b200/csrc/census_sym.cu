@@ -131,28 +131,28 @@ __device__ __forceinline__ void ld4(float* d, const float* p) {
 // the pair enters both pixels' sums in two roles, "tap" and "centre") and flag both pixels ONLY when a decision differs
 // from the fast path's sign(dd) -- most near-ties agree, and an exact +-0 (sign 0 in the reference) never does.
 // Tile rows live at index row + 4 of a column.
+// The WHOLE warp works on the pairs of one lane (`owner`): 36 pairs (16 for dx = 0), at most two per lane, so the rescan
+// is two short iterations instead of a serial chain of 36 that the other warps of the CTA wait for at the next barrier.
 __device__ __noinline__ void flag_near_ties(const float* __restrict__ E, const float* __restrict__ T, unsigned* flags, int x, int dx,
-                                            int lane, float eps) {
-  for (int k = 0; k < 4; ++k) {
-    const int ri = 4 * lane + k;
-    const float ei = E[x * CS_PT + 4 + ri], ti = T[x * CS_PT + 4 + ri];
-    for (int dy = (dx == 0 ? 1 : -R9); dy <= R9; ++dy) {
-      const int rq = ri + dy;
-      if (rq < 0 || rq >= CS_ROWS) continue;
-      const float des = ei - E[(x + dx) * CS_PT + 4 + rq], dta = ti - T[(x + dx) * CS_PT + 4 + rq];
-      const float r1 = rsqrt_approx(fmaf(des, des, eps));
-      const float r2 = rsqrt_approx(fmaf(dta, dta, eps));
-      const float dd = fmaf(des, r1, -(dta * r2));
-      if (fabsf(dd) < SIGN_GUARD) {
-        const float q1 = __fdiv_rn(des, __fsqrt_rn(__fadd_rn(__fmul_rn(des, des), eps)));
-        const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
-        const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));    // h(es_i - es_q) - h(ta_i - ta_q)
-        const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));  // h(es_q - es_i) - h(ta_q - ta_i)
-        const float sf = (__float_as_uint(dd) & 0x80000000u) ? -1.f : 1.f;                       // what or_sign() applied
-        if (sgnf(d_tap) != sf || sgnf(d_ctr) != -sf) {
-          atomicOr(&flags[x * CS_FLAGW + (ri >> 5)], 1u << (ri & 31));
-          atomicOr(&flags[(x + dx) * CS_FLAGW + (rq >> 5)], 1u << (rq & 31));
-        }
+                                            int owner, int lane, float eps) {
+  for (int p = lane; p < 36; p += 32) {
+    const int k = p / 9, dy = p % 9 - R9;
+    if (dx == 0 && dy < 1) continue;
+    const int ri = 4 * owner + k, rq = ri + dy;
+    if (rq < 0 || rq >= CS_ROWS) continue;
+    const float des = E[x * CS_PT + 4 + ri] - E[(x + dx) * CS_PT + 4 + rq], dta = T[x * CS_PT + 4 + ri] - T[(x + dx) * CS_PT + 4 + rq];
+    const float r1 = rsqrt_approx(fmaf(des, des, eps));
+    const float r2 = rsqrt_approx(fmaf(dta, dta, eps));
+    const float dd = fmaf(des, r1, -(dta * r2));
+    if (fabsf(dd) < SIGN_GUARD) {
+      const float q1 = __fdiv_rn(des, __fsqrt_rn(__fadd_rn(__fmul_rn(des, des), eps)));
+      const float q2 = __fdiv_rn(dta, __fsqrt_rn(__fadd_rn(__fmul_rn(dta, dta), eps)));
+      const float d_tap = __fsub_rn(0.5f * __fadd_rn(1.f, q1), 0.5f * __fadd_rn(1.f, q2));    // h(es_i - es_q) - h(ta_i - ta_q)
+      const float d_ctr = __fsub_rn(0.5f * __fadd_rn(1.f, -q1), 0.5f * __fadd_rn(1.f, -q2));  // h(es_q - es_i) - h(ta_q - ta_i)
+      const float sf = (__float_as_uint(dd) & 0x80000000u) ? -1.f : 1.f;                       // what or_sign() applied
+      if (sgnf(d_tap) != sf || sgnf(d_ctr) != -sf) {
+        atomicOr(&flags[x * CS_FLAGW + (ri >> 5)], 1u << (ri & 31));
+        atomicOr(&flags[(x + dx) * CS_FLAGW + (rq >> 5)], 1u << (rq & 31));
       }
     }
   }
@@ -576,12 +576,16 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
       }
     }
     if (BWD && TYPE == 3) {  // one vote per step; only the offset columns with a near-tie are scanned again
-      if (__any_sync(FULL, hit != 0u)) {
+      unsigned owners = __ballot_sync(FULL, hit != 0u);
+      while (owners) {  // warp-uniform loop over the lanes that saw a near-tie
+        const int owner = __ffs(owners) - 1;
+        owners &= owners - 1;
+        const unsigned h = __shfl_sync(FULL, hit, owner);
 #pragma unroll 1
         for (int dx = 0; dx <= 4; ++dx)
-          if (hit >> dx & 1u) flag_near_ties(E, T, flags, x, dx, lane, eps);
-        hit = 0u;
+          if (h >> dx & 1u) flag_near_ties(E, T, flags, x, dx, owner, lane, eps);
       }
+      hit = 0u;
     }
     if (x >= 4) {  // column x - 4 of the tile's outputs has met all the neighbours this warp walks over
       if (FWD) *reinterpret_cast<float4*>(SO + (x - 4) * CS_ROWS + 4 * lane) = make_float4(fI[0], fI[1], fI[2], fI[3]);
