@@ -468,7 +468,8 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
 #pragma unroll
     for (int k = 0; k < 4; ++k) fQ[d][k] = aQ[d][k] = 0.f;
   const unsigned FULL = 0xffffffffu;
-  float nm = 1.f;     // smallest |dd| among the pairs of the current offset column
+  float nmk[4] = {1.f, 1.f, 1.f, 1.f};  // smallest |dd| among the pairs of the current offset column, per own row (four
+                                        // independent min chains: one chain through all 36 pairs serialises them)
   unsigned hit = 0u;  // bit dx: this lane saw a near-tie among the pairs of offset column dx of the current step
 
 #pragma unroll 1
@@ -487,7 +488,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
       for (int k = 0; k < 3; ++k)
 #pragma unroll
         for (int rq = k + 1; rq < 4; ++rq)
-          pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], ei[rq], ti[rq], gI[rq], eps, fI[k], fI[rq], aI[k], aI[rq], nm);
+          pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], ei[rq], ti[rq], gI[rq], eps, fI[k], fI[rq], aI[k], aI[rq], nmk[k]);
       float e1[4], t1[4], g1[4];
       const float* c = E + x * CS_PT + 8 + 4 * lane;
       ld4(e1, c);
@@ -499,15 +500,15 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
       for (int k = 0; k < 4; ++k)
 #pragma unroll
         for (int j = 0; j <= k; ++j)  // row 4 lane + 4 + j: offset 4 + j - k in 1..4
-          pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], e1[j], t1[j], g1[j], eps, fI[k], lf[j], aI[k], la[j], nm);
+          pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], e1[j], t1[j], g1[j], eps, fI[k], lf[j], aI[k], la[j], nmk[k]);
 #pragma unroll
       for (int m = 0; m < 4; ++m) {
         if (FWD) fI[m] += __shfl_up_sync(FULL, lf[m], 1);
         if (BWD) aI[m] += __shfl_up_sync(FULL, la[m], 1);
       }
       if (BWD && TYPE == 3) {
-        hit |= nm < guard ? 1u : 0u;
-        nm = 1.f;
+        hit |= fminf(fminf(nmk[0], nmk[1]), fminf(nmk[2], nmk[3])) < guard ? 1u : 0u;
+        nmk[0] = nmk[1] = nmk[2] = nmk[3] = 1.f;
       }
     }
     // The four offset columns run through ONE copy of the pair code (an unrolled copy per column is 53 KB of
@@ -530,7 +531,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
           for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int j = k; j < 4; ++j)
-              pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], eq[j], tq[j], gq[j], eps, fI[k], lf[j], aI[k], la[j], nm);
+              pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], eq[j], tq[j], gq[j], eps, fI[k], lf[j], aI[k], la[j], nmk[k]);
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             if (FWD) fQ[0][m] += __shfl_down_sync(FULL, lf[m], 1);
@@ -545,7 +546,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
           for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], eq[j], tq[j], gq[j], eps, fI[k], fQ[0][j], aI[k], aQ[0][j], nm);
+              pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], eq[j], tq[j], gq[j], eps, fI[k], fQ[0][j], aI[k], aQ[0][j], nmk[k]);
         }
         {  // rows of the lane below: offsets 4 + j - k <= 4
           ld4(eq, c + 8);
@@ -556,7 +557,7 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
           for (int k = 0; k < 4; ++k)
 #pragma unroll
             for (int j = 0; j <= k; ++j)
-              pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], eq[j], tq[j], gq[j], eps, fI[k], lf[j], aI[k], la[j], nm);
+              pair_eval<TYPE, FWD, BWD>(ei[k], ti[k], gI[k], eq[j], tq[j], gq[j], eps, fI[k], lf[j], aI[k], la[j], nmk[k]);
 #pragma unroll
           for (int m = 0; m < 4; ++m) {
             if (FWD) fQ[0][m] += __shfl_up_sync(FULL, lf[m], 1);
@@ -564,8 +565,8 @@ census_sym_kernel(const float* __restrict__ es, const float* __restrict__ ta, co
           }
         }
         if (BWD && TYPE == 3) {
-          hit |= nm < guard ? 1u << dx : 0u;
-          nm = 1.f;
+          hit |= fminf(fminf(nmk[0], nmk[1]), fminf(nmk[2], nmk[3])) < guard ? 1u << dx : 0u;
+          nmk[0] = nmk[1] = nmk[2] = nmk[3] = 1.f;
         }
       }
 #pragma unroll
