@@ -133,7 +133,7 @@ __device__ __forceinline__ void ld4(float* d, const float* p) {
 // Tile rows live at index row + 4 of a column.
 // The WHOLE warp works on the pairs of one lane (`owner`): 36 pairs (16 for dx = 0), at most two per lane, so the rescan
 // is two short iterations instead of a serial chain of 36 that the other warps of the CTA wait for at the next barrier.
-__device__ __noinline__ void flag_near_ties(const float* __restrict__ E, const float* __restrict__ T, unsigned* flags, int x, int dx,
+__device__ __forceinline__ void flag_near_ties(const float* __restrict__ E, const float* __restrict__ T, unsigned* flags, int x, int dx,
                                             int owner, int lane, float eps) {
   for (int p = lane; p < 36; p += 32) {
     const int k = p / 9, dy = p % 9 - R9;
