@@ -43,11 +43,16 @@ namespace ctd {
 
 extern int g_force_generic;
 // ctd_set_option("census_sym", v): 0 = never (gather kernels of photometric.cu), 1 = every census entry point (tests, A/B
-// runs), 2 (default) = the forward-only call.  Measured on B200, batch 8 x 480x640 (tools/experiments/census_sym_ab.py,
-// profiles/r02_census_sym_*): forward 84 us here vs 103 us gather; census_sad backward 146 vs 128 us and fused
-// forward+backward+sums 173 vs 146 us -- with the gradient the walk is bound by instruction issue at ~57 % of the slots
-// (20 warps per SM at 96 registers, MUFU / shuffle / shared-memory traffic through one MIO queue), and the per-tile staging,
-// hand-over barriers and near-tie pass cost more than the halved MUFU count saves.
+// runs), 2 (default) = where it is the faster kernel.  Measured on B200 (tools/experiments/census_sym_ab.py,
+// profiles/r02_census_sym_ab.json), us per launch, this kernel / gather kernel:
+//                            batch 2      batch 8       batch 64
+//   forward                  40 / 33      82 / 103      585 / 680
+//   census_mse backward      50 / 36     103 / 113      743 / 827
+//   census_mse fused + sums  61 / 43     127 / 133      922 / 973
+//   census_sad backward      55 / 40     119 / 128      816 / 931
+//   census_sad fused + sums  69 / 48     152 / 146     1030 / 1066
+// A tile holds an SM slot for ~50 us, so a call needs about two waves of tiles (2 x 296) before the halved MUFU count
+// pays; the fused census_sad call (one more ALU instruction per pair and the near-tie pass) only wins on large batches.
 int g_census_sym = 2;
 int g_census_sym_noguard = 0;  // experiments only: never take the near-tie path (wrong signs at near-ties)
 int g_census_sym_dbg = 0;  // experiments only (wrong results): 1 = no global loads in the staging, 2 = no stores in the write-out, 4 = no band CTAs, 8 = no masked sums
@@ -57,6 +62,8 @@ namespace {
 
 constexpr int R9 = 4;
 constexpr float INV81 = 1.0f / 81.0f;
+constexpr int64_t CS_MIN_PIXELS = 1800000;             // automatic dispatch: about six 480x640 images (two waves of tiles)
+constexpr int64_t CS_MIN_PIXELS_SAD_FUSED = 7500000;   // ... the fused census_sad call: about 24 images
 // |error| of dd on the MUFU path: two rsqrt.approx (2^-22 relative each on a product of magnitude <= 1) and three
 // roundings -- below 8e-7; 2e-6 leaves a factor of two
 constexpr float SIGN_GUARD = 2e-6f;
@@ -718,7 +725,11 @@ static bool launch_variant(const float* es, const float* ta, const float* go, fl
 // sums2 = (sum(mask * out), sum(mask)).  Returns false when this path does not take the call (nothing launched).
 bool census_sym_launch(const float* es, const float* ta, const float* go, float* out, float* gi, const float* mask, float* sums2,
                        int64_t B, int64_t C, int64_t H, int64_t W, int type, float eps, cudaStream_t st) {
-  if (!g_census_sym || (g_census_sym == 2 && gi != nullptr) || g_force_generic || C != 1 || B < 1 || H < 16 || W < 16 || H * W >= (int64_t)1 << 30 || (type != 2 && type != 3)) return false;
+  if (g_census_sym == 2) {
+    const int64_t px = B * H * W;
+    if (px < CS_MIN_PIXELS || (type == 3 && out != nullptr && gi != nullptr && px < CS_MIN_PIXELS_SAD_FUSED)) return false;
+  }
+  if (!g_census_sym || g_force_generic || C != 1 || B < 1 || H < 16 || W < 16 || H * W >= (int64_t)1 << 30 || (type != 2 && type != 3)) return false;
   if (!out && !gi) return false;
   if (gi && !go) return false;
   if (mask && (!out || !sums2)) return false;
