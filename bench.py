@@ -258,6 +258,8 @@ def run_b200_arm(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
+    if args.census_sym >= 0:
+        _lib.set_option("census_sym", args.census_sym)
     strong = args.global_batch > 0   # the MAIN figure as strong scaling (a fixed global batch split over the ranks)
     if strong:
         lo, hi = shard_range(args.global_batch, rank, world)
@@ -754,6 +756,7 @@ def main():
                     help="the two losses as parallel graph branches behind LCN (1: sad on the side stream, 2: census; 0: one chain)")
     ap.add_argument("--global-batch", type=int, default=0,
                     help="run the MAIN figure as strong scaling: split this many images over the ranks instead of 8 per GPU")
+    ap.add_argument("--census-sym", type=int, default=-1, help="A/B runs: ctd_set_option('census_sym', v) before the benchmark (0 gather kernels, 1 pair-symmetric kernel everywhere, 2 automatic = library default)")
     ap.add_argument("--no-strong", action="store_true", help="skip the `strong` block (BASELINE configs[4]: global batch 64 over the ranks)")
     ap.add_argument("--no-extra", action="store_true", help="skip the extra op timings (XCorrVol, ProjNN, ...) and the reference CUDA extension leg")
     args = ap.parse_args()
