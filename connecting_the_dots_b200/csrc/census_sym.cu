@@ -63,7 +63,6 @@ namespace {
 constexpr int R9 = 4;
 constexpr float INV81 = 1.0f / 81.0f;
 constexpr int64_t CS_MIN_PIXELS = 1800000;             // automatic dispatch: about six 480x640 images (two waves of tiles)
-constexpr int64_t CS_MIN_PIXELS_SAD_FUSED = 7500000;   // ... the fused census_sad call: about 24 images
 // |error| of dd on the MUFU path: two rsqrt.approx (2^-22 relative each on a product of magnitude <= 1) and three
 // roundings -- below 8e-7; 2e-6 leaves a factor of two
 constexpr float SIGN_GUARD = 2e-6f;
@@ -727,7 +726,8 @@ bool census_sym_launch(const float* es, const float* ta, const float* go, float*
                        int64_t B, int64_t C, int64_t H, int64_t W, int type, float eps, cudaStream_t st) {
   if (g_census_sym == 2) {
     const int64_t px = B * H * W;
-    if (px < CS_MIN_PIXELS || (type == 3 && out != nullptr && gi != nullptr && px < CS_MIN_PIXELS_SAD_FUSED)) return false;
+    // forward + backward in one call: the tile kernel with packed fp32 taps wins at every size measured (r02_census_stream_ab.json)
+    if (px < CS_MIN_PIXELS || (out != nullptr && gi != nullptr)) return false;
   }
   if (!g_census_sym || g_force_generic || C != 1 || B < 1 || H < 16 || W < 16 || H * W >= (int64_t)1 << 30 || (type != 2 && type != 3)) return false;
   if (!out && !gi) return false;

@@ -15,6 +15,7 @@ int g_xcorr_nofix = 0;    // experiments: skip XCorrVol's fix-up pass (fast-path
 int g_host_chunks = 4;     // host-buffer API: image chunks per call (copies below ~2 MB lose PCIe efficiency)
 extern int g_census_pairs;
 extern int g_census_sym;
+extern int g_census_stream;
 extern int g_xcorr_serial;
 extern int g_proj_nn_tile;
 extern int g_census_sym_noguard;
@@ -211,6 +212,10 @@ CTD_API int ctd_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "census_pairs")) {
     ctd::g_census_pairs = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "census_stream")) {
+    ctd::g_census_stream = value;
     return CTD_OK;
   }
   if (name && !strcmp(name, "census_sym")) {

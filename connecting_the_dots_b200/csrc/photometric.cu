@@ -36,6 +36,19 @@ int census_pairs_fwd(const float* es, const float* ta, float* out, int64_t B, in
 // census_sym.cu: every pixel pair evaluated once (forward, backward or both, optional masked sums); false = not taken
 bool census_sym_launch(const float* es, const float* ta, const float* go, float* out, float* gi, const float* mask, float* sums2,
                        int64_t B, int64_t C, int64_t H, int64_t W, int type, float eps, cudaStream_t st);
+// census_stream.cu: persistent CTAs, tiles through a cp.async ring, packed fp32 taps (calls with a backward); false = not taken
+bool census_stream_launch(const float* es, const float* ta, const float* go, float* out, float* gi, const float* mask, float* sums2,
+                          int64_t B, int64_t C, int64_t H, int64_t W, int type, float eps, cudaStream_t st);
+extern int g_census_sym;
+// The census kernels that take whole calls: the pair-symmetric one by its own size rule (forward-only and backward-only
+// calls from ~6 images, or when forced by option), the streaming one when switched on (census_stream.cu: measured equal to the
+// tile kernels below, which take whatever is left).
+static bool census_fast_launch(const float* es, const float* ta, const float* go, float* out, float* gi, const float* mask,
+                               float* sums2, int64_t B, int64_t C, int64_t H, int64_t W, int type, float eps, cudaStream_t st) {
+  if (g_census_sym == 1 && census_sym_launch(es, ta, go, out, gi, mask, sums2, B, C, H, W, type, eps, st)) return true;
+  if (gi && census_stream_launch(es, ta, go, out, gi, mask, sums2, B, C, H, W, type, eps, st)) return true;
+  return census_sym_launch(es, ta, go, out, gi, mask, sums2, B, C, H, W, type, eps, st);
+}
 
 // ------------------------------------------------------------------------------------------
 // generic kernels (any block size, channel count, size; float or double)
@@ -675,6 +688,101 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
       if (gy == 0) { by = 5.f; sy = -1.f; }
       if (gy == H - 1) { by = 5.f; sy = 1.f; }
     }
+    if constexpr (NPX == 2) {
+      // Two taps per instruction: Blackwell's packed fp32 pipe instructions (FADD2 / FMUL2 / FFMA2 on aligned register
+      // pairs) halve the issue slots of everything around the reciprocal square roots, which is what this loop is
+      // short of (80 % of the issue slots against 66 % of the XU pipe with scalar code).  A row's ten staged values
+      // arrive as five aligned pairs; pixel 0 takes (0,1) .. (6,7) as tap pairs and column 8 alone, pixel 1 takes
+      // (2,3) .. (8,9) and column 1 alone.  acc2 / fac2 hold the even- and odd-tap partial sums.
+      float2 acc2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      float2 fac2[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+      const float2 eps2 = make_float2(eps, eps);
+#pragma unroll 1
+      for (int dy = 0; dy < 9; ++dy) {
+        float2 e2[5], t2[5], g2[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+          e2[q] = reinterpret_cast<const float2*>(&Es[yl + dy][2 * tx])[q];
+          t2[q] = reinterpret_cast<const float2*>(&Ts[yl + dy][2 * tx])[q];
+          g2[q] = reinterpret_cast<const float2*>(&Gs[yl + dy][2 * tx])[q];
+        }
+        const float my = BORDER ? fmaf(sy, float(dy - R9), by) : 1.f;
+        const bool ctr_row = dy == R9 || (BORDER && ((sy < 0.f && dy < R9) || (sy > 0.f && dy > R9)));
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const float2 ec2 = make_float2(ec[k], ec[k]), tc2 = make_float2(tc[k], tc[k]), gc2 = make_float2(gc[k], gc[k]);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int dx = 2 * q + k;  // the pair's first tap; staged columns k + dx = 2 (q + k), + 1
+            const float2 ev = e2[q + k], tv = t2[q + k];
+            const float2 des = __fadd2_rn(ec2, make_float2(-ev.x, -ev.y));
+            const float2 nta = __fadd2_rn(tv, make_float2(-tc2.x, -tc2.y));  // -(tc - t)
+            const float2 s1 = __ffma2_rn(des, des, eps2), s2 = __ffma2_rn(nta, nta, eps2);
+            const float2 r1 = make_float2(rsqrt_approx(s1.x), rsqrt_approx(s1.y));
+            const float2 r2 = make_float2(rsqrt_approx(s2.x), rsqrt_approx(s2.y));
+            const float2 dd = __ffma2_rn(des, r1, __fmul2_rn(nta, r2));
+            const float2 r3 = __fmul2_rn(__fmul2_rn(r1, r1), r1);
+            float2 gq = g2[q + k];
+            if (BORDER) {
+              const float2 wx = __ffma2_rn(make_float2(sx[k], sx[k]), make_float2(float(dx - R9), float(dx + 1 - R9)), make_float2(bx[k], bx[k]));
+              gq = __fmul2_rn(gq, __fmul2_rn(wx, make_float2(my, my)));
+            }
+            const float2 gs = __fadd2_rn(gq, gc2);
+            if (FUSE) {
+              if (TYPE == 2) fac2[k] = __ffma2_rn(dd, dd, fac2[k]);
+              else fac2[k] = __fadd2_rn(fac2[k], make_float2(fabsf(dd.x), fabsf(dd.y)));
+            }
+            if (TYPE == 2) {
+              acc2[k] = __ffma2_rn(__fmul2_rn(dd, r3), gs, acc2[k]);
+            } else {
+              const float2 sr3 = make_float2(__uint_as_float(__float_as_uint(r3.x) | (__float_as_uint(dd.x) & 0x80000000u)),
+                                             __uint_as_float(__float_as_uint(r3.y) | (__float_as_uint(dd.y) & 0x80000000u)));
+              acc2[k] = __ffma2_rn(sr3, gs, acc2[k]);
+              float m0 = fabsf(dd.x), m1 = fabsf(dd.y);
+              if (dx == R9 || BORDER) {
+                const bool cc = dx == R9 || (BORDER && (dx < R9 ? sx[k] < 0.f : sx[k] > 0.f));
+                m0 = (ctr_row && cc) ? 1.f : m0;
+              }
+              if (dx + 1 == R9 || BORDER) {
+                const bool cc = dx + 1 == R9 || (BORDER && (dx + 1 < R9 ? sx[k] < 0.f : sx[k] > 0.f));
+                m1 = (ctr_row && cc) ? 1.f : m1;
+              }
+              near0[k] = fminf(near0[k], fminf(m0, m1));
+            }
+          }
+          {  // the ninth tap: staged column 8 for pixel 0 (dx = 8), staged column 1 for pixel 1 (dx = 0)
+            const int dx = k == 0 ? 8 : 0;
+            const float ev = k == 0 ? e2[4].x : e2[0].y, tv = k == 0 ? t2[4].x : t2[0].y;
+            const float des = ec[k] - ev;
+            const float dta = tc[k] - tv;
+            const float r1 = rsqrt_approx(fmaf(des, des, eps));
+            const float r2 = rsqrt_approx(fmaf(dta, dta, eps));
+            const float dd = fmaf(des, r1, -(dta * r2));
+            const float r3 = r1 * r1 * r1;
+            float gq = k == 0 ? g2[4].x : g2[0].y;
+            if (BORDER) gq *= my * fmaf(sx[k], float(dx - R9), bx[k]);
+            if (FUSE) {
+              if (TYPE == 2) fac2[k].x = fmaf(dd, dd, fac2[k].x);
+              else fac2[k].x += fabsf(dd);
+            }
+            if (TYPE == 2) {
+              acc2[k].x = fmaf(dd * r3, gq + gc[k], acc2[k].x);
+            } else {
+              const float sr3 = __uint_as_float(__float_as_uint(r3) | (__float_as_uint(dd) & 0x80000000u));
+              acc2[k].x = fmaf(sr3, gq + gc[k], acc2[k].x);
+              float mag = fabsf(dd);
+              if (BORDER) mag = (ctr_row && (dx < R9 ? sx[k] < 0.f : sx[k] > 0.f)) ? 1.f : mag;
+              near0[k] = fminf(near0[k], mag);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        acc[k] = acc2[k].x + acc2[k].y;
+        if (FUSE) facc[half][k] += fac2[k].x + fac2[k].y;
+      }
+    } else {
 #pragma unroll 1
     for (int dy = 0; dy < 9; ++dy) {
       float e[NPX + 8], t[NPX + 8], g[NPX + 8];
@@ -717,6 +825,7 @@ __device__ __forceinline__ void census_bwd_tile(float (*Es)[CE_W], float (*Ts)[C
           }
         }
       }
+    }
     }
     if (TYPE == 3) {
       // self taps: the centre (counted with M(i,i) = bx*by as a tap of itself, plus once as the centre) and, at
@@ -988,7 +1097,7 @@ CTD_API int ctd_photometric_bwd_f32(const float* es, const float* ta, const floa
   if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
   CTD_REQUIRE(go, "photometric_bwd: null grad_out");
   if (type <= 1 && box9_tma_bwd(es, ta, go, gi, B, C, H, W, type, st)) return check_launch("photometric_bwd(tma)");
-  if (type >= 2 && es && ta && gi && census_sym_launch(es, ta, go, nullptr, gi, nullptr, nullptr, B, C, H, W, type, eps, st))
+  if (type >= 2 && es && ta && gi && census_fast_launch(es, ta, go, nullptr, gi, nullptr, nullptr, B, C, H, W, type, eps, st))
     return check_launch("photometric_bwd(census, pair-symmetric)");
   const int vec = vec_ok(W, es, ta, go, gi);
   for (int64_t b0 = 0; b0 < B; b0 += 32768) {
@@ -1020,8 +1129,8 @@ CTD_API int ctd_photometric_fwd_bwd_f32(const float* es, const float* ta, const 
   if (type >= 2 && type <= 3 && fast9_ok(bs, H, W) && C >= 1 && B >= 1) {
     if (int rc = check_common(es, ta, gi, B, C, H, W, bs, type)) return rc;
     CTD_REQUIRE(go && out, "photometric_fwd_bwd: null pointer");
-    if (es && ta && gi && census_sym_launch(es, ta, go, out, gi, nullptr, nullptr, B, C, H, W, type, eps, st))
-      return check_launch("photometric_fwd_bwd(census, pair-symmetric)");
+    if (es && ta && gi && census_fast_launch(es, ta, go, out, gi, nullptr, nullptr, B, C, H, W, type, eps, st))
+      return check_launch("photometric_fwd_bwd(census, whole-call kernel)");
     const int vec = vec_ok(W, es, ta, go, gi) && (reinterpret_cast<uintptr_t>(out) & 15) == 0;
     for (int64_t b0 = 0; b0 < B; b0 += 32768) {
       const int nb = (int)std::min<int64_t>(32768, B - b0);
@@ -1053,8 +1162,8 @@ CTD_API int ctd_photometric_fwd_bwd_masked_f32(const float* es, const float* ta,
   if (fast9_ok(bs, H, W) && C >= 1 && B >= 1 && B <= 32768) {
     if (type <= 1 && box9_tma_fwd_bwd_masked(es, ta, go, mask, out, gi, sums2, B, C, H, W, type, st))
       return check_launch("photometric_fwd_bwd_masked(box, fused)");
-    if (type >= 2 && es && ta && gi && census_sym_launch(es, ta, go, out, gi, mask, sums2, B, C, H, W, type, eps, st))
-      return check_launch("photometric_fwd_bwd_masked(census, pair-symmetric)");
+    if (type >= 2 && es && ta && gi && census_fast_launch(es, ta, go, out, gi, mask, sums2, B, C, H, W, type, eps, st))
+      return check_launch("photometric_fwd_bwd_masked(census, whole-call kernel)");
     if (type >= 2) {
       const int vec = vec_ok(W, es, ta, go, gi) && ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
       if (census_bwd_launch(es, ta, go, gi, out, (int)B, C, H, W, type, eps, vec, st, mask, sums2)) {

@@ -234,6 +234,73 @@ def test_census_pair_symmetric_kernel_exact_sign_decisions(tx):
             _lib.set_option("census_sym", 2)
 
 
+STREAM_SHAPES = [(1, 9, 12), (2, 16, 64), (1, 10, 72), (3, 21, 132), (1, 130, 200), (2, 61, 300), (1, 250, 48), (5, 40, 68)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", STREAM_SHAPES)
+@pytest.mark.parametrize("ty", (2, 3))
+def test_census_streaming_kernel_vs_oracle(tx, shape, ty):
+    """census_stream.cu (persistent CTAs, cp.async tile ring, packed fp32 taps, deferred second pass for border / near-tie pixels)
+    through the three entry points with a backward, against the oracle: images smaller than a tile, ragged last tile
+    column (width a multiple of 4 but not of 64) and last tile row (height not a multiple of 8), more tiles than one CTA
+    round, every pixel of the smallest image ON the border."""
+    B, H, W = shape
+    rng = np.random.RandomState(H * 1000 + W + ty)
+    es = rng.randn(B, 1, H, W).astype(np.float32)
+    ta = (es + 0.6 * rng.randn(B, 1, H, W)).astype(np.float32)
+    go = rng.randn(B, 1, H, W).astype(np.float32)
+    mask = (rng.rand(B, 1, H, W) + 0.5).astype(np.float32)
+    from connecting_the_dots_b200 import _lib
+    _lib.set_option("census_sym", 0)
+    _lib.set_option("census_stream", 1)   # opt-in kernel
+    try:
+        n0 = _lib.launch_count()
+        r = _census_all_entry_points(tx, es, ta, go, mask, ty)
+        assert _lib.launch_count() - n0 == 4, "one kernel per entry point"
+        _lib.set_option("census_stream", 0)   # A/B partner: the tile kernel of photometric.cu (the default)
+        tile = _census_all_entry_points(tx, es, ta, go, mask, ty)
+    finally:
+        _lib.set_option("census_stream", 0)
+        _lib.set_option("census_sym", 2)
+    of, ob = oracle.photometric_loss_forward(es, ta, 9, ty, 0.5), oracle.photometric_loss_backward(es, ta, go, 9, ty, 0.5)
+    for k in ("f_fwd", "m_fwd"):
+        assert_close(r[k], of, what=k)
+    for k in ("bwd", "f_bwd", "m_bwd"):
+        assert_close(r[k], ob, what=k)
+        assert_close(r[k], tile[k], what=k + " vs tile kernel")
+    want = np.array([(mask.astype(np.float64) * of).sum(), mask.astype(np.float64).sum()])
+    assert np.abs(r["sums"] - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.gpu
+def test_census_streaming_kernel_exact_sign_decisions_and_determinism(tx):
+    """Quantised images (many window terms exactly zero or equal up to rounding), a constant image (EVERY pixel goes
+    through the in-warp correction) and the bench frames, whose flat regions tie exactly: census_sad's sign() decisions
+    have to be the reference's, and two runs have to agree bit for bit."""
+    from connecting_the_dots_b200 import _lib, synth
+    rng = np.random.RandomState(11)
+    B, H, W = 2, 70, 120
+    es = rng.randint(0, 3, (B, 1, H, W)).astype(np.float32)
+    ta = rng.randint(0, 3, (B, 1, H, W)).astype(np.float32)
+    go = rng.rand(B, 1, H, W).astype(np.float32)
+    d = synth.make_batch(1, 96, 128)
+    cases = [(es, ta, go), (es, es.copy(), go), (np.full_like(es, 0.25), np.full_like(es, 0.75), go), (d["es"], d["ta"], d["go"])]
+    _lib.set_option("census_sym", 0)
+    _lib.set_option("census_stream", 1)
+    try:
+        for e, t, g in cases:
+            fwd, bwd = photometric_both(tx, e, t, g, 9, 3, 0.5)
+            _, again = photometric_both(tx, e, t, g, 9, 3, 0.5)
+            assert np.array_equal(bwd, again)
+            ob = oracle.photometric_loss_backward(e, t, g, 9, 3, 0.5)
+            scale = max(float(np.abs(ob).max()), 1e-30)
+            assert float(np.abs(bwd - ob).max()) <= 1e-5 * scale + 1e-12, "quantised bwd"
+    finally:
+        _lib.set_option("census_stream", 0)
+        _lib.set_option("census_sym", 2)
+
+
 @pytest.mark.parametrize("shape", [(2, 1, 40, 72), (1, 2, 33, 50), (1, 1, 96, 160), (1, 1, 7, 9)])
 @pytest.mark.parametrize("ty", range(4))
 def test_photometric_fused_forward_backward(tx, shape, ty):

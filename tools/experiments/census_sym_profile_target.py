@@ -12,8 +12,8 @@ d = {k: torch.from_numpy(np.ascontiguousarray(base[k])).to(dev) for k in ("es", 
 o1, o2, sums = torch.empty(B, 1, H, W, device=dev), torch.empty(B, 1, H, W, device=dev), torch.zeros(2, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 _lib.set_option("census_sym", 1)
-if len(sys.argv) > 3:
-    _lib.set_option(sys.argv[3], 1)
+for a in sys.argv[3:]:  # option or option=value (e.g. census_sym=0: the gather kernel)
+    _lib.set_option(a.split("=")[0], int(a.split("=")[1]) if "=" in a else 1)
 for _ in range(3):
     _lib.call("ctd_photometric_fwd_bwd_masked_f32", d["es"].data_ptr(), d["ta"].data_ptr(), d["go"].data_ptr(), d["std"].data_ptr(),
               o1.data_ptr(), o2.data_ptr(), sums.data_ptr(), B, 1, H, W, 9, ty, 0.5, st)
