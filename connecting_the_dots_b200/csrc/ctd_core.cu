@@ -12,6 +12,9 @@ int g_force_generic = 0;  // tests: route every op through its generic kernel
 int g_xcorr_direct = 0;   // tests / A-B runs: XCorrVol through the direct (centred two-pass) tile kernel
 int g_xcorr_hitcap = -1;  // tests: size of XCorrVol's fix-up hit list (0 forces the overflow path), -1 = automatic
 int g_xcorr_nofix = 0;    // experiments: skip XCorrVol's fix-up pass (fast-path error measurements)
+int g_host_graphs = 1;        // host-buffer API: capture repeated batches into CUDA graphs and replay them
+int g_host_chunks_graph = 4;  // image chunks per call in a batch that is captured (replay has no per-chunk host cost)
+int g_host_chunks_batch = 2;  // ... inside ctd_host_begin_batch / end_batch, where neighbouring calls already overlap
 int g_host_chunks = 4;     // host-buffer API: image chunks per call (copies below ~2 MB lose PCIe efficiency)
 extern int g_census_pairs;
 extern int g_census_sym;
@@ -204,6 +207,18 @@ CTD_API int ctd_set_option(const char* name, int value) {
   }
   if (name && !strcmp(name, "xcorr_hitcap")) {
     ctd::g_xcorr_hitcap = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "host_graphs")) {
+    ctd::g_host_graphs = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "host_chunks_graph")) {
+    ctd::g_host_chunks_graph = value;
+    return CTD_OK;
+  }
+  if (name && !strcmp(name, "host_chunks_batch")) {
+    ctd::g_host_chunks_batch = value;
     return CTD_OK;
   }
   if (name && !strcmp(name, "host_chunks")) {

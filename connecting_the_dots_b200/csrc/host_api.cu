@@ -9,16 +9,25 @@
 // Between ctd_host_begin_batch() and ctd_host_end_batch() the calls only enqueue: consecutive ops then overlap as well
 // (the upload of the next call runs under the download of the previous one), results are in host memory when
 // ctd_host_end_batch() returns.
+// A batch that repeats -- the same calls with the same arguments and host buffers, which is what a training loop over
+// fixed pinned buffers issues every step -- is captured into a CUDA graph the second time it is seen and replayed from
+// the third on: its ~60 copy / launch / event calls (0.3 ms of host time per step, more than the kernels) become one
+// cudaGraphLaunch, and the chunk pipeline can be cut finer than host launch overhead would allow.  See submit() below.
 // There is no CPU compute path: without a CUDA device these calls fail with CTD_ERR_CUDA.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
+#include <string>
 #include <vector>
 
 #include "ctd_common.cuh"
 
 namespace ctd {
+
+constexpr int CTD_RETRY_EAGER = -1000;  // internal: the call cannot be captured, issue the batch the ordinary way
 
 static std::atomic<bool> g_process_exiting{false};
 static void mark_exiting() { g_process_exiting.store(true, std::memory_order_relaxed); }
@@ -56,6 +65,101 @@ struct Workspace {
   std::vector<Upload> pending;
   uint64_t h2d_bytes = 0, h2d_saved = 0;  // statistics since ctd_host_begin_batch (ctd_host_batch_stats)
 
+  // ---- repeated batches as CUDA graphs ------------------------------------------------------------------------------
+  // Every call of an open batch has a signature (entry point + every argument, pointers by value).  A finished batch
+  // leaves its signature list in a small cache.  When the first call of a later batch matches a cached list, the batch
+  // is EXPECTED to repeat it:
+  //   * no graph yet (seen once): the calls run under stream capture -- same code path, the three streams forked from and
+  //     joined back into the compute stream -- and ctd_host_end_batch instantiates, keeps and launches the graph;
+  //   * graph cached: the calls only check their signature and return; ctd_host_end_batch launches the graph.
+  // A call that breaks the expectation (different signature, fewer / more calls, a host buffer that is not pinned, a
+  // workspace that would have to grow, an input overlapping an output in flight) ends it: the capture is dropped, the
+  // calls recorded so far are issued the ordinary way, and the batch carries on as before.  Graphs hold workspace
+  // addresses: they go when the workspace is reallocated or released.  Contract as before: host inputs must not change
+  // while the batch is open (a replayed batch reads them at ctd_host_end_batch), and buffers of a replayed batch must
+  // still be the pinned allocations they were.
+  enum Mode { EAGER, CAPTURE, REPLAY };
+  struct Call {
+    std::string sig;
+    std::function<int()> run;
+  };
+  struct Cached {
+    std::vector<std::string> sigs;
+    cudaGraphExec_t exec = nullptr;
+    bool no_graph = false;  // broke a capture once: always issued the ordinary way
+    uint64_t h2d = 0, saved = 0, stamp = 0;
+  };
+  static constexpr int MAX_CACHED = 8;
+  Mode mode = EAGER;
+  bool capturing = false;
+  int cand = -1;
+  uint64_t clock = 0;
+  std::vector<Call> calls;
+  std::vector<Cached> cache;
+
+  void drop_graphs() {
+    for (Cached& c : cache)
+      if (c.exec) cudaGraphExecDestroy(c.exec);
+    cache.clear();
+    cand = -1;
+  }
+  int begin_capture() {
+    CTD_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    capturing = true;
+    CTD_CUDA(cudaEventRecord(ev_in[0], stream));  // fork: the copy streams join the capture
+    CTD_CUDA(cudaStreamWaitEvent(s_in, ev_in[0], 0));
+    CTD_CUDA(cudaStreamWaitEvent(s_out, ev_in[0], 0));
+    return CTD_OK;
+  }
+  // join the copy streams and end the capture; *graph = nullptr when the capture was invalidated
+  int end_capture(cudaGraph_t* graph) {
+    *graph = nullptr;
+    capturing = false;
+    cudaEventRecord(ev_in[0], s_in);
+    cudaStreamWaitEvent(stream, ev_in[0], 0);
+    cudaEventRecord(ev_run[0], s_out);
+    cudaStreamWaitEvent(stream, ev_run[0], 0);
+    if (cudaStreamEndCapture(stream, graph) != cudaSuccess) {
+      cudaGetLastError();
+      *graph = nullptr;
+    }
+    return CTD_OK;
+  }
+  // the expectation failed: issue what has been recorded the ordinary way and carry on in EAGER mode
+  int bail(bool never_again) {
+    if (capturing) {
+      cudaGraph_t g = nullptr;
+      end_capture(&g);
+      if (g) cudaGraphDestroy(g);
+    }
+    if (never_again && cand >= 0 && cand < (int)cache.size()) cache[cand].no_graph = true;
+    mode = EAGER;
+    cand = -1;
+    used = 0;
+    uploads.clear();
+    pending.clear();
+    h2d_bytes = h2d_saved = 0;
+    for (Call& c : calls) {
+      if (int rc = c.run()) return rc;
+      c.run = nullptr;
+    }
+    return CTD_OK;
+  }
+  static bool pinned(const std::vector<const void*>& ptrs) {
+    for (const void* p : ptrs) {
+      if (!p) continue;
+      cudaPointerAttributes a;
+      if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+      }
+      if (a.type != cudaMemoryTypeHost) return false;
+    }
+    return true;
+  }
+  int submit(std::string sig, const std::vector<const void*>& host_ptrs, std::function<int()> run);
+  int end_batch();
+
   void note_download(const void* host, size_t bytes, char* dev) {
     if (deferred && bytes) pending.push_back({host, bytes, dev});
   }
@@ -77,6 +181,7 @@ struct Workspace {
         overlap = overlap || (h0 < p0 + u.bytes && p0 < h0 + bytes);
       }
       if (overlap) {  // partial overlap with an output in flight: let the downloads finish, then the host copy is current
+        if (capturing) return CTD_RETRY_EAGER;
         CTD_CUDA(cudaStreamSynchronize(s_out));
         CTD_CUDA(cudaStreamSynchronize(stream));
         pending.clear();
@@ -119,6 +224,7 @@ struct Workspace {
       device = dev;
     }
     if (!stream) {
+      if (capturing) return CTD_RETRY_EAGER;
       register_exit_hook();
       CTD_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
       CTD_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
@@ -129,6 +235,8 @@ struct Workspace {
       }
     }
     if (bytes > cap) {
+      if (capturing) return CTD_RETRY_EAGER;  // cudaMalloc / cudaDeviceSynchronize cannot be captured
+      drop_graphs();                          // they hold addresses of the old workspace
       if (base) {
         CTD_CUDA(cudaDeviceSynchronize());  // also completes every call still in flight: their results are out
         cudaFree(base);
@@ -148,6 +256,7 @@ struct Workspace {
     return CTD_OK;
   }
   void release() {
+    drop_graphs();
     if (stream) {
       cudaStreamSynchronize(stream);
       cudaStreamSynchronize(s_in);
@@ -185,6 +294,140 @@ struct Workspace {
 
 static thread_local Workspace g_ws;
 
+extern int g_host_graphs;  // ctd_set_option("host_graphs", 0): never capture / replay batches
+
+// Signature of one call: entry point + arguments (pointers by value); the host pointers are also kept for the
+// pinned-memory check in front of a capture.
+struct Sig {
+  std::string bytes;
+  std::vector<const void*> host;
+  explicit Sig(int op) { put(op); }
+  template <typename T>
+  Sig& put(T v) {
+    bytes.append(reinterpret_cast<const char*>(&v), sizeof(T));
+    return *this;
+  }
+  Sig& ptr(const void* p) {
+    host.push_back(p);
+    return put(p);
+  }
+};
+
+int Workspace::submit(std::string sig, const std::vector<const void*>& host_ptrs, std::function<int()> run) {
+  if (!deferred || !g_host_graphs) return run();
+  const size_t i = calls.size();
+  if (i == 0) {  // which cached batch does this one start like?
+    cand = -1;
+    for (int k = 0; k < (int)cache.size(); ++k)
+      if (!cache[k].sigs.empty() && cache[k].sigs[0] == sig && (cand < 0 || cache[k].stamp > cache[cand].stamp)) cand = k;
+    mode = EAGER;
+    if (cand >= 0 && !cache[cand].no_graph && stream) {
+      if (cache[cand].exec) {
+        mode = REPLAY;
+      } else {
+        if (int rc = begin_capture()) {
+          capturing = false;
+          return rc;
+        }
+        mode = CAPTURE;
+      }
+    }
+  }
+  if (mode != EAGER) {
+    const Cached& c = cache[cand];
+    bool ok = i < c.sigs.size() && c.sigs[i] == sig;
+    bool never_again = false;
+    if (ok && mode == CAPTURE && !pinned(host_ptrs)) {
+      ok = false;
+      never_again = true;  // pageable buffers: copies are staged by the driver, nothing to gain and not capturable
+    }
+    if (ok) {
+      calls.push_back({sig, run});
+      if (mode == REPLAY) return CTD_OK;
+      const int rc = run();  // under capture
+      if (rc == CTD_OK) return rc;
+      calls.pop_back();
+      if (rc != CTD_RETRY_EAGER) {  // a real error: the batch is over for the graph, the caller sees the status
+        bail(true);
+        return rc;
+      }
+      never_again = true;
+    }
+    if (int rc = bail(never_again)) return rc;
+  }
+  calls.push_back({std::move(sig), nullptr});
+  return run();
+}
+
+int Workspace::end_batch() {
+  int rc = CTD_OK;
+  bool launched = false;
+  static const bool dbg = getenv("CTD_HOST_DEBUG") != nullptr;
+  if (dbg) fprintf(stderr, "ctd_host_end_batch: %zu calls, mode %s, candidate %d of %zu cached\n", calls.size(),
+                   mode == EAGER ? "eager" : (mode == CAPTURE ? "capture" : "replay"), cand, cache.size());
+  if (mode != EAGER && calls.size() != cache[cand].sigs.size()) rc = bail(false);  // fewer calls than expected
+  if (rc == CTD_OK && mode == CAPTURE) {
+    cudaGraph_t g = nullptr;
+    end_capture(&g);
+    Cached& c = cache[cand];
+    if (g && cudaGraphInstantiate(&c.exec, g, 0) == cudaSuccess) {
+      c.h2d = h2d_bytes;
+      c.saved = h2d_saved;
+      mode = REPLAY;
+    } else {
+      cudaGetLastError();
+      c.exec = nullptr;
+      rc = bail(true);
+    }
+    if (g) cudaGraphDestroy(g);
+  }
+  if (rc == CTD_OK && mode == REPLAY) {
+    Cached& c = cache[cand];
+    h2d_bytes = c.h2d;
+    h2d_saved = c.saved;
+    c.stamp = ++clock;
+    cudaError_t e = cudaGraphLaunch(c.exec, stream);
+    if (e != cudaSuccess) rc = fail(CTD_ERR_CUDA, "ctd_host_end_batch: graph launch: %s", cudaGetErrorString(e));
+    launched = true;
+  }
+  if (rc == CTD_OK && !launched && g_host_graphs && !calls.empty()) {  // an ordinary batch: remember what it looked like
+    int slot = -1;
+    for (int k = 0; k < (int)cache.size() && slot < 0; ++k) {
+      if (cache[k].sigs.size() != calls.size()) continue;
+      bool same = true;
+      for (size_t j = 0; j < calls.size() && same; ++j) same = cache[k].sigs[j] == calls[j].sig;
+      if (same) slot = k;
+    }
+    if (slot < 0) {
+      if ((int)cache.size() < MAX_CACHED) {
+        cache.emplace_back();
+        slot = (int)cache.size() - 1;
+      } else {
+        slot = 0;
+        for (int k = 1; k < (int)cache.size(); ++k)
+          if (cache[k].stamp < cache[slot].stamp) slot = k;
+        if (cache[slot].exec) cudaGraphExecDestroy(cache[slot].exec);
+        cache[slot] = Cached();
+      }
+      for (const Call& c : calls) cache[slot].sigs.push_back(c.sig);
+    }
+    cache[slot].stamp = ++clock;
+  }
+  deferred = false;
+  used = 0;
+  uploads.clear();
+  pending.clear();
+  calls.clear();
+  mode = EAGER;
+  cand = -1;
+  if (stream) {
+    cudaError_t e1 = cudaStreamSynchronize(s_out), e2 = cudaStreamSynchronize(stream), e3 = cudaStreamSynchronize(s_in);
+    const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    if (e != cudaSuccess && rc == CTD_OK) rc = fail(CTD_ERR_CUDA, "ctd_host_end_batch: %s", cudaGetErrorString(e));
+  }
+  return rc;
+}
+
 // carve 256-byte aligned sub-buffers out of the workspace
 struct Carver {
   std::vector<size_t> sizes;
@@ -198,10 +441,13 @@ struct Carver {
 
 // images [i0, i1) of chunk c when B images are cut into n chunks
 static inline int64_t chunk_lo(int64_t B, int n, int c) { return B * c / n; }
+extern int g_host_chunks_batch;
 extern int g_host_chunks;  // ctd_set_option("host_chunks", n): upper bound on the pipeline depth (A/B runs)
+extern int g_host_chunks_graph;
 static inline int chunk_count(int64_t B, bool deferred) {
-  // inside a batch the neighbouring calls already overlap with this one: fewer, larger copies win (measured)
-  const int want = deferred ? std::min(g_host_chunks, 2) : g_host_chunks;
+  // inside a batch the neighbouring calls already overlap with this one: fewer, larger copies win (measured: every
+  // chunk is ~10 driver calls); in a batch that is being captured into a graph the calls cost nothing at replay
+  const int want = g_ws.capturing ? g_host_chunks_graph : (deferred ? std::min(g_host_chunks, g_host_chunks_batch) : g_host_chunks);
   return (int)std::min<int64_t>(std::max<int64_t>(B, 1), std::min(std::max(want, 1), (int)Workspace::MAX_CHUNKS));
 }
 
@@ -264,18 +510,24 @@ static int photometric_host(const float* es, const float* ta, const float* go, f
 CTD_API int ctd_host_photometric_fwd_f32(const float* es, const float* ta, float* out, int64_t B, int64_t C,
                                             int64_t H, int64_t W, int bs, int type, float eps) {
   CTD_REQUIRE(out || B * H * W == 0, "photometric_fwd: null output");
-  return photometric_host(es, ta, nullptr, out, nullptr, B, C, H, W, bs, type, eps);
+  Sig sg(1);
+  sg.ptr(es).ptr(ta).ptr(out).put(B).put(C).put(H).put(W).put(bs).put(type).put(eps);
+  return g_ws.submit(sg.bytes, sg.host, [=]() { return photometric_host(es, ta, nullptr, out, nullptr, B, C, H, W, bs, type, eps); });
 }
 CTD_API int ctd_host_photometric_bwd_f32(const float* es, const float* ta, const float* go, float* gi, int64_t B,
                                             int64_t C, int64_t H, int64_t W, int bs, int type, float eps) {
   CTD_REQUIRE(gi || B * C * H * W == 0, "photometric_bwd: null output");
-  return photometric_host(es, ta, go, nullptr, gi, B, C, H, W, bs, type, eps);
+  Sig sg(2);
+  sg.ptr(es).ptr(ta).ptr(go).ptr(gi).put(B).put(C).put(H).put(W).put(bs).put(type).put(eps);
+  return g_ws.submit(sg.bytes, sg.host, [=]() { return photometric_host(es, ta, go, nullptr, gi, B, C, H, W, bs, type, eps); });
 }
 CTD_API int ctd_host_photometric_fwd_bwd_f32(const float* es, const float* ta, const float* go, float* out,
                                                 float* gi, int64_t B, int64_t C, int64_t H, int64_t W, int bs,
                                                 int type, float eps) {
   CTD_REQUIRE((out && gi) || B * C * H * W == 0, "photometric_fwd_bwd: null output");
-  return photometric_host(es, ta, go, out, gi, B, C, H, W, bs, type, eps);
+  Sig sg(3);
+  sg.ptr(es).ptr(ta).ptr(go).ptr(out).ptr(gi).put(B).put(C).put(H).put(W).put(bs).put(type).put(eps);
+  return g_ws.submit(sg.bytes, sg.host, [=]() { return photometric_host(es, ta, go, out, gi, B, C, H, W, bs, type, eps); });
 }
 
 // The reference caller's whole use of the loss (model/networks.py:376-377): loss map, d loss / d es for
@@ -297,17 +549,9 @@ __global__ void add_pairs_kernel(const float* __restrict__ parts, int n, float* 
 }
 }  // namespace ctd
 
-CTD_API int ctd_host_photometric_fwd_bwd_masked_f32(const float* es, const float* ta, const float* go, const float* mask,
-                                                       float* out, float* gi, float* sums2, int64_t B, int64_t C, int64_t H,
-                                                       int64_t W, int bs, int type, float eps) {
-  CTD_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, "photometric: negative size");
-  CTD_REQUIRE(sums2, "photometric_fwd_bwd_masked: null sums2");
+static int photometric_masked_host(const float* es, const float* ta, const float* go, const float* mask, float* out, float* gi,
+                                   float* sums2, int64_t B, int64_t C, int64_t H, int64_t W, int bs, int type, float eps) {
   const size_t nin = (size_t)(B * C * H * W) * sizeof(float), nout = (size_t)(B * H * W) * sizeof(float);
-  if (nout == 0) {
-    sums2[0] = sums2[1] = 0.f;
-    return CTD_OK;
-  }
-  CTD_REQUIRE(es && ta && go && mask && gi, "photometric_fwd_bwd_masked: null pointer");
   const int nch = chunk_count(B, g_ws.deferred);
   Carver cv;
   const size_t o_es = cv.add(nin), o_ta = cv.add(nin), o_go = cv.add(nout), o_mk = cv.add(nout), o_out = cv.add(nout),
@@ -341,8 +585,24 @@ CTD_API int ctd_host_photometric_fwd_bwd_masked_f32(const float* es, const float
   return g_ws.finish(cv.total);
 }
 
-CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,
-                                     int64_t W, int64_t D, int bs) {
+CTD_API int ctd_host_photometric_fwd_bwd_masked_f32(const float* es, const float* ta, const float* go, const float* mask,
+                                                       float* out, float* gi, float* sums2, int64_t B, int64_t C, int64_t H,
+                                                       int64_t W, int bs, int type, float eps) {
+  CTD_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0, "photometric: negative size");
+  CTD_REQUIRE(sums2, "photometric_fwd_bwd_masked: null sums2");
+  if (B * H * W == 0) {  // host-side result, nothing to enqueue (and nothing for a replayed batch to miss)
+    sums2[0] = sums2[1] = 0.f;
+    return CTD_OK;
+  }
+  CTD_REQUIRE(es && ta && go && mask && gi, "photometric_fwd_bwd_masked: null pointer");
+  Sig sg(4);
+  sg.ptr(es).ptr(ta).ptr(go).ptr(mask).ptr(out).ptr(gi).ptr(sums2).put(B).put(C).put(H).put(W).put(bs).put(type).put(eps);
+  return g_ws.submit(sg.bytes, sg.host,
+                     [=]() { return photometric_masked_host(es, ta, go, mask, out, gi, sums2, B, C, H, W, bs, type, eps); });
+}
+
+static int xcorrvol_host(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H, int64_t W, int64_t D,
+                         int bs) {
   CTD_REQUIRE(B >= 0 && C >= 0 && H >= 0 && W >= 0 && D >= 0, "xcorrvol: negative size");
   const size_t nin = (size_t)(B * C * H * W) * sizeof(float), nout = (size_t)(B * D * H * W) * sizeof(float);
   Carver cv;
@@ -370,8 +630,15 @@ CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out
   return g_ws.finish(cv.total);
 }
 
-CTD_API int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const float* K, int64_t* out, int64_t B,
-                                    int64_t H, int64_t W, int ps) {
+CTD_API int ctd_host_xcorrvol_f32(const float* in0, const float* in1, float* out, int64_t B, int64_t C, int64_t H,
+                                     int64_t W, int64_t D, int bs) {
+  Sig sg(5);
+  sg.ptr(in0).ptr(in1).ptr(out).put(B).put(C).put(H).put(W).put(D).put(bs);
+  return g_ws.submit(sg.bytes, sg.host, [=]() { return xcorrvol_host(in0, in1, out, B, C, H, W, D, bs); });
+}
+
+static int proj_nn_host(const float* xyz0, const float* xyz1, const float* K, int64_t* out, int64_t B, int64_t H, int64_t W,
+                        int ps) {
   CTD_REQUIRE(B >= 0 && H >= 0 && W >= 0, "proj_nn: negative size");
   const size_t npt = (size_t)(B * H * W) * 3 * sizeof(float), nout = (size_t)(B * H * W) * sizeof(int64_t);
   Carver cv;
@@ -390,7 +657,14 @@ CTD_API int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const flo
   return g_ws.finish(cv.total);
 }
 
-CTD_API int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, int64_t N0, int64_t N1) {
+CTD_API int ctd_host_proj_nn_f32(const float* xyz0, const float* xyz1, const float* K, int64_t* out, int64_t B,
+                                    int64_t H, int64_t W, int ps) {
+  Sig sg(6);
+  sg.ptr(xyz0).ptr(xyz1).ptr(K).ptr(out).put(B).put(H).put(W).put(ps);
+  return g_ws.submit(sg.bytes, sg.host, [=]() { return proj_nn_host(xyz0, xyz1, K, out, B, H, W, ps); });
+}
+
+static int nn_host(const float* in0, const float* in1, int64_t* out, int64_t N0, int64_t N1) {
   CTD_REQUIRE(N0 >= 0 && N1 >= 0, "nn: negative size");
   const size_t n0 = (size_t)N0 * 3 * sizeof(float), n1 = (size_t)N1 * 3 * sizeof(float), no = (size_t)N0 * sizeof(int64_t);
   Carver cv;
@@ -411,7 +685,13 @@ CTD_API int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, in
   return g_ws.finish(cv.total);
 }
 
-CTD_API int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t N0, int64_t N1) {
+CTD_API int ctd_host_nn_f32(const float* in0, const float* in1, int64_t* out, int64_t N0, int64_t N1) {
+  Sig sg(7);
+  sg.ptr(in0).ptr(in1).ptr(out).put(N0).put(N1);
+  return g_ws.submit(sg.bytes, sg.host, [=]() { return nn_host(in0, in1, out, N0, N1); });
+}
+
+static int crosscheck_host(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t N0, int64_t N1) {
   CTD_REQUIRE(N0 >= 0 && N1 >= 0, "crosscheck: negative size");
   const size_t n0 = (size_t)N0 * sizeof(int64_t), n1 = (size_t)N1 * sizeof(int64_t), no = (size_t)N0;
   Carver cv;
@@ -432,8 +712,13 @@ CTD_API int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t*
   return g_ws.finish(cv.total);
 }
 
-CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, int64_t H, int64_t W, int r,
-                                float eps) {
+CTD_API int ctd_host_crosscheck(const int64_t* in0, const int64_t* in1, uint8_t* out, int64_t N0, int64_t N1) {
+  Sig sg(8);
+  sg.ptr(in0).ptr(in1).ptr(out).put(N0).put(N1);
+  return g_ws.submit(sg.bytes, sg.host, [=]() { return crosscheck_host(in0, in1, out, N0, N1); });
+}
+
+static int lcn_host(const float* x, float* lcn, float* sd, int64_t N, int64_t H, int64_t W, int r, float eps) {
   CTD_REQUIRE(N >= 0 && H >= 0 && W >= 0, "lcn: negative size");
   const size_t n = (size_t)(N * H * W) * sizeof(float);
   Carver cv;
@@ -460,28 +745,29 @@ CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, i
   return g_ws.finish(cv.total);
 }
 
+CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, int64_t H, int64_t W, int r,
+                                float eps) {
+  Sig sg(9);
+  sg.ptr(x).ptr(lcn).ptr(sd).put(N).put(H).put(W).put(r).put(eps);
+  return g_ws.submit(sg.bytes, sg.host, [=]() { return lcn_host(x, lcn, sd, N, H, W, r, eps); });
+}
+
 CTD_API int ctd_host_begin_batch(void) {
   CTD_REQUIRE(!g_ws.deferred, "ctd_host_begin_batch: a batch is already open on this thread");
   g_ws.deferred = true;
   g_ws.used = 0;
   g_ws.uploads.clear();
   g_ws.pending.clear();
+  g_ws.calls.clear();
+  g_ws.mode = Workspace::EAGER;
+  g_ws.cand = -1;
   g_ws.h2d_bytes = g_ws.h2d_saved = 0;
   return CTD_OK;
 }
 
 CTD_API int ctd_host_end_batch(void) {
   CTD_REQUIRE(g_ws.deferred, "ctd_host_end_batch: no batch is open on this thread");
-  g_ws.deferred = false;
-  g_ws.used = 0;
-  g_ws.uploads.clear();
-  g_ws.pending.clear();
-  if (g_ws.stream) {
-    CTD_CUDA(cudaStreamSynchronize(g_ws.s_out));
-    CTD_CUDA(cudaStreamSynchronize(g_ws.stream));
-    CTD_CUDA(cudaStreamSynchronize(g_ws.s_in));
-  }
-  return CTD_OK;
+  return g_ws.end_batch();
 }
 
 CTD_API void ctd_host_batch_stats(uint64_t* h2d_bytes, uint64_t* h2d_bytes_saved) {
@@ -490,7 +776,14 @@ CTD_API void ctd_host_batch_stats(uint64_t* h2d_bytes, uint64_t* h2d_bytes_saved
 }
 
 CTD_API void ctd_host_release(void) {
+  if (g_ws.capturing) {
+    cudaGraph_t g = nullptr;
+    g_ws.end_capture(&g);
+    if (g) cudaGraphDestroy(g);
+  }
   g_ws.deferred = false;
   g_ws.used = 0;
+  g_ws.calls.clear();
+  g_ws.mode = Workspace::EAGER;
   g_ws.release();
 }
