@@ -53,6 +53,7 @@ _RESTYPES = {
     "ctd_masked_sums_workspace_bytes": (ctypes.c_int64, []),
     "ctd_host_release": (None, []),
     "ctd_host_batch_stats": (None, [_ptr, _ptr]),
+    "ctd_host_graph_stats": (None, [_ptr, _ptr, _ptr]),
 }
 EXPORTS = sorted(list(SIGNATURES) + list(_RESTYPES))
 

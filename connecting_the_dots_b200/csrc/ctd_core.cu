@@ -12,8 +12,8 @@ int g_force_generic = 0;  // tests: route every op through its generic kernel
 int g_xcorr_direct = 0;   // tests / A-B runs: XCorrVol through the direct (centred two-pass) tile kernel
 int g_xcorr_hitcap = -1;  // tests: size of XCorrVol's fix-up hit list (0 forces the overflow path), -1 = automatic
 int g_xcorr_nofix = 0;    // experiments: skip XCorrVol's fix-up pass (fast-path error measurements)
-int g_host_graphs = 1;        // host-buffer API: capture repeated batches into CUDA graphs and replay them
-int g_host_chunks_graph = 4;  // image chunks per call in a batch that is captured (replay has no per-chunk host cost)
+int g_host_graphs = 0;        // host-buffer API: 1 = capture repeated batches into CUDA graphs and replay them (measured: same step time -- the bus bounds it -- and 0.09 -> 0.01 ms of host time in the calls)
+int g_host_chunks_graph = 2;  // image chunks per call in a batch that is captured (measured: finer chunks lose on the bus even with no host cost)
 int g_host_chunks_batch = 2;  // ... inside ctd_host_begin_batch / end_batch, where neighbouring calls already overlap
 int g_host_chunks = 4;     // host-buffer API: image chunks per call (copies below ~2 MB lose PCIe efficiency)
 extern int g_census_pairs;

@@ -9,10 +9,11 @@
 // Between ctd_host_begin_batch() and ctd_host_end_batch() the calls only enqueue: consecutive ops then overlap as well
 // (the upload of the next call runs under the download of the previous one), results are in host memory when
 // ctd_host_end_batch() returns.
-// A batch that repeats -- the same calls with the same arguments and host buffers, which is what a training loop over
-// fixed pinned buffers issues every step -- is captured into a CUDA graph the second time it is seen and replayed from
-// the third on: its ~60 copy / launch / event calls (0.3 ms of host time per step, more than the kernels) become one
-// cudaGraphLaunch, and the chunk pipeline can be cut finer than host launch overhead would allow.  See submit() below.
+// Opt-in (ctd_set_option("host_graphs", 1)): a batch that repeats -- the same calls with the same arguments and host
+// buffers, which is what a training loop over fixed pinned buffers issues every step -- is captured into a CUDA graph the
+// second time it is seen and replayed from the third on: its ~60 copy / launch / event calls become one cudaGraphLaunch
+// (0.09 -> 0.01 ms of host time per bench step; the step itself is bound by the bus and takes the same 1.2 ms against
+// a floor of 0.90 ms for its 79 MB with both directions busy: profiles/r02_e2e_chunks.json, r02_pcie_floor.json).  See submit().
 // There is no CPU compute path: without a CUDA device these calls fail with CTD_ERR_CUDA.
 #include <stdio.h>
 #include <stdlib.h>
@@ -94,6 +95,7 @@ struct Workspace {
   bool capturing = false;
   int cand = -1;
   uint64_t clock = 0;
+  uint64_t n_captured = 0, n_replayed = 0, n_bailed = 0;  // ctd_host_graph_stats
   std::vector<Call> calls;
   std::vector<Cached> cache;
 
@@ -127,6 +129,7 @@ struct Workspace {
   }
   // the expectation failed: issue what has been recorded the ordinary way and carry on in EAGER mode
   int bail(bool never_again) {
+    ++n_bailed;
     if (capturing) {
       cudaGraph_t g = nullptr;
       end_capture(&g);
@@ -334,9 +337,53 @@ int Workspace::submit(std::string sig, const std::vector<const void*>& host_ptrs
     }
   }
   if (mode != EAGER) {
-    const Cached& c = cache[cand];
-    bool ok = i < c.sigs.size() && c.sigs[i] == sig;
+    bool ok = i < cache[cand].sigs.size() && cache[cand].sigs[i] == sig;
     bool never_again = false;
+    if (!ok) {  // another cached batch that begins with the same calls (two kinds of step sharing their first calls)?
+      int alt = -1;
+      for (int k = 0; k < (int)cache.size(); ++k) {
+        const Cached& a = cache[k];
+        if (k == cand || a.no_graph || a.sigs.size() <= i || a.sigs[i] != sig) continue;
+        bool same = true;
+        for (size_t q = 0; q < i && same; ++q) same = a.sigs[q] == calls[q].sig;
+        if (same && (alt < 0 || (a.exec != nullptr) > (cache[alt].exec != nullptr) ||
+                     ((a.exec != nullptr) == (cache[alt].exec != nullptr) && a.stamp > cache[alt].stamp)))
+          alt = k;
+      }
+      if (alt >= 0) {
+        if (cache[alt].exec) {  // nothing of this batch has been issued yet (replay) or only into a capture (dropped)
+          if (capturing) {
+            cudaGraph_t g = nullptr;
+            end_capture(&g);
+            if (g) cudaGraphDestroy(g);
+          }
+          mode = REPLAY;
+        } else if (mode == REPLAY) {  // capture this kind of batch instead: its first calls go into the capture now
+          used = 0;
+          uploads.clear();
+          pending.clear();
+          h2d_bytes = h2d_saved = 0;
+          if (int rc = begin_capture()) {
+            capturing = false;
+            return rc;
+          }
+          mode = CAPTURE;
+          for (size_t q = 0; q < i; ++q)
+            if (int rc = calls[q].run()) {
+              cand = alt;
+              if (rc != CTD_RETRY_EAGER) {
+                bail(true);
+                return rc;
+              }
+              if (int rb = bail(true)) return rb;
+              calls.push_back({std::move(sig), nullptr});
+              return run();
+            }
+        }  // else: already capturing, and the captured prefix is this batch's too
+        cand = alt;
+        ok = true;
+      }
+    }
     if (ok && mode == CAPTURE && !pinned(host_ptrs)) {
       ok = false;
       never_again = true;  // pageable buffers: copies are staged by the driver, nothing to gain and not capturable
@@ -374,6 +421,7 @@ int Workspace::end_batch() {
       c.h2d = h2d_bytes;
       c.saved = h2d_saved;
       mode = REPLAY;
+      ++n_captured;
     } else {
       cudaGetLastError();
       c.exec = nullptr;
@@ -389,6 +437,7 @@ int Workspace::end_batch() {
     cudaError_t e = cudaGraphLaunch(c.exec, stream);
     if (e != cudaSuccess) rc = fail(CTD_ERR_CUDA, "ctd_host_end_batch: graph launch: %s", cudaGetErrorString(e));
     launched = true;
+    ++n_replayed;
   }
   if (rc == CTD_OK && !launched && g_host_graphs && !calls.empty()) {  // an ordinary batch: remember what it looked like
     int slot = -1;
@@ -773,6 +822,12 @@ CTD_API int ctd_host_end_batch(void) {
 CTD_API void ctd_host_batch_stats(uint64_t* h2d_bytes, uint64_t* h2d_bytes_saved) {
   if (h2d_bytes) *h2d_bytes = g_ws.h2d_bytes;
   if (h2d_bytes_saved) *h2d_bytes_saved = g_ws.h2d_saved;
+}
+
+CTD_API void ctd_host_graph_stats(uint64_t* captured, uint64_t* launched, uint64_t* bailed) {
+  if (captured) *captured = g_ws.n_captured;
+  if (launched) *launched = g_ws.n_replayed;
+  if (bailed) *bailed = g_ws.n_bailed;
 }
 
 CTD_API void ctd_host_release(void) {

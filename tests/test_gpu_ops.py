@@ -1000,6 +1000,92 @@ def test_host_api_deferred_batch_matches_synchronous_calls(tx):
         _lib.call("ctd_host_end_batch")  # no batch open
 
 
+def test_host_api_repeated_batch_is_replayed_as_a_graph(tx):
+    """A batch that repeats with pinned buffers: ordinary the first time, captured (and launched) the second, one graph
+    launch from the third on.  The inputs change between repetitions -- a replayed batch has to read the host buffers
+    again -- and every repetition is checked against the oracle.  Then the batch diverges in its third call (other loss
+    type): issued the ordinary way, same answers.  The same calls on pageable (numpy) buffers never become a graph."""
+    from connecting_the_dots_b200 import _lib, synth
+    B, H, W = 4, 40, 64
+    d = synth.make_batch(B, H, W)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = {k: pin(d[k]) for k in ("im", "es", "ta", "go")}
+    for k in ("lcn", "std", "gi1", "gi3"):
+        h[k] = torch.empty(B, 1, H, W).pin_memory()
+    h["sums"] = torch.zeros(4).pin_memory()
+    L = _lib.lib()
+    L.ctd_host_release()   # forget what earlier tests left in this thread's cache
+    _lib.set_option("host_graphs", 1)
+
+    def stats():
+        c, l, b = ctypes.c_uint64(0), ctypes.c_uint64(0), ctypes.c_uint64(0)
+        L.ctd_host_graph_stats(ctypes.byref(c), ctypes.byref(l), ctypes.byref(b))
+        return c.value, l.value, b.value
+
+    def batch(third_type=3):
+        _lib.call("ctd_host_begin_batch")
+        _lib.call("ctd_host_lcn_f32", P(h["im"]), P(h["lcn"]), P(h["std"]), B, H, W, 5, 0.05)
+        _lib.call("ctd_host_photometric_fwd_bwd_masked_f32", P(h["es"]), P(h["ta"]), P(h["go"]), P(h["std"]), None, P(h["gi1"]),
+                  ctypes.c_void_p(h["sums"].data_ptr()), B, 1, H, W, 9, 1, 0.5)
+        _lib.call("ctd_host_photometric_fwd_bwd_masked_f32", P(h["es"]), P(h["ta"]), P(h["go"]), P(h["std"]), None, P(h["gi3"]),
+                  ctypes.c_void_p(h["sums"].data_ptr() + 8), B, 1, H, W, 9, third_type, 0.5)
+        _lib.call("ctd_host_end_batch")
+
+    def check(third_type=3):
+        es, ta, go, im = (h[k].numpy() for k in ("es", "ta", "go", "im"))
+        lo, so = oracle.lcn(im, 5, 0.05)
+        assert_close(h["lcn"].numpy(), lo, what="lcn")
+        assert_close(h["std"].numpy(), so, what="std")
+        assert_close(h["gi1"].numpy(), oracle.photometric_loss_backward(es, ta, go, 9, 1, 0.5), what="sad gradient")
+        assert_close(h["gi3"].numpy(), oracle.photometric_loss_backward(es, ta, go, 9, third_type, 0.5), what="census gradient")
+        for j, ty in ((0, 1), (2, third_type)):
+            of = oracle.photometric_loss_forward(es, ta, 9, ty, 0.5)
+            want = np.array([(so.astype(np.float64) * of).sum(), so.astype(np.float64).sum()])
+            assert np.abs(h["sums"].numpy()[j:j + 2] - want).max() <= 1e-5 * np.abs(want).max()
+
+    base = stats()
+    rng = np.random.RandomState(3)
+    for rep in range(5):
+        for k in ("lcn", "std", "gi1", "gi3"):
+            h[k].fill_(7.0)   # poison the outputs
+        h["es"].copy_(torch.from_numpy(d["es"] + 0.1 * rep * rng.randn(B, 1, H, W).astype(np.float32)))
+        h["im"].copy_(torch.from_numpy(np.roll(d["im"], rep, axis=3)))
+        batch()
+        check()
+        c, l, b = (x - y for x, y in zip(stats(), base))
+        assert (c, l, b) == ((0, 0, 0), (1, 1, 0), (1, 2, 0), (1, 3, 0), (1, 4, 0))[rep], "repetition %d: %r" % (rep, (c, l, b))
+    batch(third_type=2)   # diverges at the third call: the first two are issued late, nothing is lost
+    check(third_type=2)
+    c, l, b = (x - y for x, y in zip(stats(), base))
+    assert (c, l, b) == (1, 4, 1)
+    batch()               # expected to be the other kind (most recent), recognised at the third call: the cached graph runs
+    check()
+    assert tuple(x - y for x, y in zip(stats(), base)) == (1, 5, 1)
+    batch(third_type=2)   # second sighting of the other kind: starts as a replay of the first, becomes a capture
+    check(third_type=2)
+    assert tuple(x - y for x, y in zip(stats(), base)) == (2, 6, 1)
+    for third in (2, 3, 3, 2):   # both kinds cached now, in any order
+        batch(third_type=third)
+        check(third_type=third)
+    assert tuple(x - y for x, y in zip(stats(), base)) == (2, 10, 1)
+    # pageable buffers: same calls three times, never captured
+    n = {k: v.numpy().copy() for k, v in h.items()}
+    Pn = lambda a, off=0: ctypes.c_void_p(a.ctypes.data + off)
+    before = stats()
+    for rep in range(3):
+        _lib.call("ctd_host_begin_batch")
+        _lib.call("ctd_host_lcn_f32", Pn(n["im"]), Pn(n["lcn"]), Pn(n["std"]), B, H, W, 5, 0.05)
+        _lib.call("ctd_host_photometric_fwd_bwd_masked_f32", Pn(n["es"]), Pn(n["ta"]), Pn(n["go"]), Pn(n["std"]), None, Pn(n["gi3"]),
+                  Pn(n["sums"]), B, 1, H, W, 9, 3, 0.5)
+        _lib.call("ctd_host_end_batch")
+        assert_close(n["gi3"], oracle.photometric_loss_backward(n["es"], n["ta"], n["go"], 9, 3, 0.5), what="pageable census gradient")
+    after = stats()
+    assert after[0] == before[0] and after[1] == before[1]
+    _lib.set_option("host_graphs", 0)
+    L.ctd_host_release()
+
+
 def test_host_api_batch_output_feeds_later_call(tx):
     """Inside a deferred batch an OUTPUT of one call that is an INPUT of a later one (LCN's lcn / std as the loss's target
     and mask; ProjNN's indices into CrossCheck) must not be re-uploaded from the stale host buffer: exact matches are
