@@ -865,9 +865,11 @@ static bool xcorr_sep_launch(const float* in0, const float* in1, float* out, int
   const int64_t uoff = ndchunks * XS_DT, ws0 = cdiv(W, 4) * 4, ws1 = uoff + ws0;
   const int64_t n0 = B * H * ws0, n1 = B * H * ws1;
   if (B * ndchunks > 65535 || cdiv(H, XH) > 65535 || cdiv(H, ST_H) > 65535 || n1 >= ((int64_t)1 << 31)) return false;
-  // hit list of the fix-up: room for 1/32 of the outputs (a few per thousand are expected), at most 4 M entries;
+  // hit list of the fix-up: room for 1/32 of the outputs, at most 16 M entries (128 MB of scratch).  Block 9 lists 0.2 % of
+  // the outputs on the bench frames, block 5 2.5 % (flat 5x5 windows of a 10 % dot pattern): with the former ceiling of 4 M
+  // entries block 5 overflowed at batch 8 and ran the fallback kernel, 986 instead of 752 us (xcorr_hitcap_bs5.py).
   // g_xcorr_hitcap >= 0 overrides (tests force the overflow path with 0)
-  const int64_t cap = (g_xcorr_hitcap >= 0 ? g_xcorr_hitcap : std::min<int64_t>(B * D * H * W / 32 + 1024, (int64_t)1 << 22)) / 2 * 2;  // even: the statistics planes behind it stay 16-byte aligned
+  const int64_t cap = (g_xcorr_hitcap >= 0 ? g_xcorr_hitcap : std::min<int64_t>(B * D * H * W / 32 + 1024, (int64_t)1 << 24)) / 2 * 2;  // even: the statistics planes behind it stay 16-byte aligned
   const size_t words = (size_t)(2 * cap) + (size_t)(3 * n0 + 3 * n1 + 4) + (size_t)(n0 + n1 + 3) / 4;
   float* scratch = static_cast<float*>(scratch_alloc(words * sizeof(float), st));
   if (!scratch) return false;
@@ -951,10 +953,22 @@ static int xcorrvol_impl(const T* in0, const T* in1, T* out, int64_t B, int64_t 
     const float* f0 = reinterpret_cast<const float*>(in0);
     const float* f1 = reinterpret_cast<const float*>(in1);
     float* fo = reinterpret_cast<float*>(out);
-    const bool done = bs == 9   ? xcorr_sep_launch<9>(f0, f1, fo, B, H, W, D, st)
-                      : bs == 7 ? xcorr_sep_launch<7>(f0, f1, fo, B, H, W, D, st)
-                      : bs == 5 ? xcorr_sep_launch<5>(f0, f1, fo, B, H, W, D, st)
-                                : xcorr_sep_launch<3>(f0, f1, fo, B, H, W, D, st);
+    // Images per launch: as many as keep the fix-up's hit list (1/32 of the outputs, 16 M entries at most) at its full
+    // relative size -- a large batch in one launch would overflow the list where many windows are flat (block 5) and fall
+    // back to the slow fix-up kernel.  12 images at 480 x 640 x 128: launches that size lose nothing to tails.
+    const int64_t per_image = D * H * W;
+    const int64_t nb_max = std::max<int64_t>(1, (((int64_t)1 << 24) - 1024) * 32 / std::max<int64_t>(per_image, 1));
+    bool done = true;
+    for (int64_t b0 = 0; b0 < B && done; b0 += nb_max) {
+      const int64_t nb = std::min(nb_max, B - b0);
+      const float *q0 = f0 + b0 * H * W, *q1 = f1 + b0 * H * W;
+      float* qo = fo + b0 * per_image;
+      done = bs == 9   ? xcorr_sep_launch<9>(q0, q1, qo, nb, H, W, D, st)
+             : bs == 7 ? xcorr_sep_launch<7>(q0, q1, qo, nb, H, W, D, st)
+             : bs == 5 ? xcorr_sep_launch<5>(q0, q1, qo, nb, H, W, D, st)
+                       : xcorr_sep_launch<3>(q0, q1, qo, nb, H, W, D, st);
+      if (!done && b0 > 0) return fail(CTD_ERR_CUDA, "xcorrvol: launch of images %lld.. failed", (long long)b0);
+    }
     if (done) return check_launch("xcorrvol(separable)");
   }
   if (sizeof(T) == 4 && C == 1 && !g_force_generic && (bs == 3 || bs == 5 || bs == 7 || bs == 9) && H <= 65535) {
