@@ -509,7 +509,7 @@ def run_b200_arm(args, rank, world, local_rank):
     # step: LCN (im -> lcn, std), then the two losses through the masked call, which returns what the reference's caller
     # uses (model/networks.py:376-377): the masked-mean scalars and d loss / d es.  The loss MAPS stay on the device (out =
     # NULL: nothing downstream reads them), and the mask is LCN's std of the same batch, served from its device buffer.
-    def e2e_step(k):
+    def e2e_issue(k, wait):
         h = host_sets[k % NSETS]
         _lib.call("ctd_host_begin_batch")
         _lib.call("ctd_host_lcn_f32", P(h["im"]), P(h["lcn"]), P(h["std"]), B, H, W, LCN_R, LCN_EPS)
@@ -517,20 +517,33 @@ def run_b200_arm(args, rank, world, local_rank):
                   ctypes.c_void_p(h["sums"].data_ptr()), B, 1, H, W, BS, 1, EPS)
         _lib.call("ctd_host_photometric_fwd_bwd_masked_f32", P(h["es"]), P(h["ta"]), P(h["go"]), P(h["std"]), None, P(h["gi_cs"]),
                   ctypes.c_void_p(h["sums"].data_ptr() + 8), B, 1, H, W, BS, 3, EPS)
-        _lib.call("ctd_host_end_batch")
+        _lib.call("ctd_host_end_batch" if wait else "ctd_host_end_batch_async")
 
+    def e2e_run(n_steps, two_deep):
+        """n_steps steps; two_deep: step k + 1 is issued before step k is waited for (its uploads cross the bus under step
+        k's downloads; the host buffer sets rotate, NSETS >= 3).  Every step's results are in host memory at the end."""
+        t0 = time.perf_counter()
+        for k in range(n_steps):
+            e2e_issue(k, wait=not two_deep)
+            if two_deep and k > 0:
+                _lib.call("ctd_host_wait_batch")  # step k - 1
+        if two_deep:
+            _lib.call("ctd_host_wait_batch")
+        return time.perf_counter() - t0
+
+    def e2e_measure(two_deep):
+        e2e_run(3 * NSETS, two_deep)
+        sync_all()
+        t = torch.tensor([e2e_run(e2e_steps, two_deep)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / e2e_steps * 1e3
+
+    assert NSETS >= 3
     e2e_steps = max(3, min(args.steps, 20))
-    for k in range(3 * NSETS):  # every host buffer set three times: its batch is a cached CUDA graph from the third visit on
-        e2e_step(k)
-    sync_all()
-    t0 = time.perf_counter()
-    for k in range(e2e_steps):
-        e2e_step(k)  # each call returns when its results are in host memory
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = float(t.item()) / e2e_steps * 1e3
+    e2e_sync_ms = e2e_measure(False)   # one step at a time: each returns when its results are in host memory
+    e2e_ms = e2e_measure(True)         # two steps in flight
+    e2e_issue(0, wait=True)            # a synchronous batch last: its byte counters are read below
     # bytes per step as the library counted them for the last batch: es / ta / grad_out are read by both loss calls and
     # uploaded once; the mask (LCN's std) never crosses the bus upwards
     copied, saved = ctypes.c_uint64(0), ctypes.c_uint64(0)
@@ -591,7 +604,9 @@ def run_b200_arm(args, rank, world, local_rank):
             "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": npx_global / (e2e_ms * 1e-3) / 1e6, "unit": "Mpix/s", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
-                    "api": "ctd_host_begin_batch; ctd_host_lcn_f32 + 2x ctd_host_photometric_fwd_bwd_masked_f32 (loss scalars + d loss / d es; loss maps stay on the device, mask = the batch's own LCN std); ctd_host_end_batch -- pinned host buffers; es / ta / grad_out uploaded once"},
+                    "one_step_at_a_time": {"ms_per_step": e2e_sync_ms, "value": npx_global / (e2e_sync_ms * 1e-3) / 1e6},
+                    "pipelining": "two steps in flight (ctd_host_end_batch_async / ctd_host_wait_batch): the uploads of step k + 1 run under the downloads of step k; every step's copies are inside the timed region",
+                    "api": "ctd_host_begin_batch; ctd_host_lcn_f32 + 2x ctd_host_photometric_fwd_bwd_masked_f32 (loss scalars + d loss / d es; loss maps stay on the device, mask = the batch's own LCN std); ctd_host_end_batch_async, then ctd_host_wait_batch for the step before -- pinned host buffers; es / ta / grad_out uploaded once"},
             "roofline": roofline, "ops": ops,
             "separate_calls": {"ms_per_step": sep_ms_per_step, "value": npx_global / (sep_ms_per_step * 1e-3) / 1e6, "steps": sep_steps,
                                "note": "same chain, forward and backward of both losses as separate calls (torch autograd path)"}}

@@ -45,6 +45,8 @@ SIGNATURES = {
     "ctd_host_lcn_f32": [_ptr, _ptr, _ptr, _i64, _i64, _i64, _int, _f32],
     "ctd_host_begin_batch": [],
     "ctd_host_end_batch": [],
+    "ctd_host_end_batch_async": [],
+    "ctd_host_wait_batch": [],
 }
 _RESTYPES = {
     "ctd_last_error": (ctypes.c_char_p, []),

@@ -47,6 +47,30 @@ struct Workspace {
   cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_run[MAX_CHUNKS] = {};
   bool deferred = false;  // inside ctd_host_begin_batch / ctd_host_end_batch
   size_t used = 0;        // bytes of the workspace owned by calls still in flight (deferred mode: no reuse)
+  // Two batches in flight (ctd_host_end_batch_async / ctd_host_wait_batch): the uploads of step k + 1 then run under the
+  // downloads of step k -- the same three streams, in issue order, nothing else is needed for the overlap.  Once a thread
+  // has used the asynchronous end, its batches alternate between the two halves of the workspace.
+  bool async_mode = false;
+  int slot = 0;                       // half of the open (or last) batch
+  size_t slot_off = 0;                // its first byte
+  bool busy[2] = {false, false};      // enqueued, not waited for
+  size_t lo[2] = {0, 0}, hi[2] = {0, 0};  // workspace bytes [lo, hi) a busy batch occupies
+  int last_ended = 0;
+  cudaEvent_t done_out[2] = {}, done_main[2] = {}, done_in[2] = {};
+
+  int wait_slot(int s) {
+    if (!busy[s]) return CTD_OK;
+    busy[s] = false;
+    cudaError_t e1 = cudaEventSynchronize(done_out[s]), e2 = cudaEventSynchronize(done_main[s]), e3 = cudaEventSynchronize(done_in[s]);
+    const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    if (e != cudaSuccess) return fail(CTD_ERR_CUDA, "host api: waiting for a batch: %s", cudaGetErrorString(e));
+    return CTD_OK;
+  }
+  int wait_batches() {  // both, oldest first
+    const int first = last_ended ^ 1;
+    const int r1 = wait_slot(first), r2 = wait_slot(first ^ 1);
+    return r1 ? r1 : r2;
+  }
   // Uploads of the open batch: an input (same host address, same size) that several calls of a batch read -- the
   // image pair of the sad and the census loss, the gradient weights -- crosses the bus once.  Later calls find the
   // device copy of the earlier one; their kernels are enqueued on the same compute stream after the kernel that
@@ -90,7 +114,7 @@ struct Workspace {
     bool no_graph = false;  // broke a capture once: always issued the ordinary way
     uint64_t h2d = 0, saved = 0, stamp = 0;
   };
-  static constexpr int MAX_CACHED = 8;
+  static constexpr int MAX_CACHED = 16;
   Mode mode = EAGER;
   bool capturing = false;
   int cand = -1;
@@ -161,7 +185,7 @@ struct Workspace {
     return true;
   }
   int submit(std::string sig, const std::vector<const void*>& host_ptrs, std::function<int()> run);
-  int end_batch();
+  int end_batch(bool wait);
 
   void note_download(const void* host, size_t bytes, char* dev) {
     if (deferred && bytes) pending.push_back({host, bytes, dev});
@@ -204,8 +228,10 @@ struct Workspace {
 
   // workspace of one call: `bytes` fresh bytes behind everything still in flight
   int carve(size_t bytes, char** out) {
-    if (int rc = ensure(used + bytes)) return rc;
-    *out = base + used;
+    const size_t need = (used + bytes + 255) & ~size_t(255);
+    if (int rc = ensure(async_mode ? 2 * need : need)) return rc;  // a reallocation waits for everything and resets `used`
+    slot_off = async_mode && slot ? (cap / 2) & ~size_t(255) : 0;
+    *out = base + slot_off + used;
     return CTD_OK;
   }
   // end of a call: wait for the results unless a batch is open
@@ -236,12 +262,18 @@ struct Workspace {
         CTD_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
         CTD_CUDA(cudaEventCreateWithFlags(&ev_run[i], cudaEventDisableTiming));
       }
+      for (int i = 0; i < 2; ++i) {
+        CTD_CUDA(cudaEventCreateWithFlags(&done_out[i], cudaEventDisableTiming));
+        CTD_CUDA(cudaEventCreateWithFlags(&done_main[i], cudaEventDisableTiming));
+        CTD_CUDA(cudaEventCreateWithFlags(&done_in[i], cudaEventDisableTiming));
+      }
     }
     if (bytes > cap) {
       if (capturing) return CTD_RETRY_EAGER;  // cudaMalloc / cudaDeviceSynchronize cannot be captured
       drop_graphs();                          // they hold addresses of the old workspace
       if (base) {
-        CTD_CUDA(cudaDeviceSynchronize());  // also completes every call still in flight: their results are out
+        CTD_CUDA(cudaDeviceSynchronize());  // also completes every call and batch still in flight: their results are out
+        busy[0] = busy[1] = false;
         cudaFree(base);
         base = nullptr;
         cap = 0;
@@ -271,6 +303,14 @@ struct Workspace {
         cudaEventDestroy(ev_in[i]);
         cudaEventDestroy(ev_run[i]);
       }
+      for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(done_out[i]);
+        cudaEventDestroy(done_main[i]);
+        cudaEventDestroy(done_in[i]);
+      }
+      busy[0] = busy[1] = false;
+      async_mode = false;
+      slot = 0;
       s_in = s_out = nullptr;
     }
     if (base) cudaFree(base);
@@ -317,7 +357,10 @@ struct Sig {
 };
 
 int Workspace::submit(std::string sig, const std::vector<const void*>& host_ptrs, std::function<int()> run) {
+  if (!deferred && (busy[0] || busy[1]))  // a synchronous call takes the workspace from its start: nothing may be in flight there
+    if (int rc = wait_batches()) return rc;
   if (!deferred || !g_host_graphs) return run();
+  sig.push_back((char)(slot + (async_mode ? 2 : 0)));  // a graph holds the addresses of the workspace half it was captured in
   const size_t i = calls.size();
   if (i == 0) {  // which cached batch does this one start like?
     cand = -1;
@@ -406,7 +449,7 @@ int Workspace::submit(std::string sig, const std::vector<const void*>& host_ptrs
   return run();
 }
 
-int Workspace::end_batch() {
+int Workspace::end_batch(bool wait) {
   int rc = CTD_OK;
   bool launched = false;
   static const bool dbg = getenv("CTD_HOST_DEBUG") != nullptr;
@@ -463,16 +506,28 @@ int Workspace::end_batch() {
     cache[slot].stamp = ++clock;
   }
   deferred = false;
+  if (stream && !wait && rc == CTD_OK) {  // leave it in flight: three events mark its end on the three streams
+    async_mode = true;
+    lo[slot] = slot_off;
+    hi[slot] = slot_off + used;
+    cudaError_t e1 = cudaEventRecord(done_out[slot], s_out), e2 = cudaEventRecord(done_main[slot], stream),
+                e3 = cudaEventRecord(done_in[slot], s_in);
+    const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
+    if (e != cudaSuccess) rc = fail(CTD_ERR_CUDA, "ctd_host_end_batch_async: %s", cudaGetErrorString(e));
+    busy[slot] = rc == CTD_OK;
+    last_ended = slot;
+  }
   used = 0;
   uploads.clear();
   pending.clear();
   calls.clear();
   mode = EAGER;
   cand = -1;
-  if (stream) {
+  if (stream && (wait || rc != CTD_OK)) {  // the streams drain in order: this also completes an earlier batch still in flight
     cudaError_t e1 = cudaStreamSynchronize(s_out), e2 = cudaStreamSynchronize(stream), e3 = cudaStreamSynchronize(s_in);
     const cudaError_t e = e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3);
     if (e != cudaSuccess && rc == CTD_OK) rc = fail(CTD_ERR_CUDA, "ctd_host_end_batch: %s", cudaGetErrorString(e));
+    busy[0] = busy[1] = false;
   }
   return rc;
 }
@@ -803,6 +858,15 @@ CTD_API int ctd_host_lcn_f32(const float* x, float* lcn, float* sd, int64_t N, i
 
 CTD_API int ctd_host_begin_batch(void) {
   CTD_REQUIRE(!g_ws.deferred, "ctd_host_begin_batch: a batch is already open on this thread");
+  if (g_ws.async_mode) {  // the other half of the workspace; at most two batches are in flight
+    g_ws.slot ^= 1;
+    if (int rc = g_ws.wait_slot(g_ws.slot)) return rc;
+    const int other = g_ws.slot ^ 1;
+    const size_t half = (g_ws.cap / 2) & ~size_t(255);
+    const size_t my_lo = g_ws.slot ? half : 0, my_hi = g_ws.slot ? g_ws.cap : half;
+    if (g_ws.busy[other] && g_ws.lo[other] < my_hi && my_lo < g_ws.hi[other])  // (the first asynchronous batch had the whole workspace)
+      if (int rc = g_ws.wait_slot(other)) return rc;
+  }
   g_ws.deferred = true;
   g_ws.used = 0;
   g_ws.uploads.clear();
@@ -816,7 +880,18 @@ CTD_API int ctd_host_begin_batch(void) {
 
 CTD_API int ctd_host_end_batch(void) {
   CTD_REQUIRE(g_ws.deferred, "ctd_host_end_batch: no batch is open on this thread");
-  return g_ws.end_batch();
+  return g_ws.end_batch(true);
+}
+
+CTD_API int ctd_host_end_batch_async(void) {
+  CTD_REQUIRE(g_ws.deferred, "ctd_host_end_batch_async: no batch is open on this thread");
+  return g_ws.end_batch(false);
+}
+
+CTD_API int ctd_host_wait_batch(void) {
+  CTD_REQUIRE(!g_ws.deferred, "ctd_host_wait_batch: a batch is open on this thread");
+  const int oldest = g_ws.busy[g_ws.last_ended ^ 1] ? g_ws.last_ended ^ 1 : g_ws.last_ended;
+  return g_ws.wait_slot(oldest);
 }
 
 CTD_API void ctd_host_batch_stats(uint64_t* h2d_bytes, uint64_t* h2d_bytes_saved) {

@@ -206,6 +206,15 @@ int ctd_host_lcn_f32(const float* x, float* lcn, float* std, int64_t N, int64_t 
  * the downloads, then uploads what the host holds. */
 int ctd_host_begin_batch(void);
 int ctd_host_end_batch(void);
+/* Two batches in flight: ctd_host_end_batch_async() returns once the batch is enqueued, ctd_host_wait_batch() waits for the
+ * OLDEST batch not waited for yet (CTD_OK at once if there is none); a thread may have two such batches outstanding -- the
+ * third ctd_host_begin_batch waits for the oldest itself.  With steps issued as begin / calls / end_async / wait (for
+ * the previous step), the uploads of step k + 1 cross the bus under the downloads of step k.  Results of a batch are in
+ * host memory after its wait; until then its host inputs must not change, its host outputs must not be read -- or be
+ * passed as inputs to a later batch.  ctd_host_end_batch() (and any ctd_host_* call outside a batch) waits for
+ * everything outstanding. */
+int ctd_host_end_batch_async(void);
+int ctd_host_wait_batch(void);
 /* host-to-device bytes the calling thread's current (or last) batch copied, and bytes it did not have to copy again */
 void ctd_host_batch_stats(uint64_t* h2d_bytes, uint64_t* h2d_bytes_saved);
 /* Repeated batches (opt-in: ctd_set_option("host_graphs", 1)): a batch whose calls (entry points, arguments, host

@@ -1086,6 +1086,83 @@ def test_host_api_repeated_batch_is_replayed_as_a_graph(tx):
     L.ctd_host_release()
 
 
+def test_host_api_two_batches_in_flight(tx):
+    """ctd_host_end_batch_async / ctd_host_wait_batch: steps issued two deep over three rotating sets of pinned buffers (the
+    uploads of step k + 1 cross the bus under the downloads of step k) give the bytes of the same steps issued one at a
+    time -- with and without graph replay, with a larger batch in the middle (the workspace has to grow while a batch is in
+    flight) and a synchronous call at the end (waits for what is outstanding)."""
+    from connecting_the_dots_b200 import _lib, synth
+    H, W = 40, 64
+    L = _lib.lib()
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    sizes = [4, 4, 4, 4, 7, 4, 4, 4, 4, 4]   # images per step
+    rng = np.random.RandomState(8)
+    steps = []
+    for k, B in enumerate(sizes):
+        d = synth.make_batch(B, H, W)
+        steps.append({"im": np.roll(d["im"], k, axis=3), "es": d["es"] + 0.05 * k * rng.randn(B, 1, H, W).astype(np.float32),
+                      "ta": d["ta"], "go": d["go"]})
+
+    def buffers(B):
+        h = {k: torch.empty(B, 1, H, W).pin_memory() for k in ("im", "es", "ta", "go", "lcn", "std", "gi")}
+        h["sums"] = torch.zeros(2).pin_memory()
+        return h
+
+    def issue(h, B):
+        _lib.call("ctd_host_lcn_f32", P(h["im"]), P(h["lcn"]), P(h["std"]), B, H, W, 5, 0.05)
+        _lib.call("ctd_host_photometric_fwd_bwd_masked_f32", P(h["es"]), P(h["ta"]), P(h["go"]), P(h["std"]), None, P(h["gi"]),
+                  P(h["sums"]), B, 1, H, W, 9, 3, 0.5)
+
+    def fill(h, st):
+        for k in ("im", "es", "ta", "go"):
+            h[k].copy_(torch.from_numpy(st[k]))
+        for k in ("lcn", "std", "gi"):
+            h[k].fill_(7.0)
+
+    def result(h):
+        return tuple(h[k].numpy().copy() for k in ("lcn", "std", "gi", "sums"))
+
+    for graphs in (0, 1):
+        L.ctd_host_release()
+        _lib.set_option("host_graphs", graphs)
+        try:
+            want = []
+            for st, B in zip(steps, sizes):   # one at a time
+                h = buffers(B)
+                fill(h, st)
+                _lib.call("ctd_host_begin_batch")
+                issue(h, B)
+                _lib.call("ctd_host_end_batch")
+                want.append(result(h))
+            sets = {}
+            got, inflight = [], []
+            for k, (st, B) in enumerate(zip(steps, sizes)):   # two deep
+                h = sets.setdefault((k % 3, B), buffers(B))
+                fill(h, st)
+                _lib.call("ctd_host_begin_batch")
+                issue(h, B)
+                _lib.call("ctd_host_end_batch_async")
+                inflight.append(h)
+                if len(inflight) == 2:
+                    _lib.call("ctd_host_wait_batch")
+                    got.append(result(inflight.pop(0)))
+            # a synchronous call now has to wait for the batch still in flight before it reuses the workspace
+            l2, s2 = np.empty((1, 1, H, W), np.float32), np.empty((1, 1, H, W), np.float32)
+            _lib.call("ctd_host_lcn_f32", ctypes.c_void_p(steps[0]["im"][:1].ctypes.data), ctypes.c_void_p(l2.ctypes.data),
+                      ctypes.c_void_p(s2.ctypes.data), 1, H, W, 5, 0.05)
+            got.append(result(inflight.pop(0)))
+            _lib.call("ctd_host_wait_batch")   # nothing outstanding: returns at once
+            assert len(got) == len(want)
+            for k, (a, b) in enumerate(zip(got, want)):
+                for x, y, name in zip(a, b, ("lcn", "std", "gi", "sums")):
+                    assert np.array_equal(x, y), "step %d: %s differs (graphs %d)" % (k, name, graphs)
+            assert np.array_equal(l2, want[0][0][:1])
+        finally:
+            _lib.set_option("host_graphs", 0)
+            L.ctd_host_release()
+
+
 def test_host_api_batch_output_feeds_later_call(tx):
     """Inside a deferred batch an OUTPUT of one call that is an INPUT of a later one (LCN's lcn / std as the loss's target
     and mask; ProjNN's indices into CrossCheck) must not be re-uploaded from the stale host buffer: exact matches are
