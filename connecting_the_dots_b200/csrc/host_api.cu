@@ -8,7 +8,9 @@
 // with pinned buffers both PCIe directions stay busy and the kernels hide behind the copies.
 // Between ctd_host_begin_batch() and ctd_host_end_batch() the calls only enqueue: consecutive ops then overlap as well
 // (the upload of the next call runs under the download of the previous one), results are in host memory when
-// ctd_host_end_batch() returns.
+// ctd_host_end_batch() returns.  ctd_host_end_batch_async() leaves the batch in flight and ctd_host_wait_batch() waits for the
+// oldest one: with two batches outstanding the uploads of step k + 1 run under the downloads of step k (bench step: 1.20 ->
+// 0.94 ms, bus floor 0.90 ms).
 // Opt-in (ctd_set_option("host_graphs", 1)): a batch that repeats -- the same calls with the same arguments and host
 // buffers, which is what a training loop over fixed pinned buffers issues every step -- is captured into a CUDA graph the
 // second time it is seen and replayed from the third on: its ~60 copy / launch / event calls become one cudaGraphLaunch
