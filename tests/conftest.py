@@ -37,8 +37,14 @@ def ref_ext():
 @pytest.fixture(scope="session")
 def tx():
     """The drop-in torchext package, with the kernel library built and loaded (fails loudly if not)."""
+    import os
     import connecting_the_dots_b200 as ctd
     ctd._lib.lib()
+    # CTD_TEST_OPTIONS="census_stream=1,host_graphs=1": run the whole suite with opt-in paths switched on (tests that set
+    # an option themselves put the library default back afterwards)
+    for item in filter(None, os.environ.get("CTD_TEST_OPTIONS", "").split(",")):
+        name, value = item.split("=")
+        ctd._lib.set_option(name.strip(), int(value))
     return ctd.torchext
 
 
