@@ -201,26 +201,50 @@ proj_nn_fixed_kernel(const T* __restrict__ xyz0, const T* __restrict__ xyz1, con
   const int ub = u0 < -(1 << 30) ? -(1 << 30) : u0 - half, vb = v0 < -(1 << 30) ? -(1 << 30) : v0 - half;
   T best_d = (T)1e9;
   int best = -1;
+  if (ub >= 0 && vb >= 0 && ub + PS <= W && vb + PS <= H) {
+    // The whole patch lies inside the image (all but the queries that project next to the border): no per-candidate
+    // tests, one row pointer per patch row with compile-time offsets behind it, and the winner remembered by its
+    // position in the scan (a constant per candidate) instead of its pixel index.  Same scan order, same strict <.
+    const T* row = img1 + (unsigned)(vb * W + ub) * 3u;
+    int bestc = -1;
 #pragma unroll
-  for (int pv = 0; pv < PS; ++pv) {
-    const int v1 = vb + pv;
-    const bool vok = v1 >= 0 && v1 < H;
-    T qx[PS], qy[PS], qz[PS];
+    for (int pv = 0; pv < PS; ++pv) {
+      T q[3 * PS];
 #pragma unroll
-    for (int pu = 0; pu < PS; ++pu) {
-      const int u1 = ub + pu;
-      const bool ok = vok && u1 >= 0 && u1 < W;
-      const T* q = img1 + (unsigned)(ok ? v1 * W + u1 : 0) * 3u;
-      qx[pu] = ok ? __ldg(q) : (T)INFINITY;
-      qy[pu] = ok ? __ldg(q + 1) : (T)0;
-      qz[pu] = ok ? __ldg(q + 2) : (T)0;
+      for (int j = 0; j < 3 * PS; ++j) q[j] = __ldg(row + j);
+#pragma unroll
+      for (int pu = 0; pu < PS; ++pu) {
+        const T dd = (x - q[3 * pu]) * (x - q[3 * pu]) + (y - q[3 * pu + 1]) * (y - q[3 * pu + 1]) + (z - q[3 * pu + 2]) * (z - q[3 * pu + 2]);
+        if (dd < best_d) {
+          best_d = dd;
+          bestc = pv * PS + pu;
+        }
+      }
+      row += (unsigned)W * 3u;
     }
+    if (bestc >= 0) best = (vb + bestc / PS) * W + (ub + bestc % PS);
+  } else {
 #pragma unroll
-    for (int pu = 0; pu < PS; ++pu) {
-      const T dd = (x - qx[pu]) * (x - qx[pu]) + (y - qy[pu]) * (y - qy[pu]) + (z - qz[pu]) * (z - qz[pu]);
-      if (dd < best_d) {
-        best_d = dd;
-        best = (vb + pv) * W + (ub + pu);
+    for (int pv = 0; pv < PS; ++pv) {
+      const int v1 = vb + pv;
+      const bool vok = v1 >= 0 && v1 < H;
+      T qx[PS], qy[PS], qz[PS];
+#pragma unroll
+      for (int pu = 0; pu < PS; ++pu) {
+        const int u1 = ub + pu;
+        const bool ok = vok && u1 >= 0 && u1 < W;
+        const T* q = img1 + (unsigned)(ok ? v1 * W + u1 : 0) * 3u;
+        qx[pu] = ok ? __ldg(q) : (T)INFINITY;
+        qy[pu] = ok ? __ldg(q + 1) : (T)0;
+        qz[pu] = ok ? __ldg(q + 2) : (T)0;
+      }
+#pragma unroll
+      for (int pu = 0; pu < PS; ++pu) {
+        const T dd = (x - qx[pu]) * (x - qx[pu]) + (y - qy[pu]) * (y - qy[pu]) + (z - qz[pu]) * (z - qz[pu]);
+        if (dd < best_d) {
+          best_d = dd;
+          best = (vb + pv) * W + (ub + pu);
+        }
       }
     }
   }
